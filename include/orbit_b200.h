@@ -1,0 +1,216 @@
+/* liborbit_b200 -- C ABI of the B200-native orbit-tracking hot path.
+ *
+ * The reference (s-balu/nbody-orbit-analysis, package `orbitanalysis` v0.1) is
+ * pure Python/numpy and has no FFI of its own: its "operator interface" for
+ * this path is the set of per-region numpy functions called from
+ * `track_orbits.py:147-217`.  Each entry point below states which of those it
+ * replaces (file:line in the reference tree) -- a maintainer binds them with
+ * ctypes exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types;
+ *   - every `const void* / void*` array argument is a DEVICE pointer unless the
+ *     name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream);
+ *   - all functions return 0 on success or a negative OA_ERR_* code, never
+ *     throw, and never synchronise unless documented; the message of the last
+ *     failure on the calling thread is available from `oa_last_error()`;
+ *   - nothing here falls back to the CPU: without a CUDA device every compute
+ *     entry point returns OA_ERR_CUDA.
+ */
+#ifndef ORBIT_B200_H
+#define ORBIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OA_OK 0
+#define OA_ERR_ARG (-1)
+#define OA_ERR_CUDA (-2)
+#define OA_ERR_UNSUPPORTED (-3)
+
+#define OA_F32 0
+#define OA_F64 1
+
+#define OA_MODE_PERICENTRIC 0 /* v_r: - -> + (track_orbits.py:311-312) */
+#define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
+
+/* ABI version; bumped whenever a struct below changes. */
+#define OA_ABI_VERSION 3
+
+int oa_abi_version(void);
+const char* oa_last_error(void);
+
+/* Device facts used by the host to size grids/buffers: SM count, compute
+ * capability, L2 bytes.  Fails (OA_ERR_CUDA) when no device is visible. */
+int oa_device_info(int* sm_count, int* cc_major, int* cc_minor,
+                   int64_t* l2_bytes, int64_t* hbm_bytes);
+
+/* ---------------------------------------------------------------------------
+ * Region table: one row per region block of the CURRENT snapshot.
+ * Replaces the per-halo Python arguments of `track(j)` / `region_frame`
+ * (track_orbits.py:147-155, 247): region centre, bulk velocity and which block
+ * of the previous snapshot holds the same halo (track_orbits.py:162-165).
+ * ------------------------------------------------------------------------- */
+typedef struct oa_region {
+    double centre[3];   /* regions()[0][j]                                   */
+    double bulk[3];     /* regions()[2][j], or written by oa_bulk_velocity   */
+    int64_t prev_begin; /* first particle of the halo's previous block, or -1 */
+    int64_t prev_count; /* its length (0 when there is no previous block)    */
+} oa_region;            /* 64 bytes */
+
+/* Bytes of one carried-state record (32 for an OA_F32 frame, 64 for OA_F64). */
+size_t oa_record_bytes(int frame_dtype);
+/* Number of uint32 slots of the ID hash table for n region-particles. */
+int64_t oa_table_slots(int64_t n);
+/* Bits needed to store a block-local particle index given the largest block. */
+int oa_index_bits(int64_t max_block_len);
+
+/* ---------------------------------------------------------------------------
+ * (b0) Derived bulk velocity of every region block.
+ * Replaces `np.mean(vel[sl], axis=0)` / the mass-weighted sum of
+ * track_orbits.py:267-284 and track_orbits_onthefly.py:96-110.
+ * Sums are accumulated in float64 in a fixed (deterministic) order; the mean is
+ * rounded to float32 when `round_f32` is set (numpy returns the input dtype).
+ * Writes regions[j].bulk and, if not NULL, bulk_out[j*3..] (float64; NaN for an
+ * empty block, like numpy's mean of an empty slice).
+ * workspace: oa_bulk_workspace_bytes(n, n_regions) bytes.
+ * ------------------------------------------------------------------------- */
+size_t oa_bulk_workspace_bytes(int64_t n, int n_regions);
+int oa_bulk_velocity(const void* vel, int vel_dtype, const void* mass,
+                     int mass_dtype, const int64_t* cur_off, int n_regions,
+                     int64_t n, int round_f32, oa_region* regions,
+                     double* bulk_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a)+(b) Fused per-snapshot tracking kernel.
+ *
+ * For every particle of the current snapshot, in block order, ONE kernel:
+ *   1. halo frame: x' = wrap(x - centre), r, rhat, v_r          region_frame
+ *      (track_orbits.py:247-290, utils.py:24-33; on-the-fly variant
+ *      track_orbits_onthefly.py:71-120 when `onthefly` is set);
+ *   2. finds the particle's record in the same halo's previous block by probing
+ *      that block's ID hash table                     compare_radial_velocities
+ *      (track_orbits.py:300-309 = setdiff1d/in1d/delete + utils.myin1d :4-11);
+ *   3. sign-flip test, angle change arccos(rhat_prev . rhat), float16 angle
+ *      accumulator update/reset     (track_orbits.py:311-325, calc_angles :330-351);
+ *   4. writes the new 32/64-byte record, the event mark of the PREVIOUS
+ *      particle (so that events can be emitted in previous-block order,
+ *      track_orbits.py:315-316) and inserts its own ID into the current
+ *      snapshot's hash table for the next call.
+ *
+ * dtypes: `data_dtype` is the dtype of pos/vel; `frame_dtype` the dtype numpy
+ * would give the halo-frame coordinates (result_type(pos, centre); on-the-fly:
+ * the dtype of pos); `centre_f32` / `bulk_f32` say whether the catalogue rows
+ * were float32 (they decide where numpy rounds to float32).  v_r is float64
+ * (track_orbits.py:275-288 under numpy>=2) unless `onthefly`.
+ * ------------------------------------------------------------------------- */
+typedef struct oa_track_args {
+    /* current snapshot (inputs) */
+    const void* pos;        /* (n_cur,3) data_dtype                           */
+    const void* vel;        /* (n_cur,3) data_dtype                           */
+    const int64_t* ids;     /* (n_cur,)                                       */
+    int64_t n_cur;
+    const int64_t* cur_off; /* (n_regions+1,) block starts + n_cur            */
+    const oa_region* regions; /* (n_regions,)                                 */
+    int32_t n_regions;
+    int32_t data_dtype;     /* OA_F32 / OA_F64                                */
+    int32_t frame_dtype;    /* OA_F32 / OA_F64                                */
+    int32_t centre_f32;
+    int32_t bulk_f32;
+    int32_t periodic;       /* 'box_size' in snapshot                         */
+    int32_t onthefly;       /* on-the-fly arithmetic + per-match outputs      */
+    int32_t mode;           /* OA_MODE_*                                      */
+    double box[3];
+    double hubble;          /* H(z), utils.py:36-39 (host scalar)             */
+    double one_plus_z;
+    /* previous generation (read) */
+    const void* rec_prev;   /* (n_prev,) records, NULL if none                */
+    const uint32_t* tab_prev; /* oa_table_slots(n_prev) slots                 */
+    int64_t n_prev;
+    int32_t prev_index_bits;
+    int32_t cur_index_bits;
+    uint16_t* mark_prev;    /* (n_prev,) event marks, updated                 */
+    /* current generation (written) */
+    void* rec_cur;          /* (n_cur,) records                               */
+    uint32_t* tab_cur;      /* oa_table_slots(n_cur) slots (filled here)      */
+    uint16_t* mark_cur;     /* (n_cur,) initialised to "no event"             */
+    /* optional per-particle outputs, NULL to skip */
+    void* out_rhat;         /* (n_cur,3) frame_dtype                          */
+    void* out_vr;           /* (n_cur,) float64 (float32 if onthefly && F32)  */
+    void* out_r;            /* (n_cur,) frame_dtype                           */
+    uint16_t* out_angle;    /* (n_cur,) float16 bits: checkpoint 'angles'     */
+    int64_t* out_match;     /* (n_cur,) previous index or -1                  */
+    void* dangle_prev;      /* (n_prev,) frame_dtype, on-the-fly 'angles'     */
+} oa_track_args;
+
+int oa_track_fused(const oa_track_args* args, void* stream);
+/* sizeof(oa_track_args) as compiled -- lets a binding verify its struct mirror. */
+size_t oa_track_args_size(void);
+
+/* ---------------------------------------------------------------------------
+ * Ordered selection ("np.argwhere(cond).flatten()", track_orbits.py:315 and
+ * the result assembly :199-217): positions i (ascending) of marks that satisfy
+ * a predicate, plus per-segment offsets.
+ *   OA_SEL_NE : marks[i] != value      OA_SEL_EQ : marks[i] == value
+ * Two steps so that the host can size the output exactly:
+ *   oa_select_count  -> writes tile counts to workspace and the total to
+ *                       *total_dev (device int64);
+ *   oa_select_gather -> writes the selected positions.
+ * ------------------------------------------------------------------------- */
+#define OA_SEL_NE 0
+#define OA_SEL_EQ 1
+size_t oa_select_workspace_bytes(int64_t n);
+int oa_select_count(const uint16_t* marks, int64_t n, int op, uint16_t value,
+                    void* workspace, size_t workspace_bytes,
+                    int64_t* total_dev, void* stream);
+int oa_select_gather(const uint16_t* marks, int64_t n, int op, uint16_t value,
+                     const void* workspace, int64_t* sel_out, void* stream);
+/* offsets_out[k] = number of selected positions < seg_begin[k]   (k < n_seg);
+ * the caller appends the total.  np.cumsum([0]+lens), track_orbits.py:214. */
+int oa_segment_offsets(const int64_t* sel, int64_t n_sel,
+                       const int64_t* seg_begin, int n_seg,
+                       int64_t* offsets_out, void* stream);
+
+/* Gathers driven by a selection. */
+int oa_gather_record_ids(const void* rec, int frame_dtype, const int64_t* sel,
+                         int64_t n_sel, int64_t* ids_out, void* stream);
+int oa_gather_u16(const uint16_t* src, const int64_t* sel, int64_t n_sel,
+                  uint16_t* out, void* stream);
+int oa_gather_i64(const int64_t* src, const int64_t* sel, int64_t n_sel,
+                  int64_t* out, void* stream);
+int oa_gather_f(const void* src, int dtype, const int64_t* sel, int64_t n_sel,
+                void* out, void* stream);
+/* marks[i] = (match[i] < 0) ? 1 : 0  -- "entered" predicate (onthefly :168) */
+int oa_mark_unmatched(const int64_t* match, int64_t n, uint16_t* marks,
+                      void* stream);
+int oa_fill_u16(uint16_t* dst, int64_t n, uint16_t value, void* stream);
+/* Overwrite the float16 angle accumulator of n records: resume from the
+ * reference's '.checkpoint' dataset (track_orbits.py:229-232). */
+int oa_set_record_angles(void* rec, int frame_dtype, const uint16_t* angles,
+                         int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * LSD radix sort of (uint64 key, uint64 value) pairs on bits
+ * [begin_bit, end_bit), stable.  Replaces the argsort/unique calls of
+ * utils.py:10, track_orbits_onthefly.py:145,168 (sorted entered/departed
+ * lists), progenitors.py:52,82,108 and postprocessing.py:135.
+ * Result is left in keys_out/vals_out.  workspace: oa_sort_workspace_bytes(n).
+ * ------------------------------------------------------------------------- */
+size_t oa_sort_workspace_bytes(int64_t n);
+int oa_sort_pairs_u64(const uint64_t* keys_in, const uint64_t* vals_in,
+                      uint64_t* keys_out, uint64_t* vals_out, int64_t n,
+                      int begin_bit, int end_bit, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
+int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBIT_B200_H */

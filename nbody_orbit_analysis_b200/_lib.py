@@ -1,0 +1,149 @@
+"""ctypes binding of ``liborbit_b200.so`` (the C ABI in ``include/orbit_b200.h``).
+
+There is no CPU fallback: if the library cannot be loaded this module raises,
+and every compute entry point returns an error without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+OA_F32, OA_F64 = 0, 1
+OA_MODE = {'pericentric': 0, 'apocentric': 1}
+OA_SEL_NE, OA_SEL_EQ = 0, 1
+OA_NO_EVENT = 0x8000
+ABI_VERSION = 3
+
+
+class OrbitB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path) or _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:    # noqa: BLE001
+            if not os.path.exists(path):
+                raise ImportError(
+                    "liborbit_b200.so is missing and could not be built (%s). "
+                    "This package has no CPU fallback: build it with "
+                    "`python -m nbody_orbit_analysis_b200._build`." % (exc,))
+    lib = C.CDLL(path)
+    lib.oa_abi_version.restype = C.c_int
+    if lib.oa_abi_version() != ABI_VERSION:
+        raise ImportError(
+            "liborbit_b200.so has ABI %d, the Python host expects %d; rebuild "
+            "with `python -m nbody_orbit_analysis_b200._build --force`"
+            % (lib.oa_abi_version(), ABI_VERSION))
+    return lib
+
+
+lib = _load()
+LIB_PATH = _build.LIB
+
+# numpy view of `oa_region` (64 bytes)
+REGION_DTYPE = np.dtype([
+    ('centre', np.float64, (3,)), ('bulk', np.float64, (3,)),
+    ('prev_begin', np.int64), ('prev_count', np.int64)])
+assert REGION_DTYPE.itemsize == 64
+
+_vp, _i64, _i32, _sz, _u16 = (C.c_void_p, C.c_int64, C.c_int32, C.c_size_t,
+                              C.c_uint16)
+
+
+class TrackArgs(C.Structure):
+    """``oa_track_args`` -- keep in sync with include/orbit_b200.h."""
+    _fields_ = [
+        ('pos', _vp), ('vel', _vp), ('ids', _vp), ('n_cur', _i64),
+        ('cur_off', _vp), ('regions', _vp),
+        ('n_regions', _i32), ('data_dtype', _i32), ('frame_dtype', _i32),
+        ('centre_f32', _i32), ('bulk_f32', _i32), ('periodic', _i32),
+        ('onthefly', _i32), ('mode', _i32),
+        ('box', C.c_double * 3), ('hubble', C.c_double),
+        ('one_plus_z', C.c_double),
+        ('rec_prev', _vp), ('tab_prev', _vp), ('n_prev', _i64),
+        ('prev_index_bits', _i32), ('cur_index_bits', _i32),
+        ('mark_prev', _vp),
+        ('rec_cur', _vp), ('tab_cur', _vp), ('mark_cur', _vp),
+        ('out_rhat', _vp), ('out_vr', _vp), ('out_r', _vp),
+        ('out_angle', _vp), ('out_match', _vp), ('dangle_prev', _vp),
+    ]
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+# every symbol declared in include/orbit_b200.h
+_sig('oa_last_error', C.c_char_p)
+_sig('oa_device_info', C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+     C.POINTER(C.c_int), C.POINTER(_i64), C.POINTER(_i64))
+_sig('oa_record_bytes', _sz, C.c_int)
+_sig('oa_table_slots', _i64, _i64)
+_sig('oa_index_bits', C.c_int, _i64)
+_sig('oa_bulk_workspace_bytes', _sz, _i64, C.c_int)
+_sig('oa_bulk_velocity', C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
+     _i64, C.c_int, _vp, _vp, _vp, _sz, _vp)
+_sig('oa_track_fused', C.c_int, C.POINTER(TrackArgs), _vp)
+_sig('oa_track_args_size', _sz)
+if lib.oa_track_args_size() != C.sizeof(TrackArgs):
+    raise ImportError("oa_track_args layout mismatch: C %d bytes, ctypes %d"
+                      % (lib.oa_track_args_size(), C.sizeof(TrackArgs)))
+_sig('oa_select_workspace_bytes', _sz, _i64)
+_sig('oa_select_count', C.c_int, _vp, _i64, C.c_int, _u16, _vp, _sz, _vp, _vp)
+_sig('oa_select_gather', C.c_int, _vp, _i64, C.c_int, _u16, _vp, _vp, _vp)
+_sig('oa_segment_offsets', C.c_int, _vp, _i64, _vp, C.c_int, _vp, _vp)
+_sig('oa_gather_record_ids', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp)
+_sig('oa_gather_u16', C.c_int, _vp, _vp, _i64, _vp, _vp)
+_sig('oa_gather_i64', C.c_int, _vp, _vp, _i64, _vp, _vp)
+_sig('oa_gather_f', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp)
+_sig('oa_mark_unmatched', C.c_int, _vp, _i64, _vp, _vp)
+_sig('oa_fill_u16', C.c_int, _vp, _i64, _u16, _vp)
+_sig('oa_set_record_angles', C.c_int, _vp, C.c_int, _vp, _i64, _vp)
+_sig('oa_sort_workspace_bytes', _sz, _i64)
+_sig('oa_sort_pairs_u64', C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
+     _vp, _sz, _vp)
+_sig('oa_minmax_i64', C.c_int, _vp, _i64, _vp, _vp)
+
+EXPORTS = [
+    'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
+    'oa_table_slots', 'oa_index_bits', 'oa_bulk_workspace_bytes',
+    'oa_bulk_velocity', 'oa_track_fused', 'oa_track_args_size',
+    'oa_select_workspace_bytes',
+    'oa_select_count', 'oa_select_gather', 'oa_segment_offsets',
+    'oa_gather_record_ids', 'oa_gather_u16', 'oa_gather_i64', 'oa_gather_f',
+    'oa_mark_unmatched', 'oa_fill_u16', 'oa_set_record_angles',
+    'oa_sort_workspace_bytes',
+    'oa_sort_pairs_u64', 'oa_minmax_i64',
+]
+
+
+def check(rc):
+    """Raise on a non-zero return code of the C ABI."""
+    if rc != 0:
+        msg = lib.oa_last_error()
+        raise OrbitB200Error(
+            "liborbit_b200 error %d: %s" % (rc, msg.decode() if msg else '?'))
+
+
+def ptr(t):
+    """Device (or pinned host) address of a torch tensor, NULL for None."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def dtype_code(np_dtype):
+    np_dtype = np.dtype(np_dtype)
+    if np_dtype == np.float32:
+        return OA_F32
+    if np_dtype == np.float64:
+        return OA_F64
+    raise TypeError("unsupported floating dtype %s" % np_dtype)

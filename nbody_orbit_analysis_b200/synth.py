@@ -53,10 +53,11 @@ def halo_sizes(n_particles, n_halos, largest_frac=0.05, slope=1.9):
         # flatten the head so that the largest halo holds ~largest_frac
         w = np.minimum(w, largest_frac)
         w = w / w.sum()
-    sizes = np.maximum(np.floor(w * n_particles).astype(np.int64), 1)
-    sizes[0] += n_particles - sizes.sum()
-    if sizes[0] < 1:
+    if n_particles < n_halos:
         raise ValueError("too many halos for this particle count")
+    # every halo gets one particle, the rest follows the power law
+    sizes = np.floor(w * (n_particles - n_halos)).astype(np.int64) + 1
+    sizes[0] += n_particles - sizes.sum()
     return sizes
 
 

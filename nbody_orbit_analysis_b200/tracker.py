@@ -1,0 +1,357 @@
+"""Device-side state machine of the orbit-tracking path.
+
+``OrbitTracker.step()`` is the GPU replacement of one iteration of the
+reference's per-snapshot loop body (reference ``track_orbits.py:147-217``: the
+per-halo ``track(j)`` calls plus result assembly).  It stages one snapshot in
+HBM, launches the fused tracking kernel and the ordered event compaction
+through the C ABI (``_lib``) and returns the small arrays the writer needs.
+
+PyTorch is used for device/pinned buffers and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+_F = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.OrbitB200Error(
+            "orbit-b200 needs a CUDA device (B200, sm_100a); there is no CPU "
+            "fallback.")
+
+
+class Generation:
+    """Carried state of one processed snapshot (reference
+    ``track_orbits.py:234-240``), resident in HBM."""
+    __slots__ = ('n', 'rec', 'tab', 'mark', 'index_bits', 'offsets',
+                 'halo_exists', 'frame_f64', 'ids_dtype', 'gpos')
+
+
+class StepResult:
+    __slots__ = ('n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
+                 'bulk_velocities', 'angles', 'diag', 'n_events',
+                 'apsis_prev_index')
+
+
+def _as_f(arr, name):
+    arr = np.asarray(arr)
+    if arr.dtype not in _F:
+        if arr.dtype.kind in 'iuf':
+            arr = arr.astype(np.float64)
+        else:
+            raise TypeError("%s must be a float array, got %s" % (
+                name, arr.dtype))
+    return arr
+
+
+class OrbitTracker:
+    """Per-snapshot GPU tracker.
+
+    Parameters
+    ----------
+    mode : 'pericentric' | 'apocentric'
+    device : torch device (default: current CUDA device)
+    onthefly : use the arithmetic of ``track_orbits_onthefly.py`` (frame and
+        v_r in the data dtype, no Hubble flow) and produce per-match outputs.
+    """
+
+    def __init__(self, mode='pericentric', device=None, onthefly=False):
+        require_cuda()
+        if mode not in _lib.OA_MODE:
+            raise ValueError("mode must be 'pericentric' or 'apocentric'")
+        self.mode = mode
+        self.device = torch.device(
+            device if device is not None else
+            'cuda:%d' % torch.cuda.current_device())
+        self.onthefly = bool(onthefly)
+        self.prev = None
+        self.launches = 0          # kernels launched through the C ABI
+
+    # -- buffers -------------------------------------------------------------
+    def _empty(self, n, dtype):
+        return torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_device(self, arr, dtype=None):
+        """Host numpy array -> device tensor through pinned staging."""
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        t = torch.from_numpy(arr.reshape(-1))
+        if t.numel() == 0:
+            return torch.empty(0, dtype=t.dtype, device=self.device)
+        if not t.is_pinned():
+            # torch's caching host allocator hands the block back only after
+            # the copy that reads it has completed on this stream
+            buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+            buf.copy_(t)
+            t = buf
+        return t.to(self.device, non_blocking=True)
+
+    # -- one snapshot ----------------------------------------------------------
+    def step(self, snapshot, halo_exists, region_positions, region_bulk_vels,
+             H=0.0, want_angles=False, diagnostics=False):
+        """Process one snapshot given as HOST arrays (the loader's dict).
+
+        Mirrors the arguments the reference's ``track`` closure captures
+        (``track_orbits.py:147-155``).  Returns a ``StepResult``; its event
+        fields are ``None`` for a snapshot without a previous generation.
+        """
+        coords = _as_f(snapshot['coordinates'], 'coordinates')
+        vels = _as_f(snapshot['velocities'], 'velocities')
+        if coords.dtype != vels.dtype:
+            coords = coords.astype(np.float64)
+            vels = vels.astype(np.float64)
+        ids = np.asarray(snapshot['ids'])
+        n = len(ids)
+        masses = snapshot['masses']
+        dev = {
+            'pos': self._to_device(coords), 'vel': self._to_device(vels),
+            'ids': self._to_device(ids, np.int64),
+            'mass': self._to_device(_as_f(masses, 'masses'))
+            if isinstance(masses, np.ndarray) else None,
+        }
+        offsets = np.concatenate((
+            np.asarray(snapshot['region_offsets'], dtype=np.int64), [n]))
+        return self.step_device(
+            dev, n, coords.dtype, ids.dtype, offsets, halo_exists,
+            region_positions, region_bulk_vels, H,
+            box_size=snapshot.get('box_size'),
+            redshift=snapshot.get('redshift', 0.0),
+            mass_dtype=masses.dtype if isinstance(masses, np.ndarray) else None,
+            want_angles=want_angles, diagnostics=diagnostics)
+
+    def step_device(self, dev, n, data_dtype, ids_dtype, offsets, halo_exists,
+                    region_positions, region_bulk_vels, H, box_size=None,
+                    redshift=0.0, mass_dtype=None, want_angles=False,
+                    diagnostics=False, gpos=None, finalize=True):
+        """Same as ``step`` with the particle arrays already in HBM
+        (``dev`` = dict of flat torch tensors ``pos``, ``vel``, ``ids``,
+        optional ``mass``)."""
+        st = self._stream()
+        data_dtype = np.dtype(data_dtype)
+        halo_exists = np.asarray(halo_exists)
+        n_h = len(halo_exists)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert len(offsets) == n_h + 1
+        region_positions = np.asarray(region_positions)
+        centre_f32 = region_positions.dtype == np.float32
+        x64 = data_dtype == np.float64
+        if self.onthefly:
+            frame_f64 = x64
+        else:
+            frame_f64 = x64 or not centre_f32
+        prev = self.prev
+        if prev is not None and prev.frame_f64 != frame_f64:
+            raise _lib.OrbitB200Error(
+                "the halo-frame dtype changed between snapshots (float%d -> "
+                "float%d); keep coordinates / region centres in one dtype"
+                % (64 if prev.frame_f64 else 32, 64 if frame_f64 else 32))
+
+        # ---- region table (oa_region rows) ---------------------------------
+        rows = np.zeros(n_h, dtype=_lib.REGION_DTYPE)
+        rows['centre'] = region_positions.astype(np.float64).reshape(n_h, 3)
+        rows['prev_begin'] = -1
+        matched = np.zeros(n_h, dtype=bool)
+        if prev is not None and n_h and len(prev.halo_exists):
+            pos_in_prev = np.searchsorted(prev.halo_exists, halo_exists)
+            pos_c = np.minimum(pos_in_prev, len(prev.halo_exists) - 1)
+            matched = prev.halo_exists[pos_c] == halo_exists
+            k = pos_c[matched]
+            rows['prev_begin'][matched] = prev.offsets[k]
+            rows['prev_count'][matched] = prev.offsets[k + 1] - prev.offsets[k]
+        derive_bulk = region_bulk_vels is None
+        if not derive_bulk:
+            bulk = np.asarray(region_bulk_vels)
+            rows['bulk'] = bulk.astype(np.float64).reshape(n_h, 3)
+            bulk_dtype = bulk.dtype if bulk.dtype in _F else np.dtype(
+                np.float64)
+        else:
+            bulk_dtype = data_dtype if mass_dtype is None else np.result_type(
+                data_dtype, mass_dtype)
+        bulk_f32 = bulk_dtype == np.float32
+
+        d_off = self._to_device(offsets)
+        d_rows = self._to_device(rows.view(np.uint8))
+        d_bulk_out = None
+        if derive_bulk:
+            ws_bytes = lib.oa_bulk_workspace_bytes(n, n_h)
+            ws = self._empty(ws_bytes, torch.uint8)
+            d_bulk_out = self._empty(max(3 * n_h, 1), torch.float64)
+            check(lib.oa_bulk_velocity(
+                ptr(dev['vel']), _lib.dtype_code(data_dtype), ptr(dev['mass']),
+                _lib.dtype_code(mass_dtype) if mass_dtype is not None else 0,
+                ptr(d_off), n_h, n, int(bulk_f32), ptr(d_rows),
+                ptr(d_bulk_out), ptr(ws), ws_bytes, st))
+            self.launches += 2
+
+        # ---- new generation buffers ------------------------------------------
+        lens = np.diff(offsets)
+        gen = Generation()
+        gen.n = n
+        gen.frame_f64 = frame_f64
+        gen.ids_dtype = np.dtype(ids_dtype)
+        gen.offsets = offsets
+        gen.halo_exists = halo_exists
+        gen.index_bits = lib.oa_index_bits(int(lens.max()) if n_h else 0)
+        gen.gpos = gpos
+        rec_bytes = lib.oa_record_bytes(int(frame_f64))
+        gen.rec = self._empty(max(n, 1) * rec_bytes, torch.uint8)
+        gen.tab = self._empty(lib.oa_table_slots(n), torch.int32)
+        gen.mark = self._empty(max(n, 1) + 8, torch.int16)
+
+        fdt = torch.float64 if frame_f64 else torch.float32
+        diag = None
+        out_angle = None
+        if want_angles:
+            out_angle = self._empty(max(n, 1), torch.int16)
+        if diagnostics:
+            vr_dt = fdt if self.onthefly else torch.float64
+            diag = {'rhat': self._empty(3 * n, fdt), 'vr': self._empty(n, vr_dt),
+                    'r': self._empty(n, fdt),
+                    'match': self._empty(n, torch.int64)}
+        dangle = None
+        if self.onthefly and prev is not None:
+            dangle = self._empty(max(prev.n, 1), fdt)
+
+        a = _lib.TrackArgs()
+        a.pos, a.vel, a.ids = ptr(dev['pos']), ptr(dev['vel']), ptr(dev['ids'])
+        a.n_cur = n
+        a.cur_off, a.regions = ptr(d_off), ptr(d_rows)
+        a.n_regions = n_h
+        a.data_dtype = int(x64)
+        a.frame_dtype = int(frame_f64)
+        a.centre_f32 = int(centre_f32)
+        a.bulk_f32 = int(bulk_f32)
+        a.periodic = int(box_size is not None)
+        a.onthefly = int(self.onthefly)
+        a.mode = _lib.OA_MODE[self.mode]
+        if box_size is not None:
+            box = np.broadcast_to(
+                np.asarray(box_size, dtype=np.float64), (3,))
+            a.box[0], a.box[1], a.box[2] = float(box[0]), float(box[1]), \
+                float(box[2])
+        a.hubble = float(H)
+        a.one_plus_z = 1 + float(redshift)
+        if prev is not None:
+            a.rec_prev, a.tab_prev = ptr(prev.rec), ptr(prev.tab)
+            a.n_prev = prev.n
+            a.prev_index_bits = prev.index_bits
+            a.mark_prev = ptr(prev.mark)
+        else:
+            a.prev_index_bits = 1
+        a.cur_index_bits = gen.index_bits
+        a.rec_cur, a.tab_cur, a.mark_cur = ptr(gen.rec), ptr(gen.tab), \
+            ptr(gen.mark)
+        a.out_angle = ptr(out_angle)
+        if diag is not None:
+            a.out_rhat, a.out_vr, a.out_r = ptr(diag['rhat']), \
+                ptr(diag['vr']), ptr(diag['r'])
+            a.out_match = ptr(diag['match'])
+        a.dangle_prev = ptr(dangle)
+        check(lib.oa_track_fused(C.byref(a), st))
+        self.launches += 1
+
+        res = StepResult()
+        res.n = n
+        res.diag = diag
+        res.hinds = np.flatnonzero(matched)
+        res.apsis_ids = res.apsis_angles = res.apsis_offsets = None
+        res.apsis_prev_index = None
+        res.n_events = 0
+        res.angles = None
+        pending = {'gen': gen, 'prev': prev, 'rows': rows, 'matched': matched,
+                   'd_bulk_out': d_bulk_out, 'derive_bulk': derive_bulk,
+                   'bulk_dtype': bulk_dtype, 'region_bulk_vels':
+                   region_bulk_vels, 'out_angle': out_angle, 'dangle': dangle,
+                   'n_h': n_h}
+        self.prev = gen
+        if finalize:
+            return self.finalize(res, pending)
+        return res, pending
+
+    def finalize(self, res, pending):
+        """Ordered event compaction + device->host of the (small) results."""
+        st = self._stream()
+        prev, rows, matched = pending['prev'], pending['rows'], \
+            pending['matched']
+        n_h = pending['n_h']
+        if pending['derive_bulk']:
+            b = pending['d_bulk_out'][:3 * n_h].cpu().numpy().reshape(n_h, 3)
+            res.bulk_velocities = b.astype(pending['bulk_dtype'])
+        else:
+            res.bulk_velocities = np.asarray(pending['region_bulk_vels'])
+        if pending['out_angle'] is not None:
+            res.angles = pending['out_angle'][:res.n].cpu().numpy().view(
+                np.float16)
+        if prev is None:
+            return res
+        sel, total = self.select(prev.mark, prev.n, _lib.OA_SEL_NE,
+                                 _lib.OA_NO_EVENT)
+        seg = rows['prev_begin'][matched]
+        res.apsis_offsets = np.concatenate(
+            (self.segment_offsets(sel, total, seg), [total])).astype(np.int64)
+        d_ids = self._empty(max(total, 1), torch.int64)
+        d_ang = self._empty(max(total, 1), torch.int16)
+        check(lib.oa_gather_record_ids(
+            ptr(prev.rec), int(prev.frame_f64), ptr(sel), total, ptr(d_ids),
+            st))
+        check(lib.oa_gather_u16(ptr(prev.mark), ptr(sel), total, ptr(d_ang),
+                                st))
+        self.launches += 2
+        res.n_events = total
+        res.apsis_ids = d_ids[:total].cpu().numpy().astype(
+            prev.ids_dtype, copy=False)
+        res.apsis_angles = d_ang[:total].cpu().numpy().view(np.float16)
+        res.apsis_prev_index = sel[:total] if total else sel[:0]
+        return res
+
+    def load_angles(self, angles):
+        """Replace the angle accumulators of the current generation with a
+        host float16 array in block order (resume, reference
+        ``track_orbits.py:229-232``)."""
+        gen = self.prev
+        angles = np.ascontiguousarray(angles, dtype=np.float16)
+        if gen is None or len(angles) != gen.n:
+            raise ValueError("checkpoint does not match the resumed snapshot")
+        d = self._to_device(angles.view(np.int16))
+        check(lib.oa_set_record_angles(ptr(gen.rec), int(gen.frame_f64), ptr(d),
+                                       gen.n, self._stream()))
+        self.launches += 1
+
+    # -- helpers shared with the on-the-fly driver -----------------------------
+    def select(self, marks, n, op, value):
+        """Ascending positions i < n with ``marks[i] (op) value`` (device
+        int64 tensor) and their count."""
+        st = self._stream()
+        ws_bytes = lib.oa_select_workspace_bytes(n)
+        ws = self._empty(ws_bytes, torch.uint8)
+        d_total = self._empty(1, torch.int64)
+        check(lib.oa_select_count(ptr(marks), n, op, value, ptr(ws), ws_bytes,
+                                  ptr(d_total), st))
+        total = int(d_total.item())        # the one host sync of a snapshot
+        sel = self._empty(max(total, 1), torch.int64)
+        if total:
+            check(lib.oa_select_gather(ptr(marks), n, op, value, ptr(ws),
+                                       ptr(sel), st))
+        self.launches += 3
+        return sel, total
+
+    def segment_offsets(self, sel, total, seg_begin):
+        """Number of selected positions below each segment start (host)."""
+        st = self._stream()
+        seg_begin = np.ascontiguousarray(seg_begin, dtype=np.int64)
+        if len(seg_begin) == 0:
+            return np.zeros(0, dtype=np.int64)
+        d_seg = self._to_device(seg_begin)
+        d_out = self._empty(len(seg_begin), torch.int64)
+        check(lib.oa_segment_offsets(ptr(sel), total, ptr(d_seg),
+                                     len(seg_begin), ptr(d_out), st))
+        self.launches += 1
+        return d_out.cpu().numpy()

@@ -1,0 +1,121 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol,
+host-side logic (storage container, synthetic workloads, argument checks)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, 'include', 'orbit_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(oa_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nbody_orbit_analysis_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(_lib.lib, name), 'missing export ' + name
+    assert sorted(_lib.EXPORTS) == names
+    assert _lib.lib.oa_abi_version() == _lib.ABI_VERSION
+    assert _lib.lib.oa_track_args_size() == C.sizeof(_lib.TrackArgs)
+    assert _lib.lib.oa_record_bytes(0) == 32
+    assert _lib.lib.oa_record_bytes(1) == 64
+    # index bits reserve the all-ones pattern for the empty slot
+    for n in (0, 1, 2, 3, 7, 8, 1000, 2**20):
+        b = _lib.lib.oa_index_bits(n)
+        assert (1 << b) - 1 > n and (b == 1 or (1 << (b - 1)) - 1 <= n)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    from nbody_orbit_analysis_b200 import _lib
+    from nbody_orbit_analysis_b200.tracker import OrbitTracker
+    from nbody_orbit_analysis_b200.track_orbits import track_orbits
+    with pytest.raises(_lib.OrbitB200Error):
+        OrbitTracker()
+    with pytest.raises(_lib.OrbitB200Error):
+        track_orbits([1], [[5]], None, None, 'x', verbose=False)
+    sm = C.c_int()
+    assert _lib.lib.oa_device_info(C.byref(sm), None, None, None, None) < 0
+    assert _lib.lib.oa_last_error()
+
+
+def test_argument_validation_precedes_everything():
+    from nbody_orbit_analysis_b200.track_orbits import track_orbits
+    with pytest.raises(ValueError):
+        track_orbits([1, 2], [[1]], None, None, 'x', verbose=False)
+    with pytest.raises(ValueError):
+        track_orbits([1], [[1]], None, None, 'x', mode='both', verbose=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, 'nbody_orbit_analysis_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f)).read()
+                assert 'import oracle' not in text and \
+                    'from oracle' not in text, f
+
+
+def test_shim_container_roundtrip(tmp_path):
+    from nbody_orbit_analysis_b200 import h5shim
+    f = str(tmp_path / 'a.h5')
+    with h5shim.File(f, 'w') as hf:
+        hf.attrs['mode'] = 'pericentric'
+        hf.attrs['box_size'] = 100.0
+    with h5shim.File(f, 'r+') as hf:
+        g = hf.create_group('snapshot_012')
+        g.create_dataset('angles', data=np.arange(5, dtype=np.float16))
+        g.create_dataset('empty', data=np.array([], dtype=np.int64))
+        g.create_dataset('pos', data=np.arange(12.).reshape(4, 3))
+        with pytest.raises(ValueError):
+            g.create_dataset('pos', data=np.zeros(1))
+    with h5shim.File(f, 'a') as hf:
+        hf.create_group('snapshot_003')
+    with h5shim.File(f, 'r') as hf:
+        assert list(hf.keys()) == ['snapshot_003', 'snapshot_012']
+        assert hf.attrs['mode'] == 'pericentric'
+        assert 'box_size' in hf.attrs and hf.attrs['box_size'] == 100.0
+        g = hf['snapshot_012']
+        assert g['angles'].dtype == np.float16 and len(g['angles']) == 5
+        assert g['angles'][1:3].tolist() == [1.0, 2.0]
+        assert g['pos'][:].shape == (4, 3) and g['pos'][2:4][0, 0] == 6.0
+        assert len(g['empty']) == 0 and g['empty'][:].dtype == np.int64
+        with pytest.raises(KeyError):
+            hf['nope']
+    with pytest.raises(FileNotFoundError):
+        h5shim.File(str(tmp_path / 'missing.h5'), 'r')
+
+
+def test_synthetic_workload_is_reproducible_and_has_apsides():
+    from nbody_orbit_analysis_b200.synth import SynthSim
+    a = SynthSim(5000, 7, 4, late_halos=0.4)
+    b = SynthSim(5000, 7, 4, late_halos=0.4)
+    assert np.array_equal(a.main_branches, b.main_branches)
+    halo_ids = a.main_branches[2][a.main_branches[2] != -1]
+    pa = a.regions(a.snapshot_numbers[2], halo_ids)
+    sa = a.load_snapshot_data(a.snapshot_numbers[2], pa[0], pa[1])
+    sb = b.load_snapshot_data(b.snapshot_numbers[2], pa[0], pa[1])
+    for k in ('ids', 'coordinates', 'velocities', 'region_offsets'):
+        assert np.array_equal(sa[k], sb[k])
+    assert len(np.unique(sa['ids'])) == len(sa['ids'])
+    assert sa['coordinates'].min() >= 0 and sa['coordinates'].max() <= a.box
+    # block order differs from snapshot to snapshot (matching is non-trivial)
+    pc = a.regions(a.snapshot_numbers[3], a.main_branches[3][
+        a.main_branches[3] != -1])
+    sc = a.load_snapshot_data(a.snapshot_numbers[3], pc[0], pc[1])
+    common = np.intersect1d(sa['ids'][:200], sc['ids'])
+    assert len(common) > 20
+    assert not np.array_equal(
+        sa['ids'][np.isin(sa['ids'], common)],
+        sc['ids'][np.isin(sc['ids'], common)])
