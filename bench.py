@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Benchmark of the orbit-tracking hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (B200)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm
+
+metric  : particle-snapshots/sec = sum over timed snapshots of the particles in
+          all region blocks / time of the tracking path (halo frame + ID match
+          + apsis detection + angle update + ordered event compaction + D2H of
+          the event lists).
+step    : one snapshot.  Workload at N=1: BASELINE config[1], 256^3 particles,
+          1000 halos, pericentric; per-GPU work is fixed as N grows (weak
+          scaling, particles sharded by ID).
+value   : inputs resident in HBM (generated there by csrc/oa_synth.cu).
+e2e     : same steps through OrbitTracker.step() with HOST (pinned) snapshot
+          arrays: H2D of ids/pos/vel and D2H of the events inside the timing.
+roofline: fused tracking kernel, algorithmic bytes = 72 B per particle-snapshot
+           / its CUDA-event duration, vs MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+B_ALG_F32 = 72.0   # 32 in + 18 state read + 4 match + 18 write
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=12)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--particles', type=int, default=256 ** 3,
+                    help='particles per GPU (universe size)')
+    ap.add_argument('--halos', type=int, default=1000)
+    ap.add_argument('--mode', default='pericentric')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-particles', type=int, default=400000,
+                    help='particles per snapshot in the CPU-baseline sample')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,'
+              'clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index),
+                 '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown',
+                                  'sw_thermal_slowdown', 'sw_power_cap'), f[3:]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(HERE, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured'
+    except (OSError, KeyError, ValueError):
+        return FALLBACK_HBM_GBS, 'fallback'
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle (numpy restatement of the reference) on host cores
+# ---------------------------------------------------------------------------
+def cpu_track(snapshots, catalog, mode):
+    """Run the oracle over a list of host snapshots; returns
+    (seconds in the tracking path, particle-snapshots, per-step outputs)."""
+    from oracle import orbit_oracle as oracle
+    prev, outs = None, []
+    seconds, count = 0.0, 0
+    for s, (snap, (pos, rad, bulk)) in enumerate(zip(snapshots, catalog)):
+        exists = np.arange(len(pos))
+        t0 = time.perf_counter()
+        state, out = oracle.track_snapshot(snap, exists, pos, bulk, 0.0, mode,
+                                           prev)
+        dt = time.perf_counter() - t0
+        if s > 0:
+            seconds += dt
+            count += len(snap['ids'])
+        outs.append(out)
+        prev = state
+    return seconds, count, outs
+
+
+def host_sample(args, n_steps, seed_rank=0):
+    """Bounded sample of the workload generated on the host: the first halos
+    of the configuration up to ~cpu_particles particles per snapshot."""
+    from nbody_orbit_analysis_b200.synth import SynthSim
+    sim = SynthSim(args.particles, args.halos, n_steps + 1, dtype=np.float32,
+                   catalogue_dtype=np.float32)
+    ncols = int(np.searchsorted(np.cumsum(sim.sizes), args.cpu_particles)) + 1
+    ncols = min(ncols, sim.n_halos)
+    cols = np.arange(ncols)
+    snaps, cat = [], []
+    for t in range(n_steps + 1):
+        pos = sim.halo_centre(t)[cols].astype(np.float32)
+        cat.append((pos, sim.radius[cols].astype(np.float32),
+                    sim.vh[cols].astype(np.float32)))
+        snaps.append(sim.load_snapshot_data(sim.snapshot_numbers[t], pos, None,
+                                            cols=cols))
+    return snaps, cat, ncols
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference
+    itself is Python and cannot travel to the GPU box) on this host."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_steps = args.warmup + args.steps
+    snaps, cat, ncols = host_sample(args, n_steps)
+    # warm-up steps are executed like the timed ones; only the last K count
+    from oracle import orbit_oracle as oracle
+    prev = None
+    secs, count = 0.0, 0
+    for s, (snap, (pos, rad, bulk)) in enumerate(zip(snaps, cat)):
+        t0 = time.perf_counter()
+        prev, _ = oracle.track_snapshot(snap, np.arange(len(pos)), pos, bulk,
+                                        0.0, args.mode, prev)
+        dt = time.perf_counter() - t0
+        if s > args.warmup:
+            secs += dt
+            count += len(snap['ids'])
+    value = count / secs
+    sample = ('first %d of %d halos (%d particles/snapshot) of the %d-particle '
+              'configuration, %d snapshots' % (
+                  ncols, args.halos, len(snaps[-1]['ids']), args.particles,
+                  args.steps))
+    line = {
+        'impl': 'reference', 'metric': 'particle-snapshots/sec',
+        'value': value, 'unit': 'particle-snapshots/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * secs / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32/f64',
+        'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': 'particle-snapshots/s',
+                         'cores': 1, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'particle-snapshots/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        'workload': '%d particles/GPU (256^3 = BASELINE config[1]), %d halos, '
+                    '%s tracking, fp32 data + int64 IDs, catalogue bulk '
+                    'velocities, periodic box' % (
+                        args.particles, args.halos, args.mode),
+        'particles_per_gpu': args.particles, 'halos': args.halos,
+        'mode': args.mode,
+        'l2': 'inputs larger than L2 (>=500 MB per step, distinct every step)',
+        'sharding': 'particle ID mod n_gpus',
+    }
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from nbody_orbit_analysis_b200.synth import DeviceSynth
+    from nbody_orbit_analysis_b200.tracker import OrbitTracker
+    from nbody_orbit_analysis_b200 import sharded
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    K, W = args.steps, args.warmup
+    n_snap = W + K + 1
+
+    gen = DeviceSynth(args.particles, args.halos, rank=rank, world=world)
+    exists = np.arange(args.halos)
+    snaps = [gen.snapshot(t) for t in range(n_snap)]
+    cats = [gen.regions(t) for t in range(n_snap)]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    comm = sharded.Comm(world, rank) if world > 1 else None
+
+    def one_step(trk, t, host=None):
+        pos, rad, bulk = cats[t]
+        if comm is not None:
+            pos, rad, bulk = comm.broadcast_catalogue(pos, rad, bulk)
+        if host is None:
+            dev, n, offsets = snaps[t]
+            res = trk.step_device(dev, n, np.float32, np.int64, offsets, exists,
+                                  pos, bulk, 0.0, box_size=gen.host.box,
+                                  gpos=dev.get('gpos'))
+        else:
+            res = trk.step(host[t], exists, pos, bulk, 0.0,
+                           gpos=host[t].get('_gpos'))
+        if comm is not None and res.apsis_ids is not None:
+            res = comm.merge_events(trk, res)
+        return res
+
+    def timed_run(host=None):
+        trk = OrbitTracker(mode=args.mode)
+        one_step(trk, 0, host)
+        for t in range(1, W + 1):
+            one_step(trk, t, host)
+        trk.timing = []
+        launches0 = trk.launches
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), \
+            torch.cuda.Event(enable_timing=True)
+        wall0 = time.time()
+        ev0.record()
+        n_part = n_events = 0
+        last = None
+        for t in range(W + 1, W + K + 1):
+            last = one_step(trk, t, host)
+            n_part += last.n
+            n_events += last.n_events
+        ev1.record()
+        barrier()
+        wall1 = time.time()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+        kern_ms = [a.elapsed_time(b) for a, b, _ in trk.timing]
+        kern_n = [n for _, _, n in trk.timing]
+        stats = torch.tensor([ms, float(n_part), float(n_events)],
+                             dtype=torch.float64, device='cuda')
+        if world > 1:
+            mx = stats.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stats.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, n_part = float(mx[0]), float(sm[1])
+            n_events = float(sm[2]) if comm is None else float(stats[2])
+        return {'ms': ms, 'particles': n_part, 'events': n_events,
+                'launches': trk.launches - launches0, 'clocks': clocks,
+                'kern_ms': kern_ms, 'kern_n': kern_n, 'last': last}
+
+    dev_run = timed_run()
+    value = dev_run['particles'] / (dev_run['ms'] * 1e-3)
+
+    # ---- end to end: host (pinned) snapshots ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for t in range(n_snap):
+            dev, n, offsets = snaps[t]
+            h = {}
+            for k, name in (('ids', 'ids'), ('pos', 'coordinates'),
+                            ('vel', 'velocities'), ('gpos', '_gpos')):
+                if dev.get(k) is None:
+                    continue
+                buf = torch.empty(dev[k].shape, dtype=dev[k].dtype,
+                                  pin_memory=True)
+                buf.copy_(dev[k])
+                arr = buf.numpy()
+                h[name] = arr.reshape(-1, 3) if k in ('pos', 'vel') else arr
+                h['_pin_' + k] = buf
+            h['masses'] = 1.0
+            h['region_offsets'] = offsets[:-1]
+            h['box_size'] = gen.host.box
+            h['redshift'] = 0.0
+            host.append(h)
+        torch.cuda.synchronize()
+        e2e_run = timed_run(host)
+        n_per_step = e2e_run['particles'] / K / world
+        ev_per_step = e2e_run['events'] / K
+        e2e = {'value': e2e_run['particles'] / (e2e_run['ms'] * 1e-3),
+               'unit': 'particle-snapshots/s',
+               'h2d_bytes_per_step': int(n_per_step * 32 + args.halos * 72),
+               'd2h_bytes_per_step': int(ev_per_step * 10 + args.halos * 8 + 8),
+               'ms_per_step': e2e_run['ms'] / K,
+               'events_per_step': ev_per_step}
+        if e2e_run['events'] != dev_run['events']:
+            e2e['warning'] = 'event count differs from the device-resident run'
+
+    # ---- roofline of the fused kernel ------------------------------------------
+    peak, peak_kind = measured_peak()
+    k_ms = float(np.mean(dev_run['kern_ms']))
+    k_n = float(np.mean(dev_run['kern_n']))
+    achieved = k_n * B_ALG_F32 / (k_ms * 1e-3) / 1e9
+    roofline = {
+        'kernel': 'oa_track_kernel<float,float,double> (fused frame + hash '
+                  'match + apsis + angle update + table insert)',
+        'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
+        'algorithmic_bytes_per_particle': B_ALG_F32,
+        'kernel_ms': k_ms, 'particles_per_launch': k_n,
+        'kernel_particle_snapshots_per_s': k_n / (k_ms * 1e-3),
+        'kernel_share_of_step': k_ms * K / dev_run['ms'],
+    }
+    traffic_file = os.path.join(HERE, 'profiles', 'traffic.json')
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                roofline['traffic'] = json.load(fh).get('oa_track_kernel')
+        except (OSError, ValueError):
+            pass
+
+    # ---- CPU baseline on a bounded sample + parity of that sample -------------
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_baseline(args, snaps, cats, gen, torch)
+
+    if rank == 0:
+        line = {
+            'metric': 'particle-snapshots/sec', 'value': value,
+            'unit': 'particle-snapshots/s', 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': dev_run['ms'] / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 frame / f64 v_r / int64 ids / f16 angles',
+            'data': 'synthetic', 'config': workload_config(args),
+            'clocks': dev_run['clocks'], 'gpu_launches': dev_run['launches'],
+            'events_per_step': dev_run['events'] / K,
+            'roofline': roofline,
+        }
+        if e2e is not None:
+            line['e2e'] = e2e
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, snaps, cats, gen, torch):
+    """Oracle on the first halos of the first snapshots of THIS run's data,
+    timed on one host core, and compared with the GPU path on the same data."""
+    from nbody_orbit_analysis_b200.tracker import OrbitTracker
+    sizes = gen.host.sizes
+    ncols = int(np.searchsorted(np.cumsum(sizes), args.cpu_particles)) + 1
+    ncols = min(ncols, len(sizes))
+    n_s = min(len(snaps), 7)
+    host, cat = [], []
+    for t in range(n_s):
+        dev, n, offsets = snaps[t]
+        hi = int(offsets[ncols])
+        host.append({
+            'ids': dev['ids'][:hi].cpu().numpy(),
+            'coordinates': dev['pos'][:3 * hi].cpu().numpy().reshape(-1, 3),
+            'velocities': dev['vel'][:3 * hi].cpu().numpy().reshape(-1, 3),
+            'masses': 1.0, 'region_offsets': offsets[:ncols].copy(),
+            'box_size': gen.host.box, 'redshift': 0.0})
+        pos, rad, bulk = cats[t]
+        cat.append((pos[:ncols], rad[:ncols], bulk[:ncols]))
+    secs, count, outs = cpu_track(host, cat, args.mode)
+    # same sample through the CUDA path
+    trk = OrbitTracker(mode=args.mode)
+    ok, n_ev = True, 0
+    for t in range(n_s):
+        res = trk.step(host[t], np.arange(ncols), cat[t][0], cat[t][2], 0.0)
+        if t > 0:
+            exp = outs[t]
+            n_ev += len(exp['apsis_ids'])
+            ok &= np.array_equal(res.apsis_ids, exp['apsis_ids'])
+            ok &= np.array_equal(res.apsis_offsets, exp['apsis_offsets'])
+            a, b = res.apsis_angles.astype(np.float32), \
+                exp['apsis_angles'].astype(np.float32)
+            ok &= bool(np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True))
+    return {
+        'value': count / secs, 'unit': 'particle-snapshots/s', 'cores': 1,
+        'kind': 'port',
+        'sample': 'first %d halos (%d particles/snapshot) x %d snapshots of '
+                  'this run, oracle (numpy port of the reference) on 1 core; '
+                  'host has %d cores' % (ncols, len(host[-1]['ids']), n_s - 1,
+                                         os.cpu_count()),
+        'seconds': secs,
+        'parity_vs_gpu_on_sample': 'ok' if ok else 'MISMATCH',
+        'sample_events': n_ev,
+    }
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

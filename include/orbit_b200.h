@@ -138,7 +138,7 @@ typedef struct oa_track_args {
     uint16_t* mark_prev;    /* (n_prev,) event marks, updated                 */
     /* current generation (written) */
     void* rec_cur;          /* (n_cur,) records                               */
-    uint32_t* tab_cur;      /* oa_table_slots(n_cur) slots (filled here)      */
+    uint32_t* tab_cur;      /* oa_table_slots(n_cur) slots, cleared beforehand */
     uint16_t* mark_cur;     /* (n_cur,) initialised to "no event"             */
     /* optional per-particle outputs, NULL to skip */
     void* out_rhat;         /* (n_cur,3) frame_dtype                          */
@@ -150,6 +150,10 @@ typedef struct oa_track_args {
 } oa_track_args;
 
 int oa_track_fused(const oa_track_args* args, void* stream);
+/* Set all oa_table_slots(n) slots of a table to "empty".  Must precede the
+ * oa_track_fused call that fills `tab_cur` (kept separate so that the fused
+ * kernel can be timed on its own). */
+int oa_table_clear(uint32_t* tab, int64_t n, void* stream);
 /* sizeof(oa_track_args) as compiled -- lets a binding verify its struct mirror. */
 size_t oa_track_args_size(void);
 
@@ -209,6 +213,36 @@ int oa_sort_pairs_u64(const uint64_t* keys_in, const uint64_t* vals_in,
                       size_t workspace_bytes, void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Benchmark workload generator (not a reference function):
+ * rosette orbits about drifting halo centres, generated directly in HBM.
+ *   oa_synth_keys : per universe particle, key = (halo << 40 | shuffle hash)
+ *                   if it lies inside its region at time t, else a sentinel
+ *                   that sorts last; counts present particles per halo.
+ *   oa_synth_fill : after sorting (key, particle) pairs with oa_sort_pairs_u64,
+ *                   writes ids / positions / velocities in block order.
+ * ------------------------------------------------------------------------- */
+typedef struct oa_synth_params {
+    uint64_t seed;
+    int64_t n_universe;
+    int64_t id_stride, id_offset;   /* id = particle * stride + offset        */
+    const int64_t* halo_start;      /* (n_halos+1,) universe ranges           */
+    const double* halo_radius;      /* (n_halos,)                             */
+    const double* halo_c0;          /* (n_halos,3) centre at t = 0            */
+    const double* halo_vh;          /* (n_halos,3) drift = bulk velocity      */
+    double box;
+    double t;                       /* snapshot index (time in snapshots)     */
+    int32_t n_halos;
+    int32_t periodic;
+} oa_synth_params;
+
+int oa_synth_keys(const oa_synth_params* params, uint64_t* keys, uint64_t* vals,
+                  int64_t* halo_counts, void* stream);
+int oa_synth_fill(const oa_synth_params* params, const uint64_t* order,
+                  int64_t n_present, int data_dtype, void* pos, void* vel,
+                  int64_t* ids, void* stream);
+size_t oa_synth_params_size(void);
 
 #ifdef __cplusplus
 }

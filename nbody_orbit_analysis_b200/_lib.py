@@ -74,6 +74,16 @@ class TrackArgs(C.Structure):
     ]
 
 
+class SynthParams(C.Structure):
+    """``oa_synth_params`` -- keep in sync with include/orbit_b200.h."""
+    _fields_ = [
+        ('seed', C.c_uint64), ('n_universe', _i64), ('id_stride', _i64),
+        ('id_offset', _i64), ('halo_start', _vp), ('halo_radius', _vp),
+        ('halo_c0', _vp), ('halo_vh', _vp), ('box', C.c_double),
+        ('t', C.c_double), ('n_halos', _i32), ('periodic', _i32),
+    ]
+
+
 def _sig(name, restype, *argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -93,6 +103,7 @@ _sig('oa_bulk_velocity', C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
      _i64, C.c_int, _vp, _vp, _vp, _sz, _vp)
 _sig('oa_track_fused', C.c_int, C.POINTER(TrackArgs), _vp)
 _sig('oa_track_args_size', _sz)
+_sig('oa_table_clear', C.c_int, _vp, _i64, _vp)
 if lib.oa_track_args_size() != C.sizeof(TrackArgs):
     raise ImportError("oa_track_args layout mismatch: C %d bytes, ctypes %d"
                       % (lib.oa_track_args_size(), C.sizeof(TrackArgs)))
@@ -111,17 +122,24 @@ _sig('oa_sort_workspace_bytes', _sz, _i64)
 _sig('oa_sort_pairs_u64', C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
      _vp, _sz, _vp)
 _sig('oa_minmax_i64', C.c_int, _vp, _i64, _vp, _vp)
+_sig('oa_synth_keys', C.c_int, C.POINTER(SynthParams), _vp, _vp, _vp, _vp)
+_sig('oa_synth_fill', C.c_int, C.POINTER(SynthParams), _vp, _i64, C.c_int,
+     _vp, _vp, _vp, _vp)
+_sig('oa_synth_params_size', _sz)
+if lib.oa_synth_params_size() != C.sizeof(SynthParams):
+    raise ImportError("oa_synth_params layout mismatch")
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
     'oa_table_slots', 'oa_index_bits', 'oa_bulk_workspace_bytes',
-    'oa_bulk_velocity', 'oa_track_fused', 'oa_track_args_size',
+    'oa_bulk_velocity', 'oa_track_fused', 'oa_track_args_size', 'oa_table_clear',
     'oa_select_workspace_bytes',
     'oa_select_count', 'oa_select_gather', 'oa_segment_offsets',
     'oa_gather_record_ids', 'oa_gather_u16', 'oa_gather_i64', 'oa_gather_f',
     'oa_mark_unmatched', 'oa_fill_u16', 'oa_set_record_angles',
     'oa_sort_workspace_bytes',
-    'oa_sort_pairs_u64', 'oa_minmax_i64',
+    'oa_sort_pairs_u64', 'oa_minmax_i64', 'oa_synth_keys', 'oa_synth_fill',
+    'oa_synth_params_size',
 ]
 
 

@@ -30,3 +30,4 @@ extern "C" int oa_device_info(int* sm_count, int* cc_major, int* cc_minor,
 }
 
 extern "C" size_t oa_track_args_size(void) { return sizeof(oa_track_args); }
+extern "C" size_t oa_synth_params_size(void) { return sizeof(oa_synth_params); }

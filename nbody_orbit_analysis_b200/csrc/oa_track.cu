@@ -324,6 +324,13 @@ extern "C" int oa_index_bits(int64_t max_block_len) {
     return bits;
 }
 
+extern "C" int oa_table_clear(uint32_t* tab, int64_t n, void* stream) {
+    OA_REQUIRE(tab && n >= 0, "oa_table_clear: bad arguments");
+    OA_CUDA_CHECK(cudaMemsetAsync(tab, 0xFF, sizeof(uint32_t) * (size_t)oa_table_slots(n),
+                                  static_cast<cudaStream_t>(stream)));
+    return OA_OK;
+}
+
 extern "C" int oa_track_fused(const oa_track_args* args, void* stream) {
     OA_REQUIRE(args != nullptr, "oa_track_fused: args is NULL");
     const oa_track_args& a = *args;
@@ -344,9 +351,6 @@ extern "C" int oa_track_fused(const oa_track_args* args, void* stream) {
     OA_REQUIRE(a.n_prev == 0 || !a.rec_prev || (a.tab_prev && a.mark_prev),
                "oa_track_fused: previous generation incomplete");
     OA_REQUIRE(a.cur_index_bits >= 1 && a.cur_index_bits <= 32, "bad cur_index_bits");
-
-    OA_CUDA_CHECK(cudaMemsetAsync(a.tab_cur, 0xFF,
-                                  sizeof(uint32_t) * (size_t)oa_table_slots(a.n_cur), st));
 
     const bool hub = (a.hubble != 0.0) && !a.onthefly;
     const bool x64 = a.data_dtype == OA_F64, f64 = a.frame_dtype == OA_F64;

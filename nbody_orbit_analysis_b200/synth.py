@@ -255,3 +255,94 @@ def _match_rows(table, rows):
     if not np.array_equal(tv[out], rv):
         raise ValueError("region positions do not belong to this simulation")
     return out
+
+
+class DeviceSynth:
+    """The same kind of workload generated directly in HBM (throughput runs).
+
+    Uses the generator kernels of ``csrc/oa_synth.cu`` and the library's radix
+    sort for the per-snapshot block shuffle.  Sharding: rank ``r`` of ``w``
+    owns particle IDs ``u * w + r`` (``id mod w == r``); every
+    rank holds a sub-block of every halo.
+    """
+
+    def __init__(self, n_particles, n_halos, seed=SEED, box=100.0,
+                 dtype=np.float32, catalogue_dtype=np.float32, rank=0,
+                 world=1, device=None):
+        import ctypes as C
+        import torch
+        from . import _lib
+        self._C, self._torch, self._lib = C, torch, _lib
+        self.host = SynthSim(n_particles, n_halos, 1, seed=seed, box=box,
+                             dtype=dtype, catalogue_dtype=catalogue_dtype)
+        self.dtype = np.dtype(dtype)
+        self.cat_dtype = np.dtype(catalogue_dtype)
+        self.device = torch.device(device if device is not None else
+                                   'cuda:%d' % torch.cuda.current_device())
+        self.rank, self.world = int(rank), int(world)
+        h = self.host
+        self.n_halos, self.M = h.n_halos, h.N
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self.d_start = up(h.starts.astype(np.int64))
+        self.d_radius = up(h.radius.astype(np.float64))
+        self.d_c0 = up(h.c0.astype(np.float64).reshape(-1))
+        self.d_vh = up(h.vh.astype(np.float64).reshape(-1))
+        self.sort_bits = 40 + int(self.n_halos).bit_length()
+        self.ws_bytes = _lib.lib.oa_sort_workspace_bytes(self.M)
+
+    def _params(self, t):
+        p = self._lib.SynthParams()
+        p.seed = self.host.seed
+        p.n_universe = self.M
+        p.id_stride, p.id_offset = self.world, self.rank
+        p.halo_start = self.d_start.data_ptr()
+        p.halo_radius = self.d_radius.data_ptr()
+        p.halo_c0 = self.d_c0.data_ptr()
+        p.halo_vh = self.d_vh.data_ptr()
+        p.box = self.host.box
+        p.t = float(t)
+        p.n_halos = self.n_halos
+        p.periodic = 1
+        return p
+
+    def regions(self, t):
+        """(centres, radii, bulk velocities) of all halos at snapshot t."""
+        h = self.host
+        return (h.halo_centre(t).astype(self.cat_dtype),
+                h.radius.astype(self.cat_dtype), h.vh.astype(self.cat_dtype))
+
+    def snapshot(self, t):
+        """Generate snapshot ``t`` in HBM.  Returns ``(dev, n, offsets)`` with
+        ``dev`` = dict of flat device tensors (pos, vel, ids)."""
+        torch, lib, C = self._torch, self._lib.lib, self._C
+        check, ptr = self._lib.check, self._lib.ptr
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        M = self.M
+
+        def empty(n, dt):
+            return torch.empty(int(n), dtype=dt, device=self.device)
+        keys, vals = empty(M, torch.int64), empty(M, torch.int64)
+        keys2, vals2 = empty(M, torch.int64), empty(M, torch.int64)
+        counts = empty(self.n_halos, torch.int64)
+        ws = empty(self.ws_bytes, torch.uint8)
+        p = self._params(t)
+        check(lib.oa_synth_keys(C.byref(p), ptr(keys), ptr(vals), ptr(counts),
+                                st))
+        check(lib.oa_sort_pairs_u64(ptr(keys), ptr(vals), ptr(keys2),
+                                    ptr(vals2), M, 0, self.sort_bits, ptr(ws),
+                                    self.ws_bytes, st))
+        lens = counts.cpu().numpy()
+        offsets = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        n = int(offsets[-1])
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        # global block-order key of every particle: (halo << 40 | shuffle hash);
+        # the order all ranks' particles would have in one unsharded block
+        dev = {'pos': empty(3 * n, tdt), 'vel': empty(3 * n, tdt),
+               'ids': empty(n, torch.int64), 'mass': None,
+               'gpos': keys2[:n].clone() if self.world > 1 else None}
+        check(lib.oa_synth_fill(C.byref(p), ptr(vals2), n,
+                                int(self.dtype == np.float64), ptr(dev['pos']),
+                                ptr(dev['vel']), ptr(dev['ids']), st))
+        return dev, n, offsets

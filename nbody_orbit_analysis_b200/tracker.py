@@ -36,7 +36,7 @@ class Generation:
 class StepResult:
     __slots__ = ('n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
-                 'apsis_prev_index')
+                 'apsis_prev_index', 'prev_gen')
 
 
 def _as_f(arr, name):
@@ -72,6 +72,8 @@ class OrbitTracker:
         self.onthefly = bool(onthefly)
         self.prev = None
         self.launches = 0          # kernels launched through the C ABI
+        self.timing = None         # list of (start, stop, n) CUDA events of
+        #                            the fused kernel when profiling is on
 
     # -- buffers -------------------------------------------------------------
     def _empty(self, n, dtype):
@@ -96,7 +98,7 @@ class OrbitTracker:
 
     # -- one snapshot ----------------------------------------------------------
     def step(self, snapshot, halo_exists, region_positions, region_bulk_vels,
-             H=0.0, want_angles=False, diagnostics=False):
+             H=0.0, want_angles=False, diagnostics=False, gpos=None):
         """Process one snapshot given as HOST arrays (the loader's dict).
 
         Mirrors the arguments the reference's ``track`` closure captures
@@ -125,7 +127,8 @@ class OrbitTracker:
             box_size=snapshot.get('box_size'),
             redshift=snapshot.get('redshift', 0.0),
             mass_dtype=masses.dtype if isinstance(masses, np.ndarray) else None,
-            want_angles=want_angles, diagnostics=diagnostics)
+            want_angles=want_angles, diagnostics=diagnostics,
+            gpos=self._to_device(gpos, np.int64) if gpos is not None else None)
 
     def step_device(self, dev, n, data_dtype, ids_dtype, offsets, halo_exists,
                     region_positions, region_bulk_vels, H, box_size=None,
@@ -255,8 +258,16 @@ class OrbitTracker:
                 ptr(diag['vr']), ptr(diag['r'])
             a.out_match = ptr(diag['match'])
         a.dangle_prev = ptr(dangle)
+        check(lib.oa_table_clear(ptr(gen.tab), n, st))
+        if self.timing is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), \
+                torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(self.device))
         check(lib.oa_track_fused(C.byref(a), st))
-        self.launches += 1
+        if self.timing is not None:
+            ev1.record(torch.cuda.current_stream(self.device))
+            self.timing.append((ev0, ev1, n))
+        self.launches += 2
 
         res = StepResult()
         res.n = n
@@ -266,6 +277,7 @@ class OrbitTracker:
         res.apsis_prev_index = None
         res.n_events = 0
         res.angles = None
+        res.prev_gen = prev
         pending = {'gen': gen, 'prev': prev, 'rows': rows, 'matched': matched,
                    'd_bulk_out': d_bulk_out, 'derive_bulk': derive_bulk,
                    'bulk_dtype': bulk_dtype, 'region_bulk_vels':
