@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 3
+#define OA_ABI_VERSION 5
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -57,16 +57,25 @@ int oa_device_info(int* sm_count, int* cc_major, int* cc_minor,
  * of the previous snapshot holds the same halo (track_orbits.py:162-165).
  * ------------------------------------------------------------------------- */
 typedef struct oa_region {
-    double centre[3];   /* regions()[0][j]                                   */
-    double bulk[3];     /* regions()[2][j], or written by oa_bulk_velocity   */
-    int64_t prev_begin; /* first particle of the halo's previous block, or -1 */
-    int64_t prev_count; /* its length (0 when there is no previous block)    */
-} oa_region;            /* 64 bytes */
+    double centre[3];    /* regions()[0][j]                                   */
+    double bulk[3];      /* regions()[2][j], or written by oa_bulk_velocity   */
+    int64_t prev_begin;  /* first particle of the halo's previous block, or -1 */
+    int64_t prev_count;  /* its length (0 when there is no previous block)    */
+    int64_t prev_bucket; /* oa_table_bucket_begin() of that previous block    */
+    int64_t cur_bucket;  /* oa_table_bucket_begin() of this block             */
+} oa_region;             /* 80 bytes */
 
 /* Bytes of one carried-state record (32 for an OA_F32 frame, 64 for OA_F64). */
 size_t oa_record_bytes(int frame_dtype);
-/* Number of uint32 slots of the ID hash table for n region-particles. */
-int64_t oa_table_slots(int64_t n);
+
+/* ID hash table of one snapshot: 32-byte buckets {count, 7 slots}; the buckets
+ * of region block j (start `block_start`, length len) are
+ *   [oa_table_bucket_begin(block_start, j), ... + (2*len)/7 + 1).            */
+#define OA_BUCKET_WORDS 8
+#define OA_BUCKET_SLOTS 7
+int64_t oa_table_bucket_begin(int64_t block_start, int64_t region_index);
+/* Number of uint32 words of the table for n region-particles in n_regions. */
+int64_t oa_table_slots(int64_t n, int64_t n_regions);
 /* Bits needed to store a block-local particle index given the largest block. */
 int oa_index_bits(int64_t max_block_len);
 
@@ -131,14 +140,14 @@ typedef struct oa_track_args {
     double one_plus_z;
     /* previous generation (read) */
     const void* rec_prev;   /* (n_prev,) records, NULL if none                */
-    const uint32_t* tab_prev; /* oa_table_slots(n_prev) slots                 */
+    const uint32_t* tab_prev; /* table filled by the previous call             */
     int64_t n_prev;
     int32_t prev_index_bits;
     int32_t cur_index_bits;
     uint16_t* mark_prev;    /* (n_prev,) event marks, updated                 */
     /* current generation (written) */
     void* rec_cur;          /* (n_cur,) records                               */
-    uint32_t* tab_cur;      /* oa_table_slots(n_cur) slots, cleared beforehand */
+    uint32_t* tab_cur;      /* oa_table_slots() words, cleared beforehand      */
     uint16_t* mark_cur;     /* (n_cur,) initialised to "no event"             */
     /* optional per-particle outputs, NULL to skip */
     void* out_rhat;         /* (n_cur,3) frame_dtype                          */
@@ -150,10 +159,10 @@ typedef struct oa_track_args {
 } oa_track_args;
 
 int oa_track_fused(const oa_track_args* args, void* stream);
-/* Set all oa_table_slots(n) slots of a table to "empty".  Must precede the
+/* Zero all oa_table_slots(n, n_regions) words of a table.  Must precede the
  * oa_track_fused call that fills `tab_cur` (kept separate so that the fused
  * kernel can be timed on its own). */
-int oa_table_clear(uint32_t* tab, int64_t n, void* stream);
+int oa_table_clear(uint32_t* tab, int64_t n, int64_t n_regions, void* stream);
 /* sizeof(oa_track_args) as compiled -- lets a binding verify its struct mirror. */
 size_t oa_track_args_size(void);
 
@@ -175,21 +184,27 @@ int oa_select_count(const uint16_t* marks, int64_t n, int op, uint16_t value,
                     int64_t* total_dev, void* stream);
 int oa_select_gather(const uint16_t* marks, int64_t n, int op, uint16_t value,
                      const void* workspace, int64_t* sel_out, void* stream);
-/* offsets_out[k] = number of selected positions < seg_begin[k]   (k < n_seg);
+/* Consumers of a selection.  `n_sel` is the number of selected positions; when
+ * `n_dev` is not NULL it points to the exact count ON THE DEVICE (as written by
+ * oa_select_count) and `n_sel` is only an upper bound used to size the launch,
+ * so a whole snapshot can be enqueued without a host synchronisation.
+ *
+ * offsets_out[k] = number of selected positions < seg_begin[k]   (k < n_seg);
  * the caller appends the total.  np.cumsum([0]+lens), track_orbits.py:214. */
-int oa_segment_offsets(const int64_t* sel, int64_t n_sel,
+int oa_segment_offsets(const int64_t* sel, int64_t n_sel, const int64_t* n_dev,
                        const int64_t* seg_begin, int n_seg,
                        int64_t* offsets_out, void* stream);
 
 /* Gathers driven by a selection. */
 int oa_gather_record_ids(const void* rec, int frame_dtype, const int64_t* sel,
-                         int64_t n_sel, int64_t* ids_out, void* stream);
+                         int64_t n_sel, const int64_t* n_dev, int64_t* ids_out,
+                         void* stream);
 int oa_gather_u16(const uint16_t* src, const int64_t* sel, int64_t n_sel,
-                  uint16_t* out, void* stream);
+                  const int64_t* n_dev, uint16_t* out, void* stream);
 int oa_gather_i64(const int64_t* src, const int64_t* sel, int64_t n_sel,
-                  int64_t* out, void* stream);
+                  const int64_t* n_dev, int64_t* out, void* stream);
 int oa_gather_f(const void* src, int dtype, const int64_t* sel, int64_t n_sel,
-                void* out, void* stream);
+                const int64_t* n_dev, void* out, void* stream);
 /* marks[i] = (match[i] < 0) ? 1 : 0  -- "entered" predicate (onthefly :168) */
 int oa_mark_unmatched(const int64_t* match, int64_t n, uint16_t* marks,
                       void* stream);
@@ -211,6 +226,23 @@ int oa_sort_pairs_u64(const uint64_t* keys_in, const uint64_t* vals_in,
                       uint64_t* keys_out, uint64_t* vals_out, int64_t n,
                       int begin_bit, int end_bit, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* Sort keys for per-segment sorting of an ID list laid out in segments
+ * [seg_off[s], seg_off[s+1]): key_hi = segment index; key_lo = id - id_minmax[0]
+ * for segments whose sort_flag is non-zero (all, if sort_flag is NULL), else the
+ * element's own position (keeps the original order, onthefly :176-177);
+ * index[i] = i.  Two stable oa_sort_pairs_u64 passes (key_lo, then key_hi)
+ * give "sorted within every segment". */
+int oa_segment_sort_keys(const int64_t* ids, int64_t n, const int64_t* seg_off,
+                         int n_seg, const uint8_t* sort_flag,
+                         const int64_t* id_minmax, uint64_t* key_lo,
+                         uint64_t* key_hi, uint64_t* index, void* stream);
+/* head[i] = 1 where a new (segment, id) run starts in a sorted sequence;
+ * np.unique(return_counts=True) per halo, postprocessing.py:133-141. */
+int oa_run_heads(const uint64_t* seg, const int64_t* ids, int64_t n,
+                 uint16_t* head, void* stream);
+/* counts[k] = length of run k given the ascending run start positions. */
+int oa_run_lengths(const int64_t* starts, int64_t n_runs, int64_t n,
+                   int64_t* counts, void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
 

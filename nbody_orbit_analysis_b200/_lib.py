@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 3
+ABI_VERSION = 5
 
 
 class OrbitB200Error(RuntimeError):
@@ -45,11 +45,12 @@ def _load():
 lib = _load()
 LIB_PATH = _build.LIB
 
-# numpy view of `oa_region` (64 bytes)
+# numpy view of `oa_region` (80 bytes)
 REGION_DTYPE = np.dtype([
     ('centre', np.float64, (3,)), ('bulk', np.float64, (3,)),
-    ('prev_begin', np.int64), ('prev_count', np.int64)])
-assert REGION_DTYPE.itemsize == 64
+    ('prev_begin', np.int64), ('prev_count', np.int64),
+    ('prev_bucket', np.int64), ('cur_bucket', np.int64)])
+assert REGION_DTYPE.itemsize == 80
 
 _vp, _i64, _i32, _sz, _u16 = (C.c_void_p, C.c_int64, C.c_int32, C.c_size_t,
                               C.c_uint16)
@@ -96,25 +97,26 @@ _sig('oa_last_error', C.c_char_p)
 _sig('oa_device_info', C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
      C.POINTER(C.c_int), C.POINTER(_i64), C.POINTER(_i64))
 _sig('oa_record_bytes', _sz, C.c_int)
-_sig('oa_table_slots', _i64, _i64)
+_sig('oa_table_slots', _i64, _i64, _i64)
+_sig('oa_table_bucket_begin', _i64, _i64, _i64)
 _sig('oa_index_bits', C.c_int, _i64)
 _sig('oa_bulk_workspace_bytes', _sz, _i64, C.c_int)
 _sig('oa_bulk_velocity', C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
      _i64, C.c_int, _vp, _vp, _vp, _sz, _vp)
 _sig('oa_track_fused', C.c_int, C.POINTER(TrackArgs), _vp)
 _sig('oa_track_args_size', _sz)
-_sig('oa_table_clear', C.c_int, _vp, _i64, _vp)
+_sig('oa_table_clear', C.c_int, _vp, _i64, _i64, _vp)
 if lib.oa_track_args_size() != C.sizeof(TrackArgs):
     raise ImportError("oa_track_args layout mismatch: C %d bytes, ctypes %d"
                       % (lib.oa_track_args_size(), C.sizeof(TrackArgs)))
 _sig('oa_select_workspace_bytes', _sz, _i64)
 _sig('oa_select_count', C.c_int, _vp, _i64, C.c_int, _u16, _vp, _sz, _vp, _vp)
 _sig('oa_select_gather', C.c_int, _vp, _i64, C.c_int, _u16, _vp, _vp, _vp)
-_sig('oa_segment_offsets', C.c_int, _vp, _i64, _vp, C.c_int, _vp, _vp)
-_sig('oa_gather_record_ids', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp)
-_sig('oa_gather_u16', C.c_int, _vp, _vp, _i64, _vp, _vp)
-_sig('oa_gather_i64', C.c_int, _vp, _vp, _i64, _vp, _vp)
-_sig('oa_gather_f', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp)
+_sig('oa_segment_offsets', C.c_int, _vp, _i64, _vp, _vp, C.c_int, _vp, _vp)
+_sig('oa_gather_record_ids', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp, _vp)
+_sig('oa_gather_u16', C.c_int, _vp, _vp, _i64, _vp, _vp, _vp)
+_sig('oa_gather_i64', C.c_int, _vp, _vp, _i64, _vp, _vp, _vp)
+_sig('oa_gather_f', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp, _vp)
 _sig('oa_mark_unmatched', C.c_int, _vp, _i64, _vp, _vp)
 _sig('oa_fill_u16', C.c_int, _vp, _i64, _u16, _vp)
 _sig('oa_set_record_angles', C.c_int, _vp, C.c_int, _vp, _i64, _vp)
@@ -122,6 +124,10 @@ _sig('oa_sort_workspace_bytes', _sz, _i64)
 _sig('oa_sort_pairs_u64', C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
      _vp, _sz, _vp)
 _sig('oa_minmax_i64', C.c_int, _vp, _i64, _vp, _vp)
+_sig('oa_segment_sort_keys', C.c_int, _vp, _i64, _vp, C.c_int, _vp, _vp, _vp,
+     _vp, _vp, _vp)
+_sig('oa_run_heads', C.c_int, _vp, _vp, _i64, _vp, _vp)
+_sig('oa_run_lengths', C.c_int, _vp, _i64, _i64, _vp, _vp)
 _sig('oa_synth_keys', C.c_int, C.POINTER(SynthParams), _vp, _vp, _vp, _vp)
 _sig('oa_synth_fill', C.c_int, C.POINTER(SynthParams), _vp, _i64, C.c_int,
      _vp, _vp, _vp, _vp)
@@ -131,7 +137,7 @@ if lib.oa_synth_params_size() != C.sizeof(SynthParams):
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
-    'oa_table_slots', 'oa_index_bits', 'oa_bulk_workspace_bytes',
+    'oa_table_slots', 'oa_table_bucket_begin', 'oa_index_bits', 'oa_bulk_workspace_bytes',
     'oa_bulk_velocity', 'oa_track_fused', 'oa_track_args_size', 'oa_table_clear',
     'oa_select_workspace_bytes',
     'oa_select_count', 'oa_select_gather', 'oa_segment_offsets',
@@ -139,7 +145,8 @@ EXPORTS = [
     'oa_mark_unmatched', 'oa_fill_u16', 'oa_set_record_angles',
     'oa_sort_workspace_bytes',
     'oa_sort_pairs_u64', 'oa_minmax_i64', 'oa_synth_keys', 'oa_synth_fill',
-    'oa_synth_params_size',
+    'oa_synth_params_size', 'oa_segment_sort_keys', 'oa_run_heads',
+    'oa_run_lengths',
 ]
 
 

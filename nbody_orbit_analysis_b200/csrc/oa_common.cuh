@@ -53,8 +53,6 @@ OA_HD uint64_t oa_mix64(uint64_t x) {
     return x;
 }
 
-constexpr uint32_t OA_EMPTY = 0xFFFFFFFFu;
-
 // slot of a hash in a table segment of `cap` slots (Lemire range reduction)
 OA_HD uint32_t oa_slot(uint32_t h, uint32_t cap) {
     return (uint32_t)(((uint64_t)h * (uint64_t)cap) >> 32);

@@ -106,13 +106,23 @@ sel_gather_kernel(const uint16_t* __restrict__ marks, int64_t n, int op,
     }
 }
 
+// Every consumer of a selection takes `n_sel` (a host-side upper bound) and an
+// optional device pointer `n_dev` to the exact count, so that a whole snapshot
+// can be enqueued without a host synchronisation in the middle.
+OA_D int64_t actual_count(int64_t n_sel, const int64_t* __restrict__ n_dev) {
+    if (n_dev == nullptr) return n_sel;
+    const int64_t v = __ldg(n_dev);
+    return v < n_sel ? v : n_sel;
+}
+
 __global__ void seg_offsets_kernel(const int64_t* __restrict__ sel, int64_t n_sel,
+                                   const int64_t* __restrict__ n_dev,
                                    const int64_t* __restrict__ seg_begin, int n_seg,
                                    int64_t* __restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_seg) return;
     const int64_t key = seg_begin[k];
-    int64_t lo = 0, hi = n_sel;          // first index with sel[i] >= key
+    int64_t lo = 0, hi = actual_count(n_sel, n_dev);   // first i with sel[i] >= key
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
         if (sel[mid] < key) lo = mid + 1; else hi = mid;
@@ -123,16 +133,18 @@ __global__ void seg_offsets_kernel(const int64_t* __restrict__ sel, int64_t n_se
 template <typename TF>
 __global__ void gather_rec_ids_kernel(const OaRec<TF>* __restrict__ rec,
                                       const int64_t* __restrict__ sel, int64_t n_sel,
+                                      const int64_t* __restrict__ n_dev,
                                       int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_sel) out[i] = rec[sel[i]].id;
+    if (i < actual_count(n_sel, n_dev)) out[i] = rec[sel[i]].id;
 }
 
 template <typename T>
 __global__ void gather_kernel(const T* __restrict__ src, const int64_t* __restrict__ sel,
-                              int64_t n_sel, T* __restrict__ out) {
+                              int64_t n_sel, const int64_t* __restrict__ n_dev,
+                              T* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_sel) out[i] = src[sel[i]];
+    if (i < actual_count(n_sel, n_dev)) out[i] = src[sel[i]];
 }
 
 __global__ void mark_unmatched_kernel(const int64_t* __restrict__ match, int64_t n,
@@ -212,65 +224,69 @@ extern "C" int oa_select_gather(const uint16_t* marks, int64_t n, int op,
 }
 
 extern "C" int oa_segment_offsets(const int64_t* sel, int64_t n_sel,
-                                  const int64_t* seg_begin, int n_seg,
-                                  int64_t* offsets_out, void* stream) {
+                                  const int64_t* n_dev, const int64_t* seg_begin,
+                                  int n_seg, int64_t* offsets_out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_seg <= 0) return OA_OK;
     OA_REQUIRE(seg_begin && offsets_out && (sel || n_sel == 0),
                "oa_segment_offsets: NULL pointer");
     seg_offsets_kernel<<<blocks_for(n_seg, 128), 128, 0, st>>>(
-        sel, n_sel, seg_begin, n_seg, offsets_out);
+        sel, n_sel, n_dev, seg_begin, n_seg, offsets_out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }
 
 extern "C" int oa_gather_record_ids(const void* rec, int frame_dtype,
                                     const int64_t* sel, int64_t n_sel,
-                                    int64_t* ids_out, void* stream) {
+                                    const int64_t* n_dev, int64_t* ids_out,
+                                    void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_sel <= 0) return OA_OK;
     OA_REQUIRE(rec && sel && ids_out, "oa_gather_record_ids: NULL pointer");
     if (frame_dtype == OA_F64)
         gather_rec_ids_kernel<double><<<blocks_for(n_sel, 256), 256, 0, st>>>(
-            static_cast<const OaRec<double>*>(rec), sel, n_sel, ids_out);
+            static_cast<const OaRec<double>*>(rec), sel, n_sel, n_dev, ids_out);
     else
         gather_rec_ids_kernel<float><<<blocks_for(n_sel, 256), 256, 0, st>>>(
-            static_cast<const OaRec<float>*>(rec), sel, n_sel, ids_out);
+            static_cast<const OaRec<float>*>(rec), sel, n_sel, n_dev, ids_out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }
 
 extern "C" int oa_gather_u16(const uint16_t* src, const int64_t* sel, int64_t n_sel,
-                             uint16_t* out, void* stream) {
+                             const int64_t* n_dev, uint16_t* out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_sel <= 0) return OA_OK;
     OA_REQUIRE(src && sel && out, "oa_gather_u16: NULL pointer");
-    gather_kernel<uint16_t><<<blocks_for(n_sel, 256), 256, 0, st>>>(src, sel, n_sel, out);
+    gather_kernel<uint16_t><<<blocks_for(n_sel, 256), 256, 0, st>>>(src, sel, n_sel,
+                                                                    n_dev, out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }
 
 extern "C" int oa_gather_i64(const int64_t* src, const int64_t* sel, int64_t n_sel,
-                             int64_t* out, void* stream) {
+                             const int64_t* n_dev, int64_t* out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_sel <= 0) return OA_OK;
     OA_REQUIRE(src && sel && out, "oa_gather_i64: NULL pointer");
-    gather_kernel<int64_t><<<blocks_for(n_sel, 256), 256, 0, st>>>(src, sel, n_sel, out);
+    gather_kernel<int64_t><<<blocks_for(n_sel, 256), 256, 0, st>>>(src, sel, n_sel,
+                                                                   n_dev, out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }
 
 extern "C" int oa_gather_f(const void* src, int dtype, const int64_t* sel,
-                           int64_t n_sel, void* out, void* stream) {
+                           int64_t n_sel, const int64_t* n_dev, void* out,
+                           void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_sel <= 0) return OA_OK;
     OA_REQUIRE(src && sel && out, "oa_gather_f: NULL pointer");
     if (dtype == OA_F64)
         gather_kernel<double><<<blocks_for(n_sel, 256), 256, 0, st>>>(
-            static_cast<const double*>(src), sel, n_sel, static_cast<double*>(out));
+            static_cast<const double*>(src), sel, n_sel, n_dev, static_cast<double*>(out));
     else
         gather_kernel<float><<<blocks_for(n_sel, 256), 256, 0, st>>>(
-            static_cast<const float*>(src), sel, n_sel, static_cast<float*>(out));
+            static_cast<const float*>(src), sel, n_sel, n_dev, static_cast<float*>(out));
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

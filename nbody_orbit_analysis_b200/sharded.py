@@ -110,7 +110,7 @@ class Comm:
         E = res.n_events
         sel = res.apsis_prev_index
         keys = torch.empty(max(E, 1), dtype=torch.int64, device=self.device)
-        check(lib.oa_gather_i64(ptr(gen.gpos), ptr(sel), E, ptr(keys), st))
+        check(lib.oa_gather_i64(ptr(gen.gpos), ptr(sel), E, None, ptr(keys), st))
         ids = torch.from_numpy(
             res.apsis_ids.astype(np.int64, copy=False)).to(self.device)
         ang = torch.from_numpy(
@@ -125,8 +125,10 @@ class Comm:
                             device=self.device)
         ang_o = torch.empty(max(total, 1), dtype=torch.int16,
                             device=self.device)
-        check(lib.oa_gather_i64(ptr(ids), ptr(perm), total, ptr(ids_o), st))
-        check(lib.oa_gather_u16(ptr(ang), ptr(perm), total, ptr(ang_o), st))
+        check(lib.oa_gather_i64(ptr(ids), ptr(perm), total, None, ptr(ids_o),
+                                 st))
+        check(lib.oa_gather_u16(ptr(ang), ptr(perm), total, None, ptr(ang_o),
+                                 st))
         tracker.launches += 3
         res.apsis_ids = ids_o[:total].cpu().numpy().astype(
             gen.ids_dtype, copy=False)

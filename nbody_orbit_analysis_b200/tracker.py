@@ -1,12 +1,16 @@
 """Device-side state machine of the orbit-tracking path.
 
-``OrbitTracker.step()`` is the GPU replacement of one iteration of the
-reference's per-snapshot loop body (reference ``track_orbits.py:147-217``: the
-per-halo ``track(j)`` calls plus result assembly).  It stages one snapshot in
-HBM, launches the fused tracking kernel and the ordered event compaction
-through the C ABI (``_lib``) and returns the small arrays the writer needs.
+``OrbitTracker`` is the GPU replacement of one iteration of the reference's
+per-snapshot loop body (reference ``track_orbits.py:147-217``: the per-halo
+``track(j)`` calls plus result assembly).  ``submit`` stages one snapshot in HBM
+and enqueues, without any host synchronisation, the fused tracking kernel, the
+ordered event compaction and the device->host copy of the small result arrays;
+``collect`` waits for that snapshot's results.  Calling ``submit`` for snapshot
+s+1 before ``collect`` for snapshot s overlaps the host side (user callbacks,
+file writing, D2H) with GPU work.  ``step`` = ``submit`` + ``collect``.
 
-PyTorch is used for device/pinned buffers and streams only.
+PyTorch is used for device/pinned buffers, streams and events only; every
+kernel is launched through the C ABI (``_lib``).
 """
 import ctypes as C
 
@@ -30,13 +34,18 @@ class Generation:
     """Carried state of one processed snapshot (reference
     ``track_orbits.py:234-240``), resident in HBM."""
     __slots__ = ('n', 'rec', 'tab', 'mark', 'index_bits', 'offsets',
-                 'halo_exists', 'frame_f64', 'ids_dtype', 'gpos')
+                 'halo_exists', 'frame_f64', 'ids_dtype', 'gpos', 'buckets')
 
 
 class StepResult:
     __slots__ = ('n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
                  'apsis_prev_index', 'prev_gen')
+
+
+class Pending:
+    """A submitted snapshot whose results have not been collected yet."""
+    pass
 
 
 def _as_f(arr, name):
@@ -74,13 +83,31 @@ class OrbitTracker:
         self.launches = 0          # kernels launched through the C ABI
         self.timing = None         # list of (start, stop, n) CUDA events of
         #                            the fused kernel when profiling is on
+        self.copy_stream = torch.cuda.Stream(self.device)
 
     # -- buffers -------------------------------------------------------------
     def _empty(self, n, dtype):
-        return torch.empty(int(n), dtype=dtype, device=self.device)
+        """Uninitialised device buffer.  Sizes are rounded up to 1/8-octave
+        bins so that torch's caching allocator sees the same few block sizes
+        every snapshot (particle counts drift by a few per cent from snapshot
+        to snapshot; unbinned requests fragment the cache and fall back to
+        synchronising cudaMalloc/cudaFree calls)."""
+        n = int(n)
+        item = torch.empty(0, dtype=dtype).element_size()
+        nbytes = n * item
+        if nbytes > (1 << 20):
+            step = (1 << (nbytes - 1).bit_length()) >> 3
+            nbytes = -(-nbytes // step) * step
+        else:
+            nbytes = -(-max(nbytes, 1) // 512) * 512
+        raw = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return raw[:n * item].view(dtype)
+
+    def _main(self):
+        return torch.cuda.current_stream(self.device)
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(self._main().cuda_stream)
 
     def _to_device(self, arr, dtype=None):
         """Host numpy array -> device tensor through pinned staging."""
@@ -96,6 +123,16 @@ class OrbitTracker:
             t = buf
         return t.to(self.device, non_blocking=True)
 
+    def _to_host_async(self, t, n=None):
+        """Device tensor -> pinned host tensor on the copy stream (the caller
+        synchronises before reading)."""
+        n = t.numel() if n is None else int(n)
+        h = torch.empty(n, dtype=t.dtype, pin_memory=True)
+        if n:
+            with torch.cuda.stream(self.copy_stream):
+                h.copy_(t[:n], non_blocking=True)
+        return h
+
     # -- one snapshot ----------------------------------------------------------
     def step(self, snapshot, halo_exists, region_positions, region_bulk_vels,
              H=0.0, want_angles=False, diagnostics=False, gpos=None):
@@ -105,6 +142,12 @@ class OrbitTracker:
         (``track_orbits.py:147-155``).  Returns a ``StepResult``; its event
         fields are ``None`` for a snapshot without a previous generation.
         """
+        return self.collect(self.submit(
+            snapshot, halo_exists, region_positions, region_bulk_vels, H,
+            want_angles, diagnostics, gpos))
+
+    def submit(self, snapshot, halo_exists, region_positions, region_bulk_vels,
+               H=0.0, want_angles=False, diagnostics=False, gpos=None):
         coords = _as_f(snapshot['coordinates'], 'coordinates')
         vels = _as_f(snapshot['velocities'], 'velocities')
         if coords.dtype != vels.dtype:
@@ -121,7 +164,7 @@ class OrbitTracker:
         }
         offsets = np.concatenate((
             np.asarray(snapshot['region_offsets'], dtype=np.int64), [n]))
-        return self.step_device(
+        return self.submit_device(
             dev, n, coords.dtype, ids.dtype, offsets, halo_exists,
             region_positions, region_bulk_vels, H,
             box_size=snapshot.get('box_size'),
@@ -130,11 +173,15 @@ class OrbitTracker:
             want_angles=want_angles, diagnostics=diagnostics,
             gpos=self._to_device(gpos, np.int64) if gpos is not None else None)
 
-    def step_device(self, dev, n, data_dtype, ids_dtype, offsets, halo_exists,
-                    region_positions, region_bulk_vels, H, box_size=None,
-                    redshift=0.0, mass_dtype=None, want_angles=False,
-                    diagnostics=False, gpos=None, finalize=True):
-        """Same as ``step`` with the particle arrays already in HBM
+    def step_device(self, *args, **kw):
+        """``submit_device`` + ``collect``."""
+        return self.collect(self.submit_device(*args, **kw))
+
+    def submit_device(self, dev, n, data_dtype, ids_dtype, offsets,
+                      halo_exists, region_positions, region_bulk_vels, H,
+                      box_size=None, redshift=0.0, mass_dtype=None,
+                      want_angles=False, diagnostics=False, gpos=None):
+        """Same as ``submit`` with the particle arrays already in HBM
         (``dev`` = dict of flat torch tensors ``pos``, ``vel``, ``ids``,
         optional ``mass``)."""
         st = self._stream()
@@ -169,6 +216,11 @@ class OrbitTracker:
             k = pos_c[matched]
             rows['prev_begin'][matched] = prev.offsets[k]
             rows['prev_count'][matched] = prev.offsets[k + 1] - prev.offsets[k]
+            rows['prev_bucket'][matched] = prev.buckets[k]
+        # closed-form bucket ranges of this snapshot's table (see
+        # oa_table_bucket_begin in include/orbit_b200.h)
+        buckets = (2 * offsets[:-1]) // 7 + np.arange(n_h, dtype=np.int64)
+        rows['cur_bucket'] = buckets
         derive_bulk = region_bulk_vels is None
         if not derive_bulk:
             bulk = np.asarray(region_bulk_vels)
@@ -179,9 +231,23 @@ class OrbitTracker:
             bulk_dtype = data_dtype if mass_dtype is None else np.result_type(
                 data_dtype, mass_dtype)
         bulk_f32 = bulk_dtype == np.float32
+        seg_begin = np.ascontiguousarray(rows['prev_begin'][matched])
+        n_m = len(seg_begin)
 
-        d_off = self._to_device(offsets)
-        d_rows = self._to_device(rows.view(np.uint8))
+        # one packed host->device copy: [rows | offsets | seg_begin]
+        nb_rows, nb_off = 80 * n_h, 8 * (n_h + 1)
+        pack = torch.empty(nb_rows + nb_off + 8 * max(n_m, 1),
+                           dtype=torch.uint8, pin_memory=True)
+        hp = pack.numpy()
+        hp[:nb_rows] = rows.view(np.uint8)
+        hp[nb_rows:nb_rows + nb_off] = offsets.view(np.uint8)
+        hp[nb_rows + nb_off:nb_rows + nb_off + 8 * n_m] = \
+            seg_begin.view(np.uint8)
+        d_pack = pack.to(self.device, non_blocking=True)
+        d_rows = d_pack[:nb_rows]
+        d_off = d_pack[nb_rows:nb_rows + nb_off]
+        d_seg = d_pack[nb_rows + nb_off:]
+
         d_bulk_out = None
         if derive_bulk:
             ws_bytes = lib.oa_bulk_workspace_bytes(n, n_h)
@@ -204,9 +270,10 @@ class OrbitTracker:
         gen.halo_exists = halo_exists
         gen.index_bits = lib.oa_index_bits(int(lens.max()) if n_h else 0)
         gen.gpos = gpos
+        gen.buckets = buckets
         rec_bytes = lib.oa_record_bytes(int(frame_f64))
         gen.rec = self._empty(max(n, 1) * rec_bytes, torch.uint8)
-        gen.tab = self._empty(lib.oa_table_slots(n), torch.int32)
+        gen.tab = self._empty(lib.oa_table_slots(n, n_h), torch.int32)
         gen.mark = self._empty(max(n, 1) + 8, torch.int16)
 
         fdt = torch.float64 if frame_f64 else torch.float32
@@ -258,70 +325,112 @@ class OrbitTracker:
                 ptr(diag['vr']), ptr(diag['r'])
             a.out_match = ptr(diag['match'])
         a.dangle_prev = ptr(dangle)
-        check(lib.oa_table_clear(ptr(gen.tab), n, st))
+        check(lib.oa_table_clear(ptr(gen.tab), n, n_h, st))
         if self.timing is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), \
                 torch.cuda.Event(enable_timing=True)
-            ev0.record(torch.cuda.current_stream(self.device))
+            ev0.record(self._main())
         check(lib.oa_track_fused(C.byref(a), st))
         if self.timing is not None:
-            ev1.record(torch.cuda.current_stream(self.device))
+            ev1.record(self._main())
             self.timing.append((ev0, ev1, n))
         self.launches += 2
 
+        p = Pending()
+        p.n, p.n_h, p.n_m = n, n_h, n_m
+        p.gen, p.prev, p.matched = gen, prev, matched
+        p.diag, p.dangle = diag, dangle
+        p.derive_bulk, p.bulk_dtype = derive_bulk, bulk_dtype
+        p.region_bulk_vels = region_bulk_vels
+        p.keep = (dev, d_pack, a)       # inputs stay alive until collected
+        p.h_bulk = p.h_angle = p.h_small = None
+        p.sel = p.d_ids = p.d_ang = None
+
+        # ---- ordered event compaction, all enqueued without a host sync -------
+        if prev is not None and not self.onthefly:
+            cap = max(min(prev.n, n), 1)
+            ws_bytes = lib.oa_select_workspace_bytes(prev.n)
+            ws = self._empty(ws_bytes, torch.uint8)
+            d_small = self._empty(n_m + 1, torch.int64)   # offsets..., total
+            d_total = d_small[n_m:]
+            check(lib.oa_select_count(
+                ptr(prev.mark), prev.n, _lib.OA_SEL_NE, _lib.OA_NO_EVENT,
+                ptr(ws), ws_bytes, ptr(d_total), st))
+            p.sel = self._empty(cap, torch.int64)
+            p.d_ids = self._empty(cap, torch.int64)
+            p.d_ang = self._empty(cap, torch.int16)
+            check(lib.oa_select_gather(
+                ptr(prev.mark), prev.n, _lib.OA_SEL_NE, _lib.OA_NO_EVENT,
+                ptr(ws), ptr(p.sel), st))
+            check(lib.oa_segment_offsets(
+                ptr(p.sel), cap, ptr(d_total), ptr(d_seg), n_m, ptr(d_small),
+                st))
+            check(lib.oa_gather_record_ids(
+                ptr(prev.rec), int(prev.frame_f64), ptr(p.sel), cap,
+                ptr(d_total), ptr(p.d_ids), st))
+            check(lib.oa_gather_u16(ptr(prev.mark), ptr(p.sel), cap,
+                                    ptr(d_total), ptr(p.d_ang), st))
+            self.launches += 6
+            p.keep += (ws, d_small)
+        else:
+            d_small = None
+
+        # ---- small device->host copies on the copy stream ----------------------
+        done = torch.cuda.Event()
+        done.record(self._main())
+        self.copy_stream.wait_event(done)
+        if d_small is not None:
+            p.h_small = self._to_host_async(d_small)
+        if derive_bulk:
+            p.h_bulk = self._to_host_async(d_bulk_out, 3 * n_h)
+            p.keep += (d_bulk_out,)
+        if out_angle is not None:
+            p.h_angle = self._to_host_async(out_angle, n)
+            p.keep += (out_angle,)
+        p.small_done = torch.cuda.Event()
+        p.small_done.record(self.copy_stream)
+        self.prev = gen
+        return p
+
+    def collect_keep(self, p):
+        """``collect`` that leaves the snapshot's device inputs and per-particle
+        outputs (``p.keep``, ``p.diag``, ``p.dangle``) alive for the caller."""
+        return self.collect(p, release=False)
+
+    def collect(self, p, release=True):
+        """Wait for a submitted snapshot and return its ``StepResult``."""
         res = StepResult()
-        res.n = n
-        res.diag = diag
-        res.hinds = np.flatnonzero(matched)
+        res.n = p.n
+        res.diag = p.diag
+        res.hinds = np.flatnonzero(p.matched)
         res.apsis_ids = res.apsis_angles = res.apsis_offsets = None
         res.apsis_prev_index = None
         res.n_events = 0
         res.angles = None
-        res.prev_gen = prev
-        pending = {'gen': gen, 'prev': prev, 'rows': rows, 'matched': matched,
-                   'd_bulk_out': d_bulk_out, 'derive_bulk': derive_bulk,
-                   'bulk_dtype': bulk_dtype, 'region_bulk_vels':
-                   region_bulk_vels, 'out_angle': out_angle, 'dangle': dangle,
-                   'n_h': n_h}
-        self.prev = gen
-        if finalize:
-            return self.finalize(res, pending)
-        return res, pending
-
-    def finalize(self, res, pending):
-        """Ordered event compaction + device->host of the (small) results."""
-        st = self._stream()
-        prev, rows, matched = pending['prev'], pending['rows'], \
-            pending['matched']
-        n_h = pending['n_h']
-        if pending['derive_bulk']:
-            b = pending['d_bulk_out'][:3 * n_h].cpu().numpy().reshape(n_h, 3)
-            res.bulk_velocities = b.astype(pending['bulk_dtype'])
+        res.prev_gen = p.prev
+        p.small_done.synchronize()
+        if p.derive_bulk:
+            res.bulk_velocities = p.h_bulk.numpy().reshape(p.n_h, 3).astype(
+                p.bulk_dtype)
         else:
-            res.bulk_velocities = np.asarray(pending['region_bulk_vels'])
-        if pending['out_angle'] is not None:
-            res.angles = pending['out_angle'][:res.n].cpu().numpy().view(
-                np.float16)
-        if prev is None:
-            return res
-        sel, total = self.select(prev.mark, prev.n, _lib.OA_SEL_NE,
-                                 _lib.OA_NO_EVENT)
-        seg = rows['prev_begin'][matched]
-        res.apsis_offsets = np.concatenate(
-            (self.segment_offsets(sel, total, seg), [total])).astype(np.int64)
-        d_ids = self._empty(max(total, 1), torch.int64)
-        d_ang = self._empty(max(total, 1), torch.int16)
-        check(lib.oa_gather_record_ids(
-            ptr(prev.rec), int(prev.frame_f64), ptr(sel), total, ptr(d_ids),
-            st))
-        check(lib.oa_gather_u16(ptr(prev.mark), ptr(sel), total, ptr(d_ang),
-                                st))
-        self.launches += 2
-        res.n_events = total
-        res.apsis_ids = d_ids[:total].cpu().numpy().astype(
-            prev.ids_dtype, copy=False)
-        res.apsis_angles = d_ang[:total].cpu().numpy().view(np.float16)
-        res.apsis_prev_index = sel[:total] if total else sel[:0]
+            res.bulk_velocities = np.asarray(p.region_bulk_vels)
+        if p.h_angle is not None:
+            res.angles = p.h_angle.numpy().view(np.float16)
+        if p.h_small is not None:
+            small = p.h_small.numpy()
+            total = int(small[p.n_m])
+            res.apsis_offsets = small.copy()
+            h_ids = self._to_host_async(p.d_ids, total)
+            h_ang = self._to_host_async(p.d_ang, total)
+            self.copy_stream.synchronize()
+            res.n_events = total
+            ids = h_ids.numpy()
+            res.apsis_ids = ids if p.prev.ids_dtype == np.int64 else \
+                ids.astype(p.prev.ids_dtype)
+            res.apsis_angles = h_ang.numpy().view(np.float16)
+            res.apsis_prev_index = p.sel[:total]
+        if release:
+            p.keep = None
         return res
 
     def load_angles(self, angles):
@@ -337,7 +446,7 @@ class OrbitTracker:
                                        gen.n, self._stream()))
         self.launches += 1
 
-    # -- helpers shared with the on-the-fly driver -----------------------------
+    # -- synchronous helpers (on-the-fly driver, tests) -------------------------
     def select(self, marks, n, op, value):
         """Ascending positions i < n with ``marks[i] (op) value`` (device
         int64 tensor) and their count."""
@@ -347,7 +456,7 @@ class OrbitTracker:
         d_total = self._empty(1, torch.int64)
         check(lib.oa_select_count(ptr(marks), n, op, value, ptr(ws), ws_bytes,
                                   ptr(d_total), st))
-        total = int(d_total.item())        # the one host sync of a snapshot
+        total = int(d_total.item())
         sel = self._empty(max(total, 1), torch.int64)
         if total:
             check(lib.oa_select_gather(ptr(marks), n, op, value, ptr(ws),
@@ -363,7 +472,7 @@ class OrbitTracker:
             return np.zeros(0, dtype=np.int64)
         d_seg = self._to_device(seg_begin)
         d_out = self._empty(len(seg_begin), torch.int64)
-        check(lib.oa_segment_offsets(ptr(sel), total, ptr(d_seg),
+        check(lib.oa_segment_offsets(ptr(sel), total, None, ptr(d_seg),
                                      len(seg_begin), ptr(d_out), st))
         self.launches += 1
         return d_out.cpu().numpy()

@@ -27,10 +27,20 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.oa_track_args_size() == C.sizeof(_lib.TrackArgs)
     assert _lib.lib.oa_record_bytes(0) == 32
     assert _lib.lib.oa_record_bytes(1) == 64
-    # index bits reserve the all-ones pattern for the empty slot
-    for n in (0, 1, 2, 3, 7, 8, 1000, 2**20):
+    # index bits hold every block-local index 0 .. n-1
+    for n in (0, 1, 2, 3, 7, 8, 9, 1000, 2**20, 2**20 + 1):
         b = _lib.lib.oa_index_bits(n)
-        assert (1 << b) - 1 > n and (b == 1 or (1 << (b - 1)) - 1 <= n)
+        assert (1 << b) >= n and (b == 1 or (1 << (b - 1)) < n)
+    # bucket ranges of consecutive blocks never overlap
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 50, 2000)
+    off = np.concatenate(([0], np.cumsum(lens)))
+    begin = np.array([_lib.lib.oa_table_bucket_begin(int(off[j]), j)
+                      for j in range(len(lens))])
+    nb = (2 * lens) // 7 + 1
+    assert np.all(begin[1:] >= begin[:-1] + nb[:-1])
+    assert (begin[-1] + nb[-1]) * 8 <= _lib.lib.oa_table_slots(
+        int(off[-1]), len(lens))
 
 
 def test_no_cpu_fallback_without_a_device():
