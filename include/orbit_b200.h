@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 5
+#define OA_ABI_VERSION 7
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -63,18 +63,29 @@ typedef struct oa_region {
     int64_t prev_count;  /* its length (0 when there is no previous block)    */
     int64_t prev_bucket; /* oa_table_bucket_begin() of that previous block    */
     int64_t cur_bucket;  /* oa_table_bucket_begin() of this block             */
-} oa_region;             /* 80 bytes */
+    int64_t cur_begin;   /* first particle of this block (= cur_off[j])       */
+    int64_t cur_count;   /* its length                                        */
+    float centre_f[3];   /* (float)centre: used when the frame is float32     */
+    float bulk_f[3];     /* (float)bulk  (oa_bulk_velocity keeps it in sync)  */
+    int64_t reserved;
+} oa_region;             /* 128 bytes; the table must be 16-byte aligned      */
 
 /* Bytes of one carried-state record (32 for an OA_F32 frame, 64 for OA_F64). */
 size_t oa_record_bytes(int frame_dtype);
 
-/* ID hash table of one snapshot: 32-byte buckets {count, 7 slots}; the buckets
+/* ID hash table of one snapshot (one uint32 array):
+ *   [ fill counters, one uint32 per bucket, padded to a multiple of 8 words |
+ *     slot buckets, 8 uint32 slots (one 32-byte sector) per bucket ]
+ * slot = fingerprint << index_bits | block-local particle index.  The buckets
  * of region block j (start `block_start`, length len) are
- *   [oa_table_bucket_begin(block_start, j), ... + (2*len)/7 + 1).            */
+ *   [oa_table_bucket_begin(block_start, j), ... + len/4 + 1).
+ * Only the counters need clearing between snapshots (oa_table_clear).        */
 #define OA_BUCKET_WORDS 8
-#define OA_BUCKET_SLOTS 7
+#define OA_BUCKET_SLOTS 8
 int64_t oa_table_bucket_begin(int64_t block_start, int64_t region_index);
-/* Number of uint32 words of the table for n region-particles in n_regions. */
+/* Number of buckets of the table for n region-particles in n_regions. */
+int64_t oa_table_buckets(int64_t n, int64_t n_regions);
+/* Number of uint32 words of that table (counters + slots). */
 int64_t oa_table_slots(int64_t n, int64_t n_regions);
 /* Bits needed to store a block-local particle index given the largest block. */
 int oa_index_bits(int64_t max_block_len);
@@ -141,14 +152,18 @@ typedef struct oa_track_args {
     /* previous generation (read) */
     const void* rec_prev;   /* (n_prev,) records, NULL if none                */
     const uint32_t* tab_prev; /* table filled by the previous call             */
+    int64_t tab_prev_buckets; /* oa_table_buckets() of that table              */
     int64_t n_prev;
     int32_t prev_index_bits;
     int32_t cur_index_bits;
     uint16_t* mark_prev;    /* (n_prev,) event marks, updated                 */
     /* current generation (written) */
     void* rec_cur;          /* (n_cur,) records                               */
-    uint32_t* tab_cur;      /* oa_table_slots() words, cleared beforehand      */
-    uint16_t* mark_cur;     /* (n_cur,) initialised to "no event"             */
+    uint32_t* tab_cur;      /* oa_table_slots() words, oa_table_clear()ed      */
+    int64_t tab_cur_buckets; /* oa_table_buckets(n_cur, n_regions)             */
+    uint16_t* mark_cur;     /* (n_cur,) written: "no event"                   */
+    void* workspace;        /* oa_track_workspace_bytes(n_cur) bytes          */
+    size_t workspace_bytes;
     /* optional per-particle outputs, NULL to skip */
     void* out_rhat;         /* (n_cur,3) frame_dtype                          */
     void* out_vr;           /* (n_cur,) float64 (float32 if onthefly && F32)  */
@@ -159,9 +174,10 @@ typedef struct oa_track_args {
 } oa_track_args;
 
 int oa_track_fused(const oa_track_args* args, void* stream);
-/* Zero all oa_table_slots(n, n_regions) words of a table.  Must precede the
- * oa_track_fused call that fills `tab_cur` (kept separate so that the fused
- * kernel can be timed on its own). */
+size_t oa_track_workspace_bytes(int64_t n_cur);
+/* Zero the fill counters of a table of oa_table_slots(n, n_regions) words.
+ * Must precede the oa_track_fused call that fills `tab_cur` (kept separate so
+ * that the fused kernel can be timed on its own). */
 int oa_table_clear(uint32_t* tab, int64_t n, int64_t n_regions, void* stream);
 /* sizeof(oa_track_args) as compiled -- lets a binding verify its struct mirror. */
 size_t oa_track_args_size(void);

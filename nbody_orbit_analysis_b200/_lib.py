@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 5
+ABI_VERSION = 7
 
 
 class OrbitB200Error(RuntimeError):
@@ -45,12 +45,15 @@ def _load():
 lib = _load()
 LIB_PATH = _build.LIB
 
-# numpy view of `oa_region` (80 bytes)
+# numpy view of `oa_region` (128 bytes)
 REGION_DTYPE = np.dtype([
     ('centre', np.float64, (3,)), ('bulk', np.float64, (3,)),
     ('prev_begin', np.int64), ('prev_count', np.int64),
-    ('prev_bucket', np.int64), ('cur_bucket', np.int64)])
-assert REGION_DTYPE.itemsize == 80
+    ('prev_bucket', np.int64), ('cur_bucket', np.int64),
+    ('cur_begin', np.int64), ('cur_count', np.int64),
+    ('centre_f', np.float32, (3,)), ('bulk_f', np.float32, (3,)),
+    ('reserved', np.int64)])
+assert REGION_DTYPE.itemsize == 128
 
 _vp, _i64, _i32, _sz, _u16 = (C.c_void_p, C.c_int64, C.c_int32, C.c_size_t,
                               C.c_uint16)
@@ -66,10 +69,12 @@ class TrackArgs(C.Structure):
         ('onthefly', _i32), ('mode', _i32),
         ('box', C.c_double * 3), ('hubble', C.c_double),
         ('one_plus_z', C.c_double),
-        ('rec_prev', _vp), ('tab_prev', _vp), ('n_prev', _i64),
+        ('rec_prev', _vp), ('tab_prev', _vp), ('tab_prev_buckets', _i64),
+        ('n_prev', _i64),
         ('prev_index_bits', _i32), ('cur_index_bits', _i32),
         ('mark_prev', _vp),
-        ('rec_cur', _vp), ('tab_cur', _vp), ('mark_cur', _vp),
+        ('rec_cur', _vp), ('tab_cur', _vp), ('tab_cur_buckets', _i64),
+        ('mark_cur', _vp), ('workspace', _vp), ('workspace_bytes', _sz),
         ('out_rhat', _vp), ('out_vr', _vp), ('out_r', _vp),
         ('out_angle', _vp), ('out_match', _vp), ('dangle_prev', _vp),
     ]
@@ -98,6 +103,8 @@ _sig('oa_device_info', C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
      C.POINTER(C.c_int), C.POINTER(_i64), C.POINTER(_i64))
 _sig('oa_record_bytes', _sz, C.c_int)
 _sig('oa_table_slots', _i64, _i64, _i64)
+_sig('oa_table_buckets', _i64, _i64, _i64)
+_sig('oa_track_workspace_bytes', _sz, _i64)
 _sig('oa_table_bucket_begin', _i64, _i64, _i64)
 _sig('oa_index_bits', C.c_int, _i64)
 _sig('oa_bulk_workspace_bytes', _sz, _i64, C.c_int)
@@ -137,7 +144,8 @@ if lib.oa_synth_params_size() != C.sizeof(SynthParams):
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
-    'oa_table_slots', 'oa_table_bucket_begin', 'oa_index_bits', 'oa_bulk_workspace_bytes',
+    'oa_table_slots', 'oa_table_buckets', 'oa_track_workspace_bytes',
+    'oa_table_bucket_begin', 'oa_index_bits', 'oa_bulk_workspace_bytes',
     'oa_bulk_velocity', 'oa_track_fused', 'oa_track_args_size', 'oa_table_clear',
     'oa_select_workspace_bytes',
     'oa_select_count', 'oa_select_gather', 'oa_segment_offsets',

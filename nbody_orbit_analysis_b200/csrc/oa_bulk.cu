@@ -123,6 +123,7 @@ bulk_finalize_kernel(const double4* __restrict__ partial,
         for (int k = 0; k < 3; ++k) {
             if (round_f32) b[k] = (double)(float)b[k];
             regions[j].bulk[k] = b[k];
+            regions[j].bulk_f[k] = (float)b[k];
             if (bulk_out) bulk_out[3 * j + k] = b[k];
         }
     }

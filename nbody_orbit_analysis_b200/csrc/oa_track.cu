@@ -6,23 +6,33 @@
 // See include/orbit_b200.h (oa_track_fused) for the contract and DESIGN.md for
 // the memory layout and the roofline accounting.
 //
-// Matching: a region-segmented, bucketised hash table in global memory that
-// stays in B200's 126 MB L2 while a block is being processed.  A bucket is one
-// 32-byte sector = {count, 7 slots}; slot = fingerprint | block-local index.
-//   insert : k = atomicAdd(bucket.count, 1); bucket.slot[k] = value   (1 atomic)
-//   probe  : one sector read, fingerprint compare in registers, then the 32 B
-//            record of the candidate -- which carries the 64-bit ID for the
-//            exact check AND rhat / v_r / angle, so match + state read is one
-//            gather.  Overflow (count > 7, <1 % of keys) spills to the next
-//            bucket of the same region.
-// Everything that is touched once (ids / positions / velocities / records /
-// marks) is loaded and stored with an L2 evict-first policy so that only the
-// tables compete for L2.
+// Structure: a persistent kernel, one 1024-thread CTA per SM, in which every
+// WARP is an autonomous software pipeline over chunks of 32 consecutive
+// particles (chunk c -> warp c mod #warps, so the warps of the whole GPU sweep
+// the snapshot as one compact front).  A warp owns a ring of D shared-memory
+// slots with one mbarrier each; lane 0 fills slot t mod D with four 1-D TMA bulk
+// copies (cp.async.bulk ... mbarrier::complete_tx, L2 evict-first): ids,
+// positions, velocities and the oa_region rows the chunk touches.  D chunks of
+// inputs are therefore in flight per warp while the dependent chain of the
+// current chunk
+//      bucket (L2) -> previous record (L2/HBM) -> new record (HBM)
+// is outstanding.  There is no block-wide barrier and no inter-warp wait.
 //
-// Latency: no block-level barriers; each warp owns chunks of 32*ITEMS
-// consecutive particles and runs the dependent chain
-//   inputs -> bucket -> record -> outputs
-// with all ITEMS loads of a stage in flight together.
+// Matching: a region-segmented, bucketised hash table in global memory.  The
+// table of a snapshot is two arrays: per-bucket fill counters (4 B / bucket,
+// ~1 B / particle: L2-resident, so clearing them and the atomics on them cost
+// next to no HBM traffic) and 32-byte slot buckets (8 slots = fingerprint |
+// block-local index; never cleared -- a stale slot can only produce a candidate
+// that the 64-bit ID check of the record rejects).
+//   insert : k = atomicAdd(count[b], 1); slot[b][k] = value
+//   probe  : one 32 B sector (ld.global.v8), XOR/compare in registers, then
+//            the 32 B record of the candidate (one more v8 load), which carries
+//            the ID for the exact check AND rhat / v_r / angle: match + state
+//            read is one gather.  Overflow (count > 8) spills to the next
+//            bucket of the same region and is resolved out of line.
+// The buckets of a region are touched while the front crosses that region,
+// i.e. from B200's 126 MB L2; data that is touched once is loaded/stored with
+// an evict-first policy.
 //
 // Arithmetic mirrors numpy's evaluation order and rounding points (no FMA
 // contraction: compiled with -fmad=false and *_rn intrinsics where the order
@@ -32,8 +42,10 @@
 
 namespace {
 
-constexpr int TRACK_THREADS = 256;
-constexpr int TRACK_WARPS = TRACK_THREADS / 32;
+constexpr int TRACK_WARPS = 32;                 // one 1024-thread CTA per SM
+constexpr int TRACK_THREADS = 32 * TRACK_WARPS;
+constexpr int CHUNK = 32;                       // particles per warp step
+constexpr int RW = 4;                           // region rows staged per chunk
 
 // ---- IEEE arithmetic without contraction ------------------------------------------
 template <typename T> struct Ar;
@@ -89,11 +101,23 @@ OA_D uint64_t policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-OA_D int4 ld16_nc(const void* a, uint64_t pol) {     // read-only, no L1 allocation
-    int4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+struct __align__(32) V8 { uint32_t w[8]; };
+// one whole 32-byte sector per thread (sm_100 256-bit global access)
+OA_D V8 ld32_nc(const void* a, uint64_t pol) {
+    V8 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                   "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+                 : "l"(a), "l"(pol));
     return v;
+}
+OA_D void st32(void* a, const V8& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.u32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+                 :: "l"(a), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+                    "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]), "l"(pol)
+                 : "memory");
 }
 OA_D int64_t ld8_nc(const int64_t* a, uint64_t pol) {
     int64_t v;
@@ -101,8 +125,6 @@ OA_D int64_t ld8_nc(const int64_t* a, uint64_t pol) {
                  : "=l"(v) : "l"(a), "l"(pol));
     return v;
 }
-// positions / velocities: (n,3) rows read with three strided scalar loads per
-// thread -- keep L1 allocation (the three loads of a warp share their lines)
 OA_D float ld_elem(const float* a, uint64_t pol) {
     float v;
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
@@ -112,10 +134,6 @@ OA_D double ld_elem(const double* a, uint64_t pol) {
     double v;
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
     return v;
-}
-OA_D void st16(void* a, const int4& v, uint64_t pol) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
-                 :: "l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 OA_D void st2(uint16_t* a, uint16_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(a), "h"(v), "l"(pol) : "memory");
@@ -133,48 +151,71 @@ OA_D uint32_t atom_add(uint32_t* a, uint32_t v, uint64_t pol) {
 template <typename TF>
 OA_D OaRec<TF> load_rec(const OaRec<TF>* p, uint64_t pol) {
     OaRec<TF> r;
-    int4* dst = reinterpret_cast<int4*>(&r);
+    V8* dst = reinterpret_cast<V8*>(&r);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(OaRec<TF>) / 16); ++i)
-        dst[i] = ld16_nc(reinterpret_cast<const int4*>(p) + i, pol);
+    for (int i = 0; i < (int)(sizeof(OaRec<TF>) / 32); ++i)
+        dst[i] = ld32_nc(reinterpret_cast<const V8*>(p) + i, pol);
     return r;
 }
 template <typename TF>
 OA_D void store_rec(OaRec<TF>* p, const OaRec<TF>& r, uint64_t pol) {
-    const int4* src = reinterpret_cast<const int4*>(&r);
+    const V8* src = reinterpret_cast<const V8*>(&r);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(OaRec<TF>) / 16); ++i)
-        st16(reinterpret_cast<int4*>(p) + i, src[i], pol);
+    for (int i = 0; i < (int)(sizeof(OaRec<TF>) / 32); ++i)
+        st32(reinterpret_cast<V8*>(p) + i, src[i], pol);
 }
 
-struct Bucket {
-    uint32_t w[OA_BUCKET_WORDS];   // w[0] = count, w[1..7] = slots
-};
-OA_D Bucket load_bucket(const uint32_t* tab, int64_t bucket, uint64_t pol) {
-    Bucket b;
-    const int4* src = reinterpret_cast<const int4*>(tab + bucket * OA_BUCKET_WORDS);
-    const int4 lo = ld16_nc(src, pol), hi = ld16_nc(src + 1, pol);
-    b.w[0] = lo.x; b.w[1] = lo.y; b.w[2] = lo.z; b.w[3] = lo.w;
-    b.w[4] = hi.x; b.w[5] = hi.y; b.w[6] = hi.z; b.w[7] = hi.w;
-    return b;
+// ---- mbarrier / TMA (1-D bulk copy) -----------------------------------------------------
+OA_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+OA_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+OA_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+OA_D void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+OA_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n"
+                     " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+OA_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                      uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 ".L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
 }
 
-struct RegionRow {
-    double c[3];
-    double b[3];
-    int64_t prev_begin, prev_count, prev_bucket, cur_bucket;
-};
-OA_D RegionRow load_region(const oa_region* regions, int j) {
-    RegionRow R;
-    const double2* src = reinterpret_cast<const double2*>(regions + j);
-    const double2 a0 = __ldg(src + 0), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
-    const longlong2* tail = reinterpret_cast<const longlong2*>(regions + j) + 3;
-    const longlong2 t0 = __ldg(tail), t1 = __ldg(tail + 1);
-    R.c[0] = a0.x; R.c[1] = a0.y; R.c[2] = a1.x;
-    R.b[0] = a1.y; R.b[1] = a2.x; R.b[2] = a2.y;
-    R.prev_begin = t0.x; R.prev_count = t0.y;
-    R.prev_bucket = t1.x; R.cur_bucket = t1.y;
-    return R;
+// ---- table geometry (closed forms, shared with the host through the C ABI) ------------
+// Region j (block start `off`, length len) owns buckets
+//   [off/4 + j, off/4 + j + len/4 + 1): mean fill <= 4 of 8 slots.
+OA_HD uint32_t bucket_count(int64_t len) { return (uint32_t)(len / 4 + 1); }
+OA_HD int64_t bucket_begin(int64_t block_start, int64_t region) {
+    return block_start / 4 + region;
+}
+OA_HD int64_t table_buckets(int64_t n, int64_t n_regions) { return n / 4 + n_regions + 2; }
+// counters first (rounded up to whole sectors), then the slot buckets
+OA_HD int64_t table_count_words(int64_t buckets) { return (buckets + 7) / 8 * 8; }
+
+// ---- region rows ------------------------------------------------------------------------------
+// The kernel reads oa_region rows (128 B, include/orbit_b200.h) as staged by
+// TMA, or -- for chunks that touch more than RW regions -- a private copy.
+using Row = oa_region;
+static_assert(sizeof(Row) == 128, "oa_region layout");
+
+OA_D void load_row(const oa_region* __restrict__ regions, int j, Row* out) {
+    const int4* src = reinterpret_cast<const int4*>(regions + j);
+    int4* dst = reinterpret_cast<int4*>(out);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(Row) / 16); ++q) dst[q] = __ldg(src + q);
 }
 
 // last j in [lo, hi] with off[j] <= c   (off is non-decreasing; empty blocks
@@ -187,287 +228,420 @@ OA_D int find_region(const int64_t* __restrict__ off, int lo, int hi, int64_t c)
     return lo;
 }
 
-OA_D uint32_t bucket_count(int64_t len) { return (uint32_t)((2 * len) / 7 + 1); }
-OA_HD int64_t bucket_begin(int64_t block_start, int64_t region) {
-    return (2 * block_start) / 7 + region;
-}
+struct ChunkMeta {
+    int jlo, jhi;        // regions the chunk touches
+    int nrows;           // rows staged in the slot (0: more than RW, look up)
+    int tma;             // inputs were staged by TMA
+};
+
+// ---- derived launch constants (host -> kernel) ----------------------------------------------
+struct TrackConst {
+    const int2* chunk_regions;    // (n_chunks,) first / last region of every chunk
+    const uint32_t* cnt_prev;     // bucket fill counters of the previous table
+    const uint32_t* slot_prev;    // its slot buckets
+    uint32_t* cnt_cur;
+    uint32_t* slot_cur;
+    int n_chunks;
+    float half_box[3];            // largest float <= L/2 (float-frame wrap test)
+    int tma_ok;                   // base pointers are 16-byte aligned
+};
 
 // ---- rare paths, kept out of line so they do not cost registers -----------------------
+// (plain loads here: ptxas 12.9 crashes on 256-bit inline-asm loads inside a
+// function that is not inlined)
 template <typename TF>
-__device__ __noinline__ int64_t probe_slow(const uint32_t* __restrict__ tab,
-                                           int64_t bucket_begin, uint32_t nb,
-                                           uint32_t home, uint32_t fp, int pbits,
-                                           uint32_t pmask,
+__device__ __noinline__ int64_t probe_slow(const uint32_t* __restrict__ cnt,
+                                           const uint32_t* __restrict__ slot,
+                                           uint32_t bucket0, uint32_t nb, uint32_t home,
+                                           uint32_t fpshift, uint32_t prev_count,
                                            const OaRec<TF>* __restrict__ rec_prev,
-                                           int64_t prev_begin, int64_t id) {
-    const uint64_t pol = policy_evict_last(), pol_s = policy_evict_first();
+                                           uint32_t prev_begin, int64_t id,
+                                           bool home_has_no_match) {
     uint32_t b = home;
     for (uint32_t t = 0; t < nb; ++t) {
-        const Bucket B = load_bucket(tab, bucket_begin + b, pol);
-        const uint32_t cnt = B.w[0];
-        const uint32_t m = cnt < OA_BUCKET_SLOTS ? cnt : OA_BUCKET_SLOTS;
-        for (uint32_t e = 1; e <= m; ++e) {
-            if ((B.w[e] >> pbits) == fp) {
-                const int64_t q = prev_begin + (int64_t)(B.w[e] & pmask);
-                const OaRec<TF> r = load_rec(rec_prev + q, pol_s);
-                if (r.id == id) return q;
+        const uint32_t fill = __ldcg(cnt + bucket0 + b);
+        uint32_t m = fill < OA_BUCKET_SLOTS ? fill : OA_BUCKET_SLOTS;
+        if (t == 0 && home_has_no_match) m = 0;      // already compared in registers
+        const uint32_t* B = slot + (size_t)(bucket0 + b) * OA_BUCKET_WORDS;
+        for (uint32_t e = 0; e < m; ++e) {
+            const uint32_t x = __ldcg(B + e) ^ fpshift;
+            if (x < prev_count) {
+                const int64_t q = (int64_t)prev_begin + (int64_t)x;
+                if (__ldcg(&rec_prev[q].id) == id) return q;
             }
         }
-        if (cnt <= OA_BUCKET_SLOTS) return -1;      // never overflowed: a miss
+        if (fill <= OA_BUCKET_SLOTS) return -1;      // never overflowed: a miss
         b = (b + 1 == nb) ? 0u : b + 1;
     }
     return -1;
 }
 
-__device__ __noinline__ void insert_slow(uint32_t* __restrict__ tab, int64_t bucket_begin,
+__device__ __noinline__ void insert_slow(uint32_t* __restrict__ cnt,
+                                         uint32_t* __restrict__ slot, uint32_t bucket0,
                                          uint32_t nb, uint32_t home, uint32_t val) {
     uint32_t b = home;
     for (uint32_t t = 1; t < nb; ++t) {
         b = (b + 1 == nb) ? 0u : b + 1;
-        uint32_t* bk = tab + (bucket_begin + b) * OA_BUCKET_WORDS;
-        const uint32_t k = atomicAdd(bk, 1u);
-        if (k < OA_BUCKET_SLOTS) { bk[1 + k] = val; return; }
+        const uint32_t k = atomicAdd(cnt + bucket0 + b, 1u);
+        if (k < OA_BUCKET_SLOTS) {
+            slot[(size_t)(bucket0 + b) * OA_BUCKET_WORDS + k] = val;
+            return;
+        }
     }
 }
 
-template <typename TX, typename TF, typename TVR, bool HUBBLE, int ITEMS>
-__global__ void __launch_bounds__(TRACK_THREADS)
-oa_track_kernel(const oa_track_args a) {
-    using AF = Ar<TF>;
-    constexpr int CHUNK = 32 * ITEMS;
+// first / last region of every chunk (one thread per chunk)
+__global__ void track_chunks_kernel(const int64_t* __restrict__ off, int n_regions,
+                                    int64_t n, int n_chunks, int2* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_chunks) return;
+    const int64_t first = (int64_t)t * CHUNK;
+    const int64_t last = min(first + (int64_t)CHUNK, n) - 1;
+    const int jlo = find_region(off, 0, n_regions - 1, first);
+    const int jhi = find_region(off, jlo, n_regions - 1, last);
+    out[t] = make_int2(jlo, jhi);
+}
 
-    const TX* __restrict__ pos = static_cast<const TX*>(a.pos);
-    const TX* __restrict__ vel = static_cast<const TX*>(a.vel);
-    const int64_t* __restrict__ off = a.cur_off;
+template <typename TX>
+struct SlotLayout {
+    static constexpr int IDS = 0;
+    static constexpr int POS = IDS + 8 * CHUNK;
+    static constexpr int VEL = POS + (int)sizeof(TX) * 3 * CHUNK;
+    static constexpr int ROWS = VEL + (int)sizeof(TX) * 3 * CHUNK;
+    static constexpr int META = ROWS + (int)sizeof(Row) * RW;
+    static constexpr int BYTES = META + 16;
+    // ring depth: four chunks of float data, three of double data
+    static constexpr int DEPTH = sizeof(TX) == 4 ? 4 : 3;
+    static_assert(POS % 16 == 0 && VEL % 16 == 0 && ROWS % 16 == 0 && BYTES % 16 == 0,
+                  "TMA destinations must be 16-byte aligned");
+};
+
+template <typename T> struct Vec3 { T x, y, z; };
+
+// Per-particle state carried from the issue of the table traffic (track_begin)
+// to its consumption (track_finish).
+template <typename TF, typename TVR>
+struct Particle {
+    int64_t id;
+    TF rh[3], r;
+    TVR vr;
+    uint32_t c;
+    uint32_t ins_k, ins_val, ins_b, ins_nb, ins_home;
+    uint32_t fpshift, prev_count, prev_begin, prb_b0, prb_nb, prb_home;
+    V8 bk;
+};
+
+// Frame, hash, insert atomic and bucket load of one particle.  `R` is the row of
+// the particle's region (shared memory, or a private copy on the rare path).
+template <typename TX, typename TF, typename TVR, bool HUBBLE>
+OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Row* R,
+                      const Vec3<TX> xin, const Vec3<TX> vin, Particle<TF, TVR>& P) {
+    using AF = Ar<TF>;
+    const TX x[3] = {xin.x, xin.y, xin.z}, v[3] = {vin.x, vin.y, vin.z};
+    const uint64_t pol_keep = policy_evict_last();
+    // halo frame (region_frame)
+    TF d[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (std::is_same<TX, double>::value || !a.centre_f32) {
+            double dd = __dsub_rn((double)x[q], R->centre[q]);
+            if (a.periodic) {
+                const double Lq = a.box[q], h = Lq * 0.5;
+                if (dd > h) dd = __dsub_rn(dd, Lq);
+                if (dd < -h) dd = __dadd_rn(dd, Lq);
+            }
+            d[q] = (TF)dd;
+        } else {
+            // float frame: `(double)df > L/2` <=> `df > rd_float(L/2)`
+            float df = __fsub_rn((float)x[q], R->centre_f[q]);
+            if (a.periodic) {
+                const float hf = k.half_box[q];
+                if (df > hf) df = (float)__dsub_rn((double)df, a.box[q]);
+                if (df < -hf) df = (float)__dadd_rn((double)df, a.box[q]);
+            }
+            d[q] = (TF)df;
+        }
+    }
+    P.r = AF::sqrt(AF::dot3(d[0], d[1], d[2], d[0], d[1], d[2]));
+#pragma unroll
+    for (int q = 0; q < 3; ++q) P.rh[q] = AF::div(d[q], P.r);
+    TVR w[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double wk;
+        if (std::is_same<TX, double>::value || !a.bulk_f32)
+            wk = __dsub_rn((double)v[q], R->bulk[q]);
+        else
+            wk = (double)__fsub_rn((float)v[q], R->bulk_f[q]);
+        if (HUBBLE)
+            wk = __dadd_rn(wk, __ddiv_rn(__dmul_rn(a.hubble, (double)d[q]), a.one_plus_z));
+        w[q] = (TVR)wk;
+    }
+    P.vr = Ar<TVR>::dot3(w[0], w[1], w[2], (TVR)P.rh[0], (TVR)P.rh[1], (TVR)P.rh[2]);
+
+    const uint64_t hsh = oa_mix64((uint64_t)P.id);
+    const uint32_t h_slot = (uint32_t)(hsh >> 32), h_fp = (uint32_t)hsh;
+    const int pbits = a.prev_index_bits, cbits = a.cur_index_bits;
+
+    // insert into the current table: the atomic is issued now, its result is
+    // consumed at the very end
+    P.ins_nb = bucket_count(R->cur_count);
+    P.ins_home = oa_slot(h_slot, P.ins_nb);
+    P.ins_b = (uint32_t)R->cur_bucket;
+    P.ins_val = ((h_fp >> cbits) << cbits) | (P.c - (uint32_t)R->cur_begin);
+    P.ins_k = atom_add(k.cnt_cur + (P.ins_b + P.ins_home), 1u, pol_keep);
+
+    // probe of the previous table: one sector
+    P.prev_count = (a.rec_prev != nullptr && R->prev_count > 0) ? (uint32_t)R->prev_count : 0u;
+    P.fpshift = (h_fp >> pbits) << pbits;
+    if (P.prev_count > 0) {
+        P.prev_begin = (uint32_t)R->prev_begin;
+        P.prb_b0 = (uint32_t)R->prev_bucket;
+        P.prb_nb = bucket_count(P.prev_count);
+        P.prb_home = oa_slot(h_slot, P.prb_nb);
+        P.bk = ld32_nc(k.slot_prev + (size_t)(P.prb_b0 + P.prb_home) * OA_BUCKET_WORDS,
+                       pol_keep);
+    }
+}
+
+// Candidate record, exact ID check, apsis test, angle accumulator, outputs.
+template <typename TF, typename TVR>
+OA_D void track_finish(const oa_track_args& a, const TrackConst& k, Particle<TF, TVR>& P) {
+    using AF = Ar<TF>;
     const OaRec<TF>* __restrict__ rec_prev = static_cast<const OaRec<TF>*>(a.rec_prev);
     OaRec<TF>* __restrict__ rec_cur = static_cast<OaRec<TF>*>(a.rec_cur);
-    const bool have_prev = (a.rec_prev != nullptr) && (a.n_prev > 0);
-    const int pbits = a.prev_index_bits, cbits = a.cur_index_bits;
-    const uint32_t pmask = (1u << pbits) - 1u;
-    const int64_t n = a.n_cur;
-    const int64_t n_chunks = (n + CHUNK - 1) / CHUNK;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * TRACK_WARPS + (threadIdx.x >> 5);
-    const int64_t warps = (int64_t)gridDim.x * TRACK_WARPS;
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t pol_keep = policy_evict_last();
+    const uint32_t c = P.c;
 
-    for (int64_t chunk = warp0; chunk < n_chunks; chunk += warps) {
-        const int64_t base = chunk * CHUNK;
-        const int64_t last = min(base + (int64_t)CHUNK, n) - 1;
-
-        // ---- stage 1: inputs (all ITEMS in flight) ---------------------------------
-        int64_t id[ITEMS];
-        TX x[ITEMS][3], v[ITEMS][3];
+    int64_t p = -1;
+    OaRec<TF> prev;
+    if (P.prev_count > 0) {
+        uint32_t cand = 0xFFFFFFFFu;
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            const int64_t c = base + it * 32 + lane;
-            if (c < n) {
-                id[it] = ld8_nc(a.ids + c, pol_stream);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    x[it][k] = ld_elem(pos + 3 * c + k, pol_stream);
-                    v[it][k] = ld_elem(vel + 3 * c + k, pol_stream);
-                }
-            }
+        for (int e = OA_BUCKET_SLOTS - 1; e >= 0; --e) {
+            const uint32_t xr = P.bk.w[e] ^ P.fpshift;   // == index iff fingerprint equal
+            if (xr < P.prev_count) cand = xr;
         }
-        // region range of this chunk (warp-uniform loads, overlap with stage 1)
-        const int jlo = find_region(off, 0, a.n_regions - 1, base);
-        const int jhi = find_region(off, jlo, a.n_regions - 1, last);
-
-        // ---- stage 2: frame, hash, table traffic issued ---------------------------
-        TF rh[ITEMS][3], r[ITEMS];
-        TVR vr[ITEMS];
-        Bucket bk[ITEMS];
-        uint32_t ins_k[ITEMS], ins_val[ITEMS], fp[ITEMS];
-        uint32_t* ins_ptr[ITEMS];
-        int64_t prev_begin[ITEMS];
-        int jreg[ITEMS];
-        bool probe[ITEMS];
-#pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            const int64_t c = base + it * 32 + lane;
-            probe[it] = false;
-            if (c >= n) continue;
-            const int j = find_region(off, jlo, jhi, c);
-            jreg[it] = j;
-            const RegionRow R = load_region(a.regions, j);
-            const int64_t cur_begin = __ldg(off + j);
-            const int64_t cur_len = __ldg(off + j + 1) - cur_begin;
-
-            // halo frame (region_frame)
-            TF d[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (std::is_same<TX, double>::value || !a.centre_f32) {
-                    double dd = __dsub_rn((double)x[it][k], R.c[k]);
-                    if (a.periodic) {
-                        const double L = a.box[k], h = L * 0.5;
-                        if (dd > h) dd = __dsub_rn(dd, L);
-                        if (dd < -h) dd = __dadd_rn(dd, L);
-                    }
-                    d[k] = (TF)dd;
-                } else {
-                    float df = __fsub_rn((float)x[it][k], (float)R.c[k]);
-                    if (a.periodic) {
-                        const double L = a.box[k], h = L * 0.5;
-                        if ((double)df > h) df = (float)__dsub_rn((double)df, L);
-                        if ((double)df < -h) df = (float)__dadd_rn((double)df, L);
-                    }
-                    d[k] = (TF)df;
-                }
-            }
-            r[it] = AF::sqrt(AF::dot3(d[0], d[1], d[2], d[0], d[1], d[2]));
-#pragma unroll
-            for (int k = 0; k < 3; ++k) rh[it][k] = AF::div(d[k], r[it]);
-            TVR w[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                double wk;
-                if (std::is_same<TX, double>::value || !a.bulk_f32)
-                    wk = __dsub_rn((double)v[it][k], R.b[k]);
-                else
-                    wk = (double)__fsub_rn((float)v[it][k], (float)R.b[k]);
-                if (HUBBLE)
-                    wk = __dadd_rn(wk, __ddiv_rn(__dmul_rn(a.hubble, (double)d[k]),
-                                                 a.one_plus_z));
-                w[k] = (TVR)wk;
-            }
-            vr[it] = Ar<TVR>::dot3(w[0], w[1], w[2], (TVR)rh[it][0], (TVR)rh[it][1],
-                                   (TVR)rh[it][2]);
-
-            const uint64_t hsh = oa_mix64((uint64_t)id[it]);
-            const uint32_t h_slot = (uint32_t)(hsh >> 32), h_fp = (uint32_t)hsh;
-
-            // insert into the current table: the atomic is issued now, its result
-            // is consumed at the very end
-            ins_ptr[it] = a.tab_cur + (R.cur_bucket + oa_slot(h_slot, bucket_count(cur_len))) *
-                                          OA_BUCKET_WORDS;
-            ins_val[it] = ((h_fp >> cbits) << cbits) | (uint32_t)(c - cur_begin);
-            ins_k[it] = atom_add(ins_ptr[it], 1u, pol_keep);
-
-            // probe of the previous table: one sector
-            if (have_prev && R.prev_count > 0) {
-                probe[it] = true;
-                prev_begin[it] = R.prev_begin;
-                fp[it] = h_fp >> pbits;
-                bk[it] = load_bucket(
-                    a.tab_prev,
-                    R.prev_bucket + oa_slot(h_slot, bucket_count(R.prev_count)), pol_keep);
-            }
+        bool slow = true;         // no candidate: a miss, unless the bucket overflowed
+        if (cand != 0xFFFFFFFFu) {
+            p = (int64_t)P.prev_begin + (int64_t)cand;
+            prev = load_rec(rec_prev + p, pol_stream);
+            slow = prev.id != P.id;                   // stale slot / collision
         }
-
-        // ---- stage 3: candidate record loads ------------------------------------------
-        int64_t p[ITEMS];
-        OaRec<TF> prev[ITEMS];
-        bool slow[ITEMS];
-#pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            p[it] = -1;
-            slow[it] = false;
-            if (!probe[it]) continue;
-            const uint32_t cnt = bk[it].w[0];
-            const uint32_t m = cnt < OA_BUCKET_SLOTS ? cnt : OA_BUCKET_SLOTS;
-            int64_t cand = -1;
-#pragma unroll
-            for (int e = OA_BUCKET_SLOTS; e >= 1; --e)
-                if ((uint32_t)e <= m && (bk[it].w[e] >> pbits) == fp[it])
-                    cand = prev_begin[it] + (int64_t)(bk[it].w[e] & pmask);
-            if (cand >= 0) {
-                prev[it] = load_rec(rec_prev + cand, pol_stream);
-                p[it] = cand;
-            } else if (cnt > OA_BUCKET_SLOTS) {
-                slow[it] = true;             // bucket overflowed: look further
-            }
+        if (slow) {
+            p = probe_slow<TF>(k.cnt_prev, k.slot_prev, P.prb_b0, P.prb_nb, P.prb_home,
+                               P.fpshift, P.prev_count, rec_prev, P.prev_begin, P.id,
+                               cand == 0xFFFFFFFFu);
+            if (p >= 0) prev = load_rec(rec_prev + p, pol_stream);
         }
+    }
 
-        // ---- stage 4: verify, apsis test, angle accumulator, outputs ------------------
-#pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            const int64_t c = base + it * 32 + lane;
-            if (c >= n) continue;
-            if (p[it] >= 0 && prev[it].id != id[it]) { p[it] = -1; slow[it] = true; }
-            if (slow[it]) {        // fingerprint collision or overflowed bucket (rare)
-                const RegionRow R = load_region(a.regions, jreg[it]);
-                const uint32_t nb = bucket_count(R.prev_count);
-                const uint32_t home =
-                    oa_slot((uint32_t)(oa_mix64((uint64_t)id[it]) >> 32), nb);
-                p[it] = probe_slow<TF>(a.tab_prev, R.prev_bucket, nb, home, fp[it], pbits,
-                                       pmask, rec_prev, R.prev_begin, id[it]);
-                if (p[it] >= 0) prev[it] = load_rec(rec_prev + p[it], pol_stream);
+    __half angle_new = __ushort_as_half((unsigned short)0);
+    if (p >= 0) {
+        const TF dotp = AF::dot3((TF)prev.rx, (TF)prev.ry, (TF)prev.rz, P.rh[0], P.rh[1],
+                                 P.rh[2]);
+        const TF dang = AF::acos(dotp);
+        bool ev;
+        if (a.mode == OA_MODE_PERICENTRIC) ev = (prev.vr < 0) && (P.vr > 0);
+        else ev = (prev.vr > 0) && (P.vr < 0);
+        if (a.onthefly) {
+            if (a.dangle_prev) static_cast<TF*>(a.dangle_prev)[p] = dang;
+            a.mark_prev[p] = ev ? (uint16_t)1 : (uint16_t)0;
+        } else {
+            TF run = AF::add((TF)__half2float(prev.angle), dang);
+            if (ev) {
+                a.mark_prev[p] = __half_as_ushort(AF::to_half(run));
+                run = (TF)0;
             }
-
-            __half angle_new = __ushort_as_half((unsigned short)0);
-            if (p[it] >= 0) {
-                const TF dotp = AF::dot3((TF)prev[it].rx, (TF)prev[it].ry, (TF)prev[it].rz,
-                                         rh[it][0], rh[it][1], rh[it][2]);
-                const TF dang = AF::acos(dotp);
-                bool ev;
-                if (a.mode == OA_MODE_PERICENTRIC) ev = (prev[it].vr < 0) && (vr[it] > 0);
-                else ev = (prev[it].vr > 0) && (vr[it] < 0);
-                if (a.onthefly) {
-                    if (a.dangle_prev) static_cast<TF*>(a.dangle_prev)[p[it]] = dang;
-                    a.mark_prev[p[it]] = ev ? (uint16_t)1 : (uint16_t)0;
-                } else {
-                    TF run = AF::add((TF)__half2float(prev[it].angle), dang);
-                    if (ev) {
-                        a.mark_prev[p[it]] = __half_as_ushort(AF::to_half(run));
-                        run = (TF)0;
-                    }
-                    angle_new = AF::to_half(run);
-                }
-            }
-
-            OaRec<TF> rec;
-            rec.id = id[it];
-            rec.rx = rh[it][0]; rec.ry = rh[it][1]; rec.rz = rh[it][2];
-            set_vr<TF, TVR>(rec, vr[it]);
-            rec.r = r[it];
-            rec.angle = angle_new;
-            rec.flags = 0;
-            store_rec(rec_cur + c, rec, pol_stream);
-            st2(a.mark_cur + c, OA_NO_EVENT, pol_stream);
-
-            if (ins_k[it] < OA_BUCKET_SLOTS) {
-                st4(ins_ptr[it] + 1 + ins_k[it], ins_val[it], pol_keep);
-            } else {               // home bucket full (rare): spill to the next ones
-                const int64_t cb = __ldg(off + jreg[it]);
-                const uint32_t nb = bucket_count(__ldg(off + jreg[it] + 1) - cb);
-                const int64_t first = bucket_begin(cb, jreg[it]);
-                const uint32_t home =
-                    (uint32_t)((ins_ptr[it] - a.tab_cur) / OA_BUCKET_WORDS - first);
-                insert_slow(a.tab_cur, first, nb, home, ins_val[it]);
-            }
-
-            if (a.out_rhat) {
-                TF* o = static_cast<TF*>(a.out_rhat) + 3 * c;
-                o[0] = rh[it][0]; o[1] = rh[it][1]; o[2] = rh[it][2];
-            }
-            if (a.out_vr) static_cast<TVR*>(a.out_vr)[c] = vr[it];
-            if (a.out_r) static_cast<TF*>(a.out_r)[c] = r[it];
-            if (a.out_angle) a.out_angle[c] = __half_as_ushort(angle_new);
-            if (a.out_match) a.out_match[c] = p[it];
+            angle_new = AF::to_half(run);
         }
+    }
+
+    OaRec<TF> rec;
+    rec.id = P.id;
+    rec.rx = P.rh[0]; rec.ry = P.rh[1]; rec.rz = P.rh[2];
+    set_vr<TF, TVR>(rec, P.vr);
+    rec.r = P.r;
+    rec.angle = angle_new;
+    rec.flags = 0;
+    store_rec(rec_cur + c, rec, pol_stream);
+    st2(a.mark_cur + c, OA_NO_EVENT, pol_stream);
+
+    if (P.ins_k < OA_BUCKET_SLOTS)
+        st4(k.slot_cur + (size_t)(P.ins_b + P.ins_home) * OA_BUCKET_WORDS + P.ins_k,
+            P.ins_val, pol_keep);
+    else               // home bucket full (rare): spill to the next ones
+        insert_slow(k.cnt_cur, k.slot_cur, P.ins_b, P.ins_nb, P.ins_home, P.ins_val);
+
+    if (a.out_rhat) {
+        TF* o = static_cast<TF*>(a.out_rhat) + 3 * (size_t)c;
+        o[0] = P.rh[0]; o[1] = P.rh[1]; o[2] = P.rh[2];
+    }
+    if (a.out_vr) static_cast<TVR*>(a.out_vr)[c] = P.vr;
+    if (a.out_r) static_cast<TF*>(a.out_r)[c] = P.r;
+    if (a.out_angle) a.out_angle[c] = __half_as_ushort(angle_new);
+    if (a.out_match) a.out_match[c] = p;
+}
+
+template <typename TX, typename TF, typename TVR, bool HUBBLE>
+__global__ void __launch_bounds__(TRACK_THREADS, 1)
+oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__ TrackConst k) {
+    using L = SlotLayout<TX>;
+    constexpr int D = L::DEPTH;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[TRACK_WARPS * D];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const wsm = smem + (size_t)warp * D * L::BYTES;
+    uint64_t* const full = bars + warp * D;
+    const int64_t n = a.n_cur;
+    const int stride = gridDim.x * TRACK_WARPS;
+    const int first = blockIdx.x * TRACK_WARPS + warp;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane 0: stage chunk `ch` (regions jr.x..jr.y) into slot `s`
+    auto issue = [&](int ch, int s, int2 jr) {
+        unsigned char* st = wsm + s * L::BYTES;
+        const int64_t base = (int64_t)ch * CHUNK;
+        const int nrows = jr.y - jr.x + 1;
+        const bool tma = k.tma_ok && (base + CHUNK <= n);
+        ChunkMeta* m = reinterpret_cast<ChunkMeta*>(st + L::META);
+        m->jlo = jr.x;
+        m->jhi = jr.y;
+        m->nrows = nrows <= RW ? nrows : 0;
+        m->tma = tma ? 1 : 0;
+        constexpr uint32_t B_IDS = 8u * CHUNK, B_X = (uint32_t)sizeof(TX) * 3u * CHUNK;
+        const uint32_t b_rows = nrows <= RW ? (uint32_t)sizeof(Row) * nrows : 0u;
+        const uint64_t pol_stream = policy_evict_first();
+        mbar_arrive_expect_tx(&full[s], (tma ? B_IDS + 2u * B_X : 0u) + b_rows);
+        if (tma) {
+            tma_load_1d(st + L::IDS, a.ids + base, B_IDS, &full[s], pol_stream);
+            tma_load_1d(st + L::POS, static_cast<const TX*>(a.pos) + 3 * base, B_X, &full[s],
+                        pol_stream);
+            tma_load_1d(st + L::VEL, static_cast<const TX*>(a.vel) + 3 * base, B_X, &full[s],
+                        pol_stream);
+        }
+        if (b_rows)
+            tma_load_1d(st + L::ROWS, a.regions + jr.x, b_rows, &full[s], policy_evict_last());
+    };
+
+    // ---- prologue: D chunks in flight -------------------------------------------------------
+    if (lane == 0) {
+        for (int s = 0; s < D; ++s) {
+            const int ch = first + s * stride;
+            if (ch < k.n_chunks) issue(ch, s, __ldg(k.chunk_regions + ch));
+        }
+    }
+    int2 jr_next = make_int2(0, 0);           // regions of the chunk D steps ahead
+    if (first + D * stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + first + D * stride);
+
+    int t = 0;
+    for (int ch = first; ch < k.n_chunks; ch += stride, ++t) {
+        const int s = t % D;
+        unsigned char* st = wsm + s * L::BYTES;
+        mbar_wait(&full[s], (uint32_t)(t / D) & 1u);
+        const ChunkMeta meta = *reinterpret_cast<const ChunkMeta*>(st + L::META);
+        const int64_t c = (int64_t)ch * CHUNK + lane;
+        const bool active = c < n;
+
+        Particle<TF, TVR> P;
+        P.c = (uint32_t)c;
+        P.id = 0;
+        P.prev_count = 0;
+        Vec3<TX> x = {0, 0, 0}, v = {0, 0, 0};
+        if (meta.tma) {
+            P.id = reinterpret_cast<const int64_t*>(st + L::IDS)[lane];
+            const TX* sp = reinterpret_cast<const TX*>(st + L::POS) + 3 * lane;
+            const TX* sv = reinterpret_cast<const TX*>(st + L::VEL) + 3 * lane;
+            x.x = sp[0]; x.y = sp[1]; x.z = sp[2];
+            v.x = sv[0]; v.y = sv[1]; v.z = sv[2];
+        } else if (active) {
+            const uint64_t pol_stream = policy_evict_first();
+            P.id = ld8_nc(a.ids + c, pol_stream);
+            const TX* gp = static_cast<const TX*>(a.pos) + 3 * c;
+            const TX* gv = static_cast<const TX*>(a.vel) + 3 * c;
+            x.x = ld_elem(gp, pol_stream); x.y = ld_elem(gp + 1, pol_stream);
+            x.z = ld_elem(gp + 2, pol_stream);
+            v.x = ld_elem(gv, pol_stream); v.y = ld_elem(gv + 1, pol_stream);
+            v.z = ld_elem(gv + 2, pol_stream);
+        }
+        if (active) {
+            Row own;              // rare path only: more regions than a slot stages
+            const Row* R = reinterpret_cast<const Row*>(st + L::ROWS);
+            if (meta.nrows > 0) {
+                // first staged row whose block ends beyond this particle (empty
+                // blocks in between end where they begin and are skipped)
+                for (int q = 1; q < meta.nrows; ++q)
+                    if (c >= R->cur_begin + R->cur_count) ++R;
+            } else {
+                load_row(a.regions, find_region(a.cur_off, meta.jlo, meta.jhi, c), &own);
+                R = &own;
+            }
+            track_begin<TX, TF, TVR, HUBBLE>(a, k, R, x, v, P);
+        }
+        // the slot has been consumed: refill it with the chunk D steps ahead
+        __syncwarp();
+        const int ahead = ch + D * stride;
+        if (ahead < k.n_chunks) {
+            if (lane == 0) issue(ahead, s, jr_next);
+            if (ahead + stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + ahead + stride);
+        }
+        if (active) track_finish<TF, TVR>(a, k, P);
     }
 }
 
 template <typename TX, typename TF, typename TVR, bool HUBBLE>
 int launch_track(const oa_track_args& a, cudaStream_t st) {
-    constexpr int ITEMS = 2;
-    auto kern = oa_track_kernel<TX, TF, TVR, HUBBLE, ITEMS>;
-    int per_sm = 0;
-    OA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, kern, TRACK_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
+    auto kern = oa_track_kernel<TX, TF, TVR, HUBBLE>;
+    using L = SlotLayout<TX>;
+    constexpr int smem_bytes = TRACK_WARPS * L::DEPTH * L::BYTES;
+    static bool configured = false;     // per instantiation
+    if (!configured) {
+        OA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes));
+        configured = true;
+    }
     int dev = 0, sms = OA_NUM_SMS;
     OA_CUDA_CHECK(cudaGetDevice(&dev));
     OA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t per_block = (int64_t)TRACK_WARPS * 32 * ITEMS;
-    const int64_t blocks_needed = (a.n_cur + per_block - 1) / per_block;
-    int64_t grid = (int64_t)sms * per_sm;       // persistent: a multiple of 148
-    if (grid > blocks_needed) grid = blocks_needed;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, TRACK_THREADS, 0, st>>>(a);
+
+    TrackConst k;
+    k.n_chunks = (int)((a.n_cur + CHUNK - 1) / CHUNK);
+    OA_REQUIRE(a.workspace && a.workspace_bytes >= sizeof(int2) * (size_t)k.n_chunks,
+               "oa_track_fused: workspace too small (need oa_track_workspace_bytes)");
+    int2* chunks = static_cast<int2*>(a.workspace);
+    k.chunk_regions = chunks;
+    k.cnt_prev = a.tab_prev;
+    k.slot_prev = a.tab_prev ? a.tab_prev + table_count_words(a.tab_prev_buckets) : nullptr;
+    k.cnt_cur = a.tab_cur;
+    k.slot_cur = a.tab_cur + table_count_words(a.tab_cur_buckets);
+    for (int q = 0; q < 3; ++q) {
+        // largest float <= L/2
+        const double h = a.box[q] * 0.5;
+        float hf = (float)h;
+        if ((double)hf > h) hf = nextafterf(hf, -INFINITY);
+        k.half_box[q] = hf;
+    }
+    OA_REQUIRE((reinterpret_cast<uintptr_t>(a.regions) & 15u) == 0,
+               "oa_track_fused: the region table must be 16-byte aligned");
+    k.tma_ok = ((reinterpret_cast<uintptr_t>(a.ids) | reinterpret_cast<uintptr_t>(a.pos) |
+                 reinterpret_cast<uintptr_t>(a.vel)) & 15u) == 0;
+
+    const int tb = 256;
+    track_chunks_kernel<<<(unsigned)((k.n_chunks + tb - 1) / tb), tb, 0, st>>>(
+        a.cur_off, a.n_regions, a.n_cur, k.n_chunks, chunks);
+    OA_LAUNCH_CHECK();
+    int64_t grid = sms;                         // persistent: one CTA per SM
+    const int64_t ctas_needed = (k.n_chunks + TRACK_WARPS - 1) / TRACK_WARPS;
+    if (grid > ctas_needed) grid = ctas_needed;
+    kern<<<(unsigned)grid, TRACK_THREADS, smem_bytes, st>>>(a, k);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }
@@ -478,14 +652,17 @@ extern "C" size_t oa_record_bytes(int frame_dtype) {
     return frame_dtype == OA_F64 ? sizeof(OaRec<double>) : sizeof(OaRec<float>);
 }
 
-// Bucket b of region j (block start `off`, length `len`) lives at bucket index
-// (2*off)/7 + j + b,  b < (2*len)/7 + 1:  closed form, no prefix sum needed.
 extern "C" int64_t oa_table_bucket_begin(int64_t block_start, int64_t region_index) {
     return bucket_begin(block_start, region_index);
 }
 
+extern "C" int64_t oa_table_buckets(int64_t n, int64_t n_regions) {
+    return table_buckets(n, n_regions);
+}
+
 extern "C" int64_t oa_table_slots(int64_t n, int64_t n_regions) {
-    return ((2 * n) / 7 + n_regions + 2) * OA_BUCKET_WORDS;
+    const int64_t b = table_buckets(n, n_regions);
+    return table_count_words(b) + b * OA_BUCKET_WORDS;
 }
 
 extern "C" int oa_index_bits(int64_t max_block_len) {
@@ -494,11 +671,17 @@ extern "C" int oa_index_bits(int64_t max_block_len) {
     return bits;
 }
 
+extern "C" size_t oa_track_workspace_bytes(int64_t n_cur) {
+    return sizeof(int2) * (size_t)((n_cur + CHUNK - 1) / CHUNK + 1);
+}
+
+// Only the fill counters are cleared; slot buckets are validated by the counters
+// (and, on the fast path, by the ID check of the record).
 extern "C" int oa_table_clear(uint32_t* tab, int64_t n, int64_t n_regions, void* stream) {
     OA_REQUIRE(tab && n >= 0, "oa_table_clear: bad arguments");
-    OA_CUDA_CHECK(cudaMemsetAsync(tab, 0,
-                                  sizeof(uint32_t) * (size_t)oa_table_slots(n, n_regions),
-                                  static_cast<cudaStream_t>(stream)));
+    OA_CUDA_CHECK(cudaMemsetAsync(
+        tab, 0, sizeof(uint32_t) * (size_t)table_count_words(table_buckets(n, n_regions)),
+        static_cast<cudaStream_t>(stream)));
     return OA_OK;
 }
 
@@ -516,14 +699,19 @@ extern "C" int oa_track_fused(const oa_track_args* args, void* stream) {
     OA_REQUIRE(a.frame_dtype == OA_F32 || a.frame_dtype == OA_F64, "bad frame_dtype");
     OA_REQUIRE(!(a.data_dtype == OA_F64 && a.frame_dtype == OA_F32),
                "oa_track_fused: float64 data cannot have a float32 frame");
+    OA_REQUIRE(a.frame_dtype == OA_F64 || a.centre_f32 || a.onthefly,
+               "oa_track_fused: a float32 frame needs float32 region centres");
     if (a.n_cur == 0) return OA_OK;
     OA_REQUIRE(a.pos && a.vel && a.ids && a.cur_off && a.regions && a.rec_cur &&
                a.tab_cur && a.mark_cur, "oa_track_fused: NULL required pointer");
+    OA_REQUIRE(a.n_regions >= 1, "oa_track_fused: particles without a region");
     OA_REQUIRE(a.n_prev == 0 || !a.rec_prev || (a.tab_prev && a.mark_prev),
                "oa_track_fused: previous generation incomplete");
     OA_REQUIRE(a.cur_index_bits >= 1 && a.cur_index_bits <= 31, "bad cur_index_bits");
     OA_REQUIRE(!a.rec_prev || (a.prev_index_bits >= 1 && a.prev_index_bits <= 31),
                "bad prev_index_bits");
+    OA_REQUIRE(a.tab_cur_buckets > 0 && (!a.tab_prev || a.tab_prev_buckets > 0),
+               "oa_track_fused: table bucket counts missing (oa_table_buckets)");
 
     const bool hub = (a.hubble != 0.0) && !a.onthefly;
     const bool x64 = a.data_dtype == OA_F64, f64 = a.frame_dtype == OA_F64;

@@ -34,7 +34,8 @@ class Generation:
     """Carried state of one processed snapshot (reference
     ``track_orbits.py:234-240``), resident in HBM."""
     __slots__ = ('n', 'rec', 'tab', 'mark', 'index_bits', 'offsets',
-                 'halo_exists', 'frame_f64', 'ids_dtype', 'gpos', 'buckets')
+                 'halo_exists', 'frame_f64', 'ids_dtype', 'gpos', 'buckets',
+                 'n_buckets')
 
 
 class StepResult:
@@ -207,6 +208,9 @@ class OrbitTracker:
         # ---- region table (oa_region rows) ---------------------------------
         rows = np.zeros(n_h, dtype=_lib.REGION_DTYPE)
         rows['centre'] = region_positions.astype(np.float64).reshape(n_h, 3)
+        rows['centre_f'] = rows['centre']
+        rows['cur_begin'] = offsets[:-1]
+        rows['cur_count'] = np.diff(offsets)
         rows['prev_begin'] = -1
         matched = np.zeros(n_h, dtype=bool)
         if prev is not None and n_h and len(prev.halo_exists):
@@ -219,12 +223,13 @@ class OrbitTracker:
             rows['prev_bucket'][matched] = prev.buckets[k]
         # closed-form bucket ranges of this snapshot's table (see
         # oa_table_bucket_begin in include/orbit_b200.h)
-        buckets = (2 * offsets[:-1]) // 7 + np.arange(n_h, dtype=np.int64)
+        buckets = offsets[:-1] // 4 + np.arange(n_h, dtype=np.int64)
         rows['cur_bucket'] = buckets
         derive_bulk = region_bulk_vels is None
         if not derive_bulk:
             bulk = np.asarray(region_bulk_vels)
             rows['bulk'] = bulk.astype(np.float64).reshape(n_h, 3)
+            rows['bulk_f'] = rows['bulk']
             bulk_dtype = bulk.dtype if bulk.dtype in _F else np.dtype(
                 np.float64)
         else:
@@ -235,7 +240,7 @@ class OrbitTracker:
         n_m = len(seg_begin)
 
         # one packed host->device copy: [rows | offsets | seg_begin]
-        nb_rows, nb_off = 80 * n_h, 8 * (n_h + 1)
+        nb_rows, nb_off = 128 * n_h, 8 * (n_h + 1)
         pack = torch.empty(nb_rows + nb_off + 8 * max(n_m, 1),
                            dtype=torch.uint8, pin_memory=True)
         hp = pack.numpy()
@@ -274,6 +279,7 @@ class OrbitTracker:
         rec_bytes = lib.oa_record_bytes(int(frame_f64))
         gen.rec = self._empty(max(n, 1) * rec_bytes, torch.uint8)
         gen.tab = self._empty(lib.oa_table_slots(n, n_h), torch.int32)
+        gen.n_buckets = lib.oa_table_buckets(n, n_h)
         gen.mark = self._empty(max(n, 1) + 8, torch.int16)
 
         fdt = torch.float64 if frame_f64 else torch.float32
@@ -311,6 +317,7 @@ class OrbitTracker:
         a.one_plus_z = 1 + float(redshift)
         if prev is not None:
             a.rec_prev, a.tab_prev = ptr(prev.rec), ptr(prev.tab)
+            a.tab_prev_buckets = prev.n_buckets
             a.n_prev = prev.n
             a.prev_index_bits = prev.index_bits
             a.mark_prev = ptr(prev.mark)
@@ -325,6 +332,10 @@ class OrbitTracker:
                 ptr(diag['vr']), ptr(diag['r'])
             a.out_match = ptr(diag['match'])
         a.dangle_prev = ptr(dangle)
+        a.tab_cur_buckets = gen.n_buckets
+        a.workspace_bytes = lib.oa_track_workspace_bytes(n)
+        tile_ws = self._empty(a.workspace_bytes, torch.uint8)
+        a.workspace = ptr(tile_ws)
         check(lib.oa_table_clear(ptr(gen.tab), n, n_h, st))
         if self.timing is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), \
@@ -334,7 +345,7 @@ class OrbitTracker:
         if self.timing is not None:
             ev1.record(self._main())
             self.timing.append((ev0, ev1, n))
-        self.launches += 2
+        self.launches += 3
 
         p = Pending()
         p.n, p.n_h, p.n_m = n, n_h, n_m
@@ -342,7 +353,7 @@ class OrbitTracker:
         p.diag, p.dangle = diag, dangle
         p.derive_bulk, p.bulk_dtype = derive_bulk, bulk_dtype
         p.region_bulk_vels = region_bulk_vels
-        p.keep = (dev, d_pack, a)       # inputs stay alive until collected
+        p.keep = (dev, d_pack, a, tile_ws)       # inputs stay alive until collected
         p.h_bulk = p.h_angle = p.h_small = None
         p.sel = p.d_ids = p.d_ang = None
 

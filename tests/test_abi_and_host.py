@@ -37,10 +37,11 @@ def test_library_exports_every_declared_symbol():
     off = np.concatenate(([0], np.cumsum(lens)))
     begin = np.array([_lib.lib.oa_table_bucket_begin(int(off[j]), j)
                       for j in range(len(lens))])
-    nb = (2 * lens) // 7 + 1
+    nb = lens // 4 + 1
     assert np.all(begin[1:] >= begin[:-1] + nb[:-1])
-    assert (begin[-1] + nb[-1]) * 8 <= _lib.lib.oa_table_slots(
-        int(off[-1]), len(lens))
+    n_buckets = _lib.lib.oa_table_buckets(int(off[-1]), len(lens))
+    assert begin[-1] + nb[-1] <= n_buckets
+    assert _lib.lib.oa_table_slots(int(off[-1]), len(lens)) >= 9 * n_buckets
 
 
 def test_no_cpu_fallback_without_a_device():
