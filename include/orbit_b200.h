@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 7
+#define OA_ABI_VERSION 8
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -78,10 +78,11 @@ size_t oa_record_bytes(int frame_dtype);
  *     slot buckets, 8 uint32 slots (one 32-byte sector) per bucket ]
  * slot = fingerprint << index_bits | block-local particle index.  The buckets
  * of region block j (start `block_start`, length len) are
- *   [oa_table_bucket_begin(block_start, j), ... + len/4 + 1).
+ *   [oa_table_bucket_begin(block_start, j), ... + len/OA_BUCKET_LOAD + 1).
  * Only the counters need clearing between snapshots (oa_table_clear).        */
 #define OA_BUCKET_WORDS 8
 #define OA_BUCKET_SLOTS 8
+#define OA_BUCKET_LOAD 3   /* particles per bucket (mean fill of the 8 slots) */
 int64_t oa_table_bucket_begin(int64_t block_start, int64_t region_index);
 /* Number of buckets of the table for n region-particles in n_regions. */
 int64_t oa_table_buckets(int64_t n, int64_t n_regions);

@@ -38,6 +38,7 @@
 // contraction: compiled with -fmad=false and *_rn intrinsics where the order
 // matters) -- see SURVEY.md 2.2 / 7.4-7.6.
 #include "oa_common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace {
@@ -96,6 +97,11 @@ OA_D uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+OA_D uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 OA_D uint64_t policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -137,15 +143,6 @@ OA_D double ld_elem(const double* a, uint64_t pol) {
 }
 OA_D void st2(uint16_t* a, uint16_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(a), "h"(v), "l"(pol) : "memory");
-}
-OA_D void st4(uint32_t* a, uint32_t v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(a), "r"(v), "l"(pol) : "memory");
-}
-OA_D uint32_t atom_add(uint32_t* a, uint32_t v, uint64_t pol) {
-    uint32_t o;
-    asm volatile("atom.global.add.L2::cache_hint.u32 %0, [%1], %2, %3;"
-                 : "=r"(o) : "l"(a), "r"(v), "l"(pol) : "memory");
-    return o;
 }
 
 template <typename TF>
@@ -196,12 +193,16 @@ OA_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
 
 // ---- table geometry (closed forms, shared with the host through the C ABI) ------------
 // Region j (block start `off`, length len) owns buckets
-//   [off/4 + j, off/4 + j + len/4 + 1): mean fill <= 4 of 8 slots.
-OA_HD uint32_t bucket_count(int64_t len) { return (uint32_t)(len / 4 + 1); }
+//   [off/3 + j, off/3 + j + len/3 + 1): mean fill <= 3 of 8 slots, so that only
+// 0.4 % of the buckets overflow (Poisson) -- an overflow costs its whole warp a
+// second, serialised round trip.
+OA_HD uint32_t bucket_count(int64_t len) { return (uint32_t)(len / OA_BUCKET_LOAD + 1); }
 OA_HD int64_t bucket_begin(int64_t block_start, int64_t region) {
-    return block_start / 4 + region;
+    return block_start / OA_BUCKET_LOAD + region;
 }
-OA_HD int64_t table_buckets(int64_t n, int64_t n_regions) { return n / 4 + n_regions + 2; }
+OA_HD int64_t table_buckets(int64_t n, int64_t n_regions) {
+    return n / OA_BUCKET_LOAD + n_regions + 2;
+}
 // counters first (rounded up to whole sectors), then the slot buckets
 OA_HD int64_t table_count_words(int64_t buckets) { return (buckets + 7) / 8 * 8; }
 
@@ -389,7 +390,8 @@ OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Row* R,
     P.ins_home = oa_slot(h_slot, P.ins_nb);
     P.ins_b = (uint32_t)R->cur_bucket;
     P.ins_val = ((h_fp >> cbits) << cbits) | (P.c - (uint32_t)R->cur_begin);
-    P.ins_k = atom_add(k.cnt_cur + (P.ins_b + P.ins_home), 1u, pol_keep);
+    // (no L2 hint on the table writes: evict-last on them measured 20 % slower)
+    P.ins_k = atomicAdd(k.cnt_cur + (P.ins_b + P.ins_home), 1u);
 
     // probe of the previous table: one sector
     P.prev_count = (a.rec_prev != nullptr && R->prev_count > 0) ? (uint32_t)R->prev_count : 0u;
@@ -405,13 +407,13 @@ OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Row* R,
 }
 
 // Candidate record, exact ID check, apsis test, angle accumulator, outputs.
-template <typename TF, typename TVR>
+template <typename TF, typename TVR, bool DIAG>
 OA_D void track_finish(const oa_track_args& a, const TrackConst& k, Particle<TF, TVR>& P) {
     using AF = Ar<TF>;
     const OaRec<TF>* __restrict__ rec_prev = static_cast<const OaRec<TF>*>(a.rec_prev);
     OaRec<TF>* __restrict__ rec_cur = static_cast<OaRec<TF>*>(a.rec_cur);
     const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_keep = policy_evict_last();
+    const uint64_t pol_gather = policy_evict_normal();
     const uint32_t c = P.c;
 
     int64_t p = -1;
@@ -423,17 +425,24 @@ OA_D void track_finish(const oa_track_args& a, const TrackConst& k, Particle<TF,
             const uint32_t xr = P.bk.w[e] ^ P.fpshift;   // == index iff fingerprint equal
             if (xr < P.prev_count) cand = xr;
         }
-        bool slow = true;         // no candidate: a miss, unless the bucket overflowed
+        // Second round trip, issued by every lane at once: the candidate's record,
+        // or -- no fingerprint matched -- the fill counter of the home bucket,
+        // which tells a plain miss (newly entered particle) from an overflow.
+        bool slow;
         if (cand != 0xFFFFFFFFu) {
+            // normal eviction priority: HBM delivers 64 B, and the other half is
+            // the record of a neighbour that is gathered soon (-25 % HBM reads)
             p = (int64_t)P.prev_begin + (int64_t)cand;
-            prev = load_rec(rec_prev + p, pol_stream);
+            prev = load_rec(rec_prev + p, pol_gather);
             slow = prev.id != P.id;                   // stale slot / collision
+        } else {
+            slow = __ldcg(k.cnt_prev + (P.prb_b0 + P.prb_home)) > OA_BUCKET_SLOTS;
         }
         if (slow) {
             p = probe_slow<TF>(k.cnt_prev, k.slot_prev, P.prb_b0, P.prb_nb, P.prb_home,
                                P.fpshift, P.prev_count, rec_prev, P.prev_begin, P.id,
                                cand == 0xFFFFFFFFu);
-            if (p >= 0) prev = load_rec(rec_prev + p, pol_stream);
+            if (p >= 0) prev = load_rec(rec_prev + p, pol_gather);
         }
     }
 
@@ -469,22 +478,23 @@ OA_D void track_finish(const oa_track_args& a, const TrackConst& k, Particle<TF,
     st2(a.mark_cur + c, OA_NO_EVENT, pol_stream);
 
     if (P.ins_k < OA_BUCKET_SLOTS)
-        st4(k.slot_cur + (size_t)(P.ins_b + P.ins_home) * OA_BUCKET_WORDS + P.ins_k,
-            P.ins_val, pol_keep);
+        k.slot_cur[(size_t)(P.ins_b + P.ins_home) * OA_BUCKET_WORDS + P.ins_k] = P.ins_val;
     else               // home bucket full (rare): spill to the next ones
         insert_slow(k.cnt_cur, k.slot_cur, P.ins_b, P.ins_nb, P.ins_home, P.ins_val);
 
-    if (a.out_rhat) {
-        TF* o = static_cast<TF*>(a.out_rhat) + 3 * (size_t)c;
-        o[0] = P.rh[0]; o[1] = P.rh[1]; o[2] = P.rh[2];
+    if (DIAG) {        // optional per-particle outputs (checkpoint, diagnostics, on-the-fly)
+        if (a.out_rhat) {
+            TF* o = static_cast<TF*>(a.out_rhat) + 3 * (size_t)c;
+            o[0] = P.rh[0]; o[1] = P.rh[1]; o[2] = P.rh[2];
+        }
+        if (a.out_vr) static_cast<TVR*>(a.out_vr)[c] = P.vr;
+        if (a.out_r) static_cast<TF*>(a.out_r)[c] = P.r;
+        if (a.out_angle) a.out_angle[c] = __half_as_ushort(angle_new);
+        if (a.out_match) a.out_match[c] = p;
     }
-    if (a.out_vr) static_cast<TVR*>(a.out_vr)[c] = P.vr;
-    if (a.out_r) static_cast<TF*>(a.out_r)[c] = P.r;
-    if (a.out_angle) a.out_angle[c] = __half_as_ushort(angle_new);
-    if (a.out_match) a.out_match[c] = p;
 }
 
-template <typename TX, typename TF, typename TVR, bool HUBBLE>
+template <typename TX, typename TF, typename TVR, bool HUBBLE, bool DIAG>
 __global__ void __launch_bounds__(TRACK_THREADS, 1)
 oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__ TrackConst k) {
     using L = SlotLayout<TX>;
@@ -542,11 +552,11 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
     int2 jr_next = make_int2(0, 0);           // regions of the chunk D steps ahead
     if (first + D * stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + first + D * stride);
 
-    int t = 0;
-    for (int ch = first; ch < k.n_chunks; ch += stride, ++t) {
-        const int s = t % D;
+    int s = 0;
+    uint32_t phase = 0;
+    for (int ch = first; ch < k.n_chunks; ch += stride) {
         unsigned char* st = wsm + s * L::BYTES;
-        mbar_wait(&full[s], (uint32_t)(t / D) & 1u);
+        mbar_wait(&full[s], phase);
         const ChunkMeta meta = *reinterpret_cast<const ChunkMeta*>(st + L::META);
         const int64_t c = (int64_t)ch * CHUNK + lane;
         const bool active = c < n;
@@ -593,13 +603,14 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
             if (lane == 0) issue(ahead, s, jr_next);
             if (ahead + stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + ahead + stride);
         }
-        if (active) track_finish<TF, TVR>(a, k, P);
+        if (active) track_finish<TF, TVR, DIAG>(a, k, P);
+        if (++s == D) { s = 0; phase ^= 1u; }
     }
 }
 
-template <typename TX, typename TF, typename TVR, bool HUBBLE>
-int launch_track(const oa_track_args& a, cudaStream_t st) {
-    auto kern = oa_track_kernel<TX, TF, TVR, HUBBLE>;
+template <typename TX, typename TF, typename TVR, bool HUBBLE, bool DIAG>
+int launch_track_impl(const oa_track_args& a, cudaStream_t st) {
+    auto kern = oa_track_kernel<TX, TF, TVR, HUBBLE, DIAG>;
     using L = SlotLayout<TX>;
     constexpr int smem_bytes = TRACK_WARPS * L::DEPTH * L::BYTES;
     static bool configured = false;     // per instantiation
@@ -644,6 +655,13 @@ int launch_track(const oa_track_args& a, cudaStream_t st) {
     kern<<<(unsigned)grid, TRACK_THREADS, smem_bytes, st>>>(a, k);
     OA_LAUNCH_CHECK();
     return OA_OK;
+}
+
+template <typename TX, typename TF, typename TVR, bool HUBBLE>
+int launch_track(const oa_track_args& a, cudaStream_t st) {
+    const bool diag = a.out_rhat || a.out_vr || a.out_r || a.out_angle || a.out_match;
+    return diag ? launch_track_impl<TX, TF, TVR, HUBBLE, true>(a, st)
+                : launch_track_impl<TX, TF, TVR, HUBBLE, false>(a, st);
 }
 
 }  // namespace

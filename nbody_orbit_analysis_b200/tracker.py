@@ -84,25 +84,40 @@ class OrbitTracker:
         self.launches = 0          # kernels launched through the C ABI
         self.timing = None         # list of (start, stop, n) CUDA events of
         #                            the fused kernel when profiling is on
-        self.copy_stream = torch.cuda.Stream(self.device)
+        self.copy_stream = torch.cuda.Stream(self.device)   # device -> host
+        self.h2d_stream = torch.cuda.Stream(self.device)    # host -> device
+        self._pool = {}
+        self._step = 0             # submitted snapshots
+        self._consumed = {}        # ring slot -> event: inputs read by the kernel
+        self._last_events = 0      # event count of the last collected snapshot
 
     # -- buffers -------------------------------------------------------------
+    RING = 3      # generations / in-flight steps a buffer name cycles through
+
     def _empty(self, n, dtype):
-        """Uninitialised device buffer.  Sizes are rounded up to 1/8-octave
-        bins so that torch's caching allocator sees the same few block sizes
-        every snapshot (particle counts drift by a few per cent from snapshot
-        to snapshot; unbinned requests fragment the cache and fall back to
-        synchronising cudaMalloc/cudaFree calls)."""
-        n = int(n)
+        """Uninitialised device buffer from torch's caching allocator (used
+        for buffers handed to the caller)."""
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
+
+    def _buf(self, name, n, dtype, slot=None):
+        """Persistent device buffer ``name`` of the ring slot of the current
+        step.  The tracker owns its working set in HBM: a buffer is allocated
+        once, grows geometrically when a later snapshot needs more (particle
+        counts drift by a few per cent between snapshots) and is otherwise
+        reused every ``RING`` steps.  Reuse is safe without events because every
+        kernel that touches these buffers is ordered on the main stream; the
+        copy stream only reads per-step outputs, which ``collect`` has
+        synchronised on long before their slot comes round again."""
+        slot = self._step % self.RING if slot is None else slot
         item = torch.empty(0, dtype=dtype).element_size()
-        nbytes = n * item
-        if nbytes > (1 << 20):
-            step = (1 << (nbytes - 1).bit_length()) >> 3
-            nbytes = -(-nbytes // step) * step
-        else:
-            nbytes = -(-max(nbytes, 1) // 512) * 512
-        raw = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        return raw[:n * item].view(dtype)
+        nbytes = max(int(n), 1) * item
+        key = (name, slot)
+        raw = self._pool.get(key)
+        if raw is None or raw.numel() < nbytes:
+            cap = -(-int(nbytes * 1.25) // 512) * 512
+            raw = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self._pool[key] = raw
+        return raw[:int(n) * item].view(dtype)
 
     def _main(self):
         return torch.cuda.current_stream(self.device)
@@ -110,19 +125,30 @@ class OrbitTracker:
     def _stream(self):
         return C.c_void_p(self._main().cuda_stream)
 
-    def _to_device(self, arr, dtype=None):
-        """Host numpy array -> device tensor through pinned staging."""
+    def _to_device(self, arr, dtype=None, name=None):
+        """Host numpy array -> device tensor.
+
+        With ``name`` the destination is the tracker's ring buffer of that name
+        and the copy runs on the host->device stream, so that the upload of
+        snapshot s+1 overlaps the kernels of snapshot s (double-buffered
+        ingest); the main stream waits for it in ``_inputs_ready``.  Pageable
+        arrays are staged through pinned memory first."""
         arr = np.ascontiguousarray(arr, dtype=dtype)
         t = torch.from_numpy(arr.reshape(-1))
         if t.numel() == 0:
             return torch.empty(0, dtype=t.dtype, device=self.device)
         if not t.is_pinned():
             # torch's caching host allocator hands the block back only after
-            # the copy that reads it has completed on this stream
+            # the copy that reads it has completed on its stream
             buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
             buf.copy_(t)
             t = buf
-        return t.to(self.device, non_blocking=True)
+        if name is None:
+            return t.to(self.device, non_blocking=True)
+        dst = self._buf(name, t.numel(), t.dtype)
+        with torch.cuda.stream(self.h2d_stream):
+            dst.copy_(t, non_blocking=True)
+        return dst
 
     def _to_host_async(self, t, n=None):
         """Device tensor -> pinned host tensor on the copy stream (the caller
@@ -157,12 +183,22 @@ class OrbitTracker:
         ids = np.asarray(snapshot['ids'])
         n = len(ids)
         masses = snapshot['masses']
+        # the ring slot is free once the kernel that read it three steps ago
+        # has finished
+        slot = self._step % self.RING
+        ev = self._consumed.get(slot)
+        if ev is not None:
+            self.h2d_stream.wait_event(ev)
         dev = {
-            'pos': self._to_device(coords), 'vel': self._to_device(vels),
-            'ids': self._to_device(ids, np.int64),
-            'mass': self._to_device(_as_f(masses, 'masses'))
+            'pos': self._to_device(coords, name='in_pos'),
+            'vel': self._to_device(vels, name='in_vel'),
+            'ids': self._to_device(ids, np.int64, name='in_ids'),
+            'mass': self._to_device(_as_f(masses, 'masses'), name='in_mass')
             if isinstance(masses, np.ndarray) else None,
         }
+        uploaded = torch.cuda.Event()
+        uploaded.record(self.h2d_stream)
+        self._main().wait_event(uploaded)
         offsets = np.concatenate((
             np.asarray(snapshot['region_offsets'], dtype=np.int64), [n]))
         return self.submit_device(
@@ -223,7 +259,8 @@ class OrbitTracker:
             rows['prev_bucket'][matched] = prev.buckets[k]
         # closed-form bucket ranges of this snapshot's table (see
         # oa_table_bucket_begin in include/orbit_b200.h)
-        buckets = offsets[:-1] // 4 + np.arange(n_h, dtype=np.int64)
+        buckets = offsets[:-1] // _lib.BUCKET_LOAD + np.arange(
+            n_h, dtype=np.int64)
         rows['cur_bucket'] = buckets
         derive_bulk = region_bulk_vels is None
         if not derive_bulk:
@@ -248,7 +285,8 @@ class OrbitTracker:
         hp[nb_rows:nb_rows + nb_off] = offsets.view(np.uint8)
         hp[nb_rows + nb_off:nb_rows + nb_off + 8 * n_m] = \
             seg_begin.view(np.uint8)
-        d_pack = pack.to(self.device, non_blocking=True)
+        d_pack = self._buf('pack', pack.numel(), torch.uint8)
+        d_pack.copy_(pack, non_blocking=True)
         d_rows = d_pack[:nb_rows]
         d_off = d_pack[nb_rows:nb_rows + nb_off]
         d_seg = d_pack[nb_rows + nb_off:]
@@ -256,8 +294,8 @@ class OrbitTracker:
         d_bulk_out = None
         if derive_bulk:
             ws_bytes = lib.oa_bulk_workspace_bytes(n, n_h)
-            ws = self._empty(ws_bytes, torch.uint8)
-            d_bulk_out = self._empty(max(3 * n_h, 1), torch.float64)
+            ws = self._buf('bulk_ws', ws_bytes, torch.uint8)
+            d_bulk_out = self._buf('bulk_out', max(3 * n_h, 1), torch.float64)
             check(lib.oa_bulk_velocity(
                 ptr(dev['vel']), _lib.dtype_code(data_dtype), ptr(dev['mass']),
                 _lib.dtype_code(mass_dtype) if mass_dtype is not None else 0,
@@ -277,10 +315,10 @@ class OrbitTracker:
         gen.gpos = gpos
         gen.buckets = buckets
         rec_bytes = lib.oa_record_bytes(int(frame_f64))
-        gen.rec = self._empty(max(n, 1) * rec_bytes, torch.uint8)
-        gen.tab = self._empty(lib.oa_table_slots(n, n_h), torch.int32)
+        gen.rec = self._buf('rec', max(n, 1) * rec_bytes, torch.uint8)
+        gen.tab = self._buf('tab', lib.oa_table_slots(n, n_h), torch.int32)
         gen.n_buckets = lib.oa_table_buckets(n, n_h)
-        gen.mark = self._empty(max(n, 1) + 8, torch.int16)
+        gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16)
 
         fdt = torch.float64 if frame_f64 else torch.float32
         diag = None
@@ -334,7 +372,7 @@ class OrbitTracker:
         a.dangle_prev = ptr(dangle)
         a.tab_cur_buckets = gen.n_buckets
         a.workspace_bytes = lib.oa_track_workspace_bytes(n)
-        tile_ws = self._empty(a.workspace_bytes, torch.uint8)
+        tile_ws = self._buf('chunk_ws', a.workspace_bytes, torch.uint8)
         a.workspace = ptr(tile_ws)
         check(lib.oa_table_clear(ptr(gen.tab), n, n_h, st))
         if self.timing is not None:
@@ -346,6 +384,9 @@ class OrbitTracker:
             ev1.record(self._main())
             self.timing.append((ev0, ev1, n))
         self.launches += 3
+        consumed = torch.cuda.Event()
+        consumed.record(self._main())
+        self._consumed[self._step % self.RING] = consumed
 
         p = Pending()
         p.n, p.n_h, p.n_m = n, n_h, n_m
@@ -361,15 +402,16 @@ class OrbitTracker:
         if prev is not None and not self.onthefly:
             cap = max(min(prev.n, n), 1)
             ws_bytes = lib.oa_select_workspace_bytes(prev.n)
-            ws = self._empty(ws_bytes, torch.uint8)
-            d_small = self._empty(n_m + 1, torch.int64)   # offsets..., total
+            ws = self._buf('sel_ws', ws_bytes, torch.uint8)
+            d_small = self._buf('small', n_m + 1, torch.int64)  # offsets..., total
             d_total = d_small[n_m:]
             check(lib.oa_select_count(
                 ptr(prev.mark), prev.n, _lib.OA_SEL_NE, _lib.OA_NO_EVENT,
                 ptr(ws), ws_bytes, ptr(d_total), st))
-            p.sel = self._empty(cap, torch.int64)
-            p.d_ids = self._empty(cap, torch.int64)
-            p.d_ang = self._empty(cap, torch.int16)
+            # (valid until RING further snapshots have been submitted)
+            p.sel = self._buf('sel', cap, torch.int64)
+            p.d_ids = self._buf('ev_ids', cap, torch.int64)
+            p.d_ang = self._buf('ev_ang', cap, torch.int16)
             check(lib.oa_select_gather(
                 ptr(prev.mark), prev.n, _lib.OA_SEL_NE, _lib.OA_NO_EVENT,
                 ptr(ws), ptr(p.sel), st))
@@ -390,8 +432,16 @@ class OrbitTracker:
         done = torch.cuda.Event()
         done.record(self._main())
         self.copy_stream.wait_event(done)
+        p.h_ids = p.h_ang = None
+        p.n_spec = 0
         if d_small is not None:
             p.h_small = self._to_host_async(d_small)
+            # speculative copy of the event lists: their exact length is only
+            # known on the device, so copy as many records as the last snapshot
+            # produced (+25 %) now and the remainder, if any, in collect()
+            p.n_spec = min(cap, int(self._last_events * 1.25) + 1024)
+            p.h_ids = self._to_host_async(p.d_ids, p.n_spec)
+            p.h_ang = self._to_host_async(p.d_ang, p.n_spec)
         if derive_bulk:
             p.h_bulk = self._to_host_async(d_bulk_out, 3 * n_h)
             p.keep += (d_bulk_out,)
@@ -401,6 +451,7 @@ class OrbitTracker:
         p.small_done = torch.cuda.Event()
         p.small_done.record(self.copy_stream)
         self.prev = gen
+        self._step += 1
         return p
 
     def collect_keep(self, p):
@@ -431,14 +482,16 @@ class OrbitTracker:
             small = p.h_small.numpy()
             total = int(small[p.n_m])
             res.apsis_offsets = small.copy()
-            h_ids = self._to_host_async(p.d_ids, total)
-            h_ang = self._to_host_async(p.d_ang, total)
-            self.copy_stream.synchronize()
+            self._last_events = total
+            if total > p.n_spec:          # the speculative copy fell short
+                p.h_ids = self._to_host_async(p.d_ids, total)
+                p.h_ang = self._to_host_async(p.d_ang, total)
+                self.copy_stream.synchronize()
             res.n_events = total
-            ids = h_ids.numpy()
+            ids = p.h_ids.numpy()[:total]
             res.apsis_ids = ids if p.prev.ids_dtype == np.int64 else \
                 ids.astype(p.prev.ids_dtype)
-            res.apsis_angles = h_ang.numpy().view(np.float16)
+            res.apsis_angles = p.h_ang.numpy()[:total].view(np.float16)
             res.apsis_prev_index = p.sel[:total]
         if release:
             p.keep = None

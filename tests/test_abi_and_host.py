@@ -37,8 +37,10 @@ def test_library_exports_every_declared_symbol():
     off = np.concatenate(([0], np.cumsum(lens)))
     begin = np.array([_lib.lib.oa_table_bucket_begin(int(off[j]), j)
                       for j in range(len(lens))])
-    nb = lens // 4 + 1
+    nb = lens // _lib.BUCKET_LOAD + 1
     assert np.all(begin[1:] >= begin[:-1] + nb[:-1])
+    assert np.array_equal(begin, off[:-1] // _lib.BUCKET_LOAD + np.arange(
+        len(lens)))
     n_buckets = _lib.lib.oa_table_buckets(int(off[-1]), len(lens))
     assert begin[-1] + nb[-1] <= n_buckets
     assert _lib.lib.oa_table_slots(int(off[-1]), len(lens)) >= 9 * n_buckets

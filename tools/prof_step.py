@@ -27,5 +27,5 @@ run()
 trk=OrbitTracker()
 torch.cuda.synchronize()
 pr=cProfile.Profile(); pr.enable(); run(); torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(25)
+pstats.Stats(pr).sort_stats('tottime').print_stats(30)
 print(torch.cuda.memory_stats()['num_alloc_retries'], torch.cuda.memory_stats()['num_device_alloc'], torch.cuda.memory_stats()['num_device_free'])
