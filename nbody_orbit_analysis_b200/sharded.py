@@ -90,13 +90,17 @@ class Comm:
         counts = local_counts.clone()
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
 
-        def gather(x):
-            pad = torch.zeros(cap, dtype=x.dtype, device=self.device)
-            pad[:x.numel()] = x
-            out = [torch.empty_like(pad) for _ in range(self.world)]
-            dist.all_gather(out, pad)
-            return torch.cat([o[:s] for o, s in zip(out, sizes)])
-        return gather(keys), gather(ids), gather(angles), counts
+        # one all-gather of packed (key, id, angle bits) records
+        rec = torch.zeros((cap, 3), dtype=torch.int64, device=self.device)
+        m = keys.numel()
+        rec[:m, 0] = keys
+        rec[:m, 1] = ids
+        rec[:m, 2] = angles.to(torch.int64)
+        out = [torch.empty_like(rec) for _ in range(self.world)]
+        dist.all_gather(out, rec)
+        rec = torch.cat([o[:s] for o, s in zip(out, sizes)])
+        return (rec[:, 0].contiguous(), rec[:, 1].contiguous(),
+                rec[:, 2].to(angles.dtype).contiguous(), counts)
 
     def merge_events(self, tracker, res):
         """Turn a rank-local ``StepResult`` into the global event lists (same
@@ -117,26 +121,43 @@ class Comm:
             res.apsis_angles.view(np.int16)).to(self.device)
         local_counts = torch.from_numpy(
             np.diff(res.apsis_offsets)).to(self.device)
-        keys, ids, ang, counts = self.exchange_events(
-            keys[:E], ids, ang, local_counts)
-        total = keys.numel()
-        order_keys, perm = self.sort_keys(keys, st)
-        ids_o = torch.empty(max(total, 1), dtype=torch.int64,
-                            device=self.device)
-        ang_o = torch.empty(max(total, 1), dtype=torch.int16,
-                            device=self.device)
-        check(lib.oa_gather_i64(ptr(ids), ptr(perm), total, None, ptr(ids_o),
-                                 st))
-        check(lib.oa_gather_u16(ptr(ang), ptr(perm), total, None, ptr(ang_o),
-                                 st))
+        def order(keys_all):
+            _, perm = self.sort_keys(keys_all, st)
+            return perm
+
+        def take(src, perm):
+            out = torch.empty(max(perm.numel(), 1), dtype=src.dtype,
+                              device=self.device)
+            fn = lib.oa_gather_i64 if src.dtype == torch.int64 else \
+                lib.oa_gather_u16
+            check(fn(ptr(src), ptr(perm), perm.numel(), None, ptr(out), st))
+            return out[:perm.numel()]
+        ids_o, ang_o, offsets = self.merge(keys[:E], ids, ang, local_counts,
+                                           order, take)
         tracker.launches += 3
-        res.apsis_ids = ids_o[:total].cpu().numpy().astype(
-            gen.ids_dtype, copy=False)
-        res.apsis_angles = ang_o[:total].cpu().numpy().view(np.float16)
-        res.apsis_offsets = np.concatenate(
-            ([0], np.cumsum(counts.cpu().numpy()))).astype(np.int64)
-        res.n_events = total
+        res.apsis_ids = ids_o.cpu().numpy().astype(gen.ids_dtype, copy=False)
+        res.apsis_angles = ang_o.cpu().numpy().view(np.float16)
+        res.apsis_offsets = offsets
+        res.n_events = int(ids_o.numel())
         return res
+
+    def merge(self, keys, ids, angles, local_counts, order, take):
+        """Exchange + ordering step shared by the GPU path and the gloo tests.
+
+        ``keys`` are the positions of the rank's event particles in the
+        UNSHARDED previous snapshot; sorting the gathered records by key
+        reproduces the reference order (``track_orbits.py:315-316``) because the
+        blocks of the halos are contiguous there.  ``order(keys) -> perm`` and
+        ``take(src, perm)`` are the device primitives (radix sort / gather
+        through the C ABI on the GPU)."""
+        keys, ids, angles, counts = self.exchange_events(
+            keys, ids, angles, local_counts)
+        if keys.numel():
+            perm = order(keys)
+            ids, angles = take(ids, perm), take(angles, perm)
+        offsets = np.concatenate(
+            ([0], np.cumsum(counts.cpu().numpy()))).astype(np.int64)
+        return ids, angles, offsets
 
     def sort_keys(self, keys, st):
         """Radix sort of int64 order keys; returns (sorted keys, permutation)."""
