@@ -44,6 +44,10 @@ def parse():
                     help='particles per GPU (universe size)')
     ap.add_argument('--halos', type=int, default=1000)
     ap.add_argument('--mode', default='pericentric')
+    ap.add_argument('--depth', type=int, default=2,
+                    help='snapshots submitted ahead of the one being collected')
+    ap.add_argument('--profile', action='store_true',
+                    help='cProfile of the timed host loop (to stderr)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-particles', type=int, default=400000,
@@ -83,36 +87,43 @@ class ClockSampler:
     REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'),
                (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
 
-    def __init__(self, index=0, period=0.01):
+    def __init__(self, index=0, period=None):
+        period = float(os.environ.get('OA_BENCH_CLOCK_PERIOD', '0.01')) \
+            if period is None else period
         self.index, self.period = index, period
         self.rows = []
         self.proc = None
 
     def start(self):
+        import tempfile
         try:
             vis = os.environ.get('CUDA_VISIBLE_DEVICES')
             idx = int(vis.split(',')[self.index]) if vis else self.index
         except (ValueError, IndexError):
             idx = self.index
         try:
+            # output goes to a file: no reader thread competes for the GIL of
+            # the (host-bound) benchmark loop
+            self.out = tempfile.NamedTemporaryFile(
+                'w+', prefix='oa_clocks_', suffix='.csv', delete=False)
             self.proc = subprocess.Popen(
                 [sys.executable, '-c', SAMPLER_SRC, str(idx), str(self.period)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+                stdout=self.out, stderr=subprocess.DEVNULL)
             time.sleep(0.5)          # NVML initialisation happens before timing
         except OSError:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
 
     def stop(self, t0, t1):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
         time.sleep(2 * self.period)
         self.proc.terminate()
+        self.proc.wait()
+        self.out.flush()
+        self.out.seek(0)
+        self.rows = [ln.strip() for ln in self.out.read().splitlines()]
+        self.out.close()
+        os.unlink(self.out.name)
         sm, smax, reasons = [], [], set()
         for line in list(self.rows):
             f = line.split(',')
@@ -284,27 +295,32 @@ def run_b200(args):
 
     def collect_step(trk, pending):
         res = trk.collect(pending)
-        if comm is not None and res.apsis_ids is not None:
-            res = comm.merge_events(trk, res)
+        if comm is not None and res.apsis_offsets is not None:
+            # the merged lists are needed on the host by the writing rank only
+            res = comm.merge_events(trk, res, to_host=(rank == 0))
         return res
 
     def timed_run(host=None):
-        """W+1 untimed snapshots, then K timed ones.  Snapshot t+1 is submitted
-        before the results of snapshot t are collected (software pipeline: the
-        host-side collection overlaps the next snapshot's kernels)."""
+        """W+1 untimed snapshots, then K timed ones.  Up to `depth` snapshots
+        are submitted ahead of the one whose results are being collected
+        (software pipeline: host-side collection, H2D and D2H overlap the
+        kernels of the following snapshots)."""
         trk = OrbitTracker(mode=args.mode)
+        trk.events_on_device = comm is not None
         # nvidia-smi is started before the warm-up: its NVML initialisation
         # stalls CUDA calls for tens of ms and must not fall in the timed region
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        pending = None
+        from collections import deque
+        depth = max(1, args.depth)     # snapshots in flight (tracker ring = 3)
+        queue = deque()
         for t in range(0, W + 1):      # same pipelined pattern as the timed loop
-            nxt = submit_step(trk, t, host)
-            if pending is not None:
-                collect_step(trk, pending)
-            pending = nxt
-        collect_step(trk, pending)
+            queue.append(submit_step(trk, t, host))
+            if len(queue) > depth:
+                collect_step(trk, queue.popleft())
+        while queue:
+            collect_step(trk, queue.popleft())
         trk.timing = []
         launches0 = trk.launches
         barrier()
@@ -313,17 +329,30 @@ def run_b200(args):
         wall0 = time.time()
         ev0.record()
         n_part = n_events = 0
-        last = pending = None
+        last = None
+
+        def take(p):
+            nonlocal n_part, n_events, last
+            last = collect_step(trk, p)
+            n_part += last.n
+            n_events += last.n_events
+        prof = None
+        if args.profile and rank == 0:
+            import cProfile
+            prof = cProfile.Profile()
+            prof.enable()
         for t in range(W + 1, W + K + 1):
-            nxt = submit_step(trk, t, host)
-            if pending is not None:
-                last = collect_step(trk, pending)
-                n_part += last.n
-                n_events += last.n_events
-            pending = nxt
-        last = collect_step(trk, pending)
-        n_part += last.n
-        n_events += last.n_events
+            queue.append(submit_step(trk, t, host))
+            if len(queue) > depth:
+                take(queue.popleft())
+        while queue:
+            take(queue.popleft())
+        if prof is not None:
+            import pstats
+            prof.disable()
+            st_ = pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime')
+            st_.print_stats(12)
+            st_.print_callers('torch.empty')
         ev1.record()
         barrier()
         wall1 = time.time()

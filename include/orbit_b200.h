@@ -260,6 +260,15 @@ int oa_run_heads(const uint64_t* seg, const int64_t* ids, int64_t n,
 /* counts[k] = length of run k given the ascending run start positions. */
 int oa_run_lengths(const int64_t* starts, int64_t n_runs, int64_t n,
                    int64_t* counts, void* stream);
+/* Multi-GPU event ordering: merge n_lists event lists, each
+ * ascending in `keys` (= position of the event particle in the UNSHARDED
+ * previous snapshot, distinct across lists) and stored back to back
+ * (list r = [list_off[r], list_off[r+1])), into one list in key order -- the
+ * reference's event order, track_orbits.py:315-316. */
+int oa_merge_event_lists(const int64_t* keys, const int64_t* ids,
+                         const uint16_t* angles, int64_t n,
+                         const int64_t* list_off, int n_lists, int64_t* ids_out,
+                         uint16_t* angles_out, void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
 

@@ -134,6 +134,8 @@ _sig('oa_sort_pairs_u64', C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
 _sig('oa_minmax_i64', C.c_int, _vp, _i64, _vp, _vp)
 _sig('oa_segment_sort_keys', C.c_int, _vp, _i64, _vp, C.c_int, _vp, _vp, _vp,
      _vp, _vp, _vp)
+_sig('oa_merge_event_lists', C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, _vp,
+     _vp, _vp)
 _sig('oa_run_heads', C.c_int, _vp, _vp, _i64, _vp, _vp)
 _sig('oa_run_lengths', C.c_int, _vp, _i64, _i64, _vp, _vp)
 _sig('oa_synth_keys', C.c_int, C.POINTER(SynthParams), _vp, _vp, _vp, _vp)
@@ -155,7 +157,7 @@ EXPORTS = [
     'oa_sort_workspace_bytes',
     'oa_sort_pairs_u64', 'oa_minmax_i64', 'oa_synth_keys', 'oa_synth_fill',
     'oa_synth_params_size', 'oa_segment_sort_keys', 'oa_run_heads',
-    'oa_run_lengths',
+    'oa_run_lengths', 'oa_merge_event_lists',
 ]
 
 

@@ -51,6 +51,34 @@ __global__ void run_lengths_kernel(const int64_t* __restrict__ starts, int64_t n
     counts[k] = next - starts[k];
 }
 
+// Multi-way merge of n_lists ascending key lists laid out back to back
+// (list r = [list_off[r], list_off[r+1])): the output position of an element is
+// its own rank plus the number of smaller keys in every other list (keys are
+// distinct across lists: they are positions in one unsharded snapshot).
+__global__ void merge_lists_kernel(const int64_t* __restrict__ keys,
+                                   const int64_t* __restrict__ ids,
+                                   const uint16_t* __restrict__ angles, int64_t n,
+                                   const int64_t* __restrict__ list_off, int n_lists,
+                                   int64_t* __restrict__ ids_out,
+                                   uint16_t* __restrict__ angles_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t key = keys[i];
+    int64_t pos = 0;
+    for (int r = 0; r < n_lists; ++r) {
+        const int64_t b = __ldg(list_off + r), e = __ldg(list_off + r + 1);
+        if (i >= b && i < e) { pos += i - b; continue; }
+        int64_t lo = b, hi = e;                 // first element of list r with key' >= key
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        pos += lo - b;
+    }
+    ids_out[pos] = ids[i];
+    angles_out[pos] = angles[i];
+}
+
 inline unsigned blocks_for(int64_t n, int threads) {
     return (unsigned)((n + threads - 1) / threads);
 }
@@ -67,6 +95,20 @@ extern "C" int oa_segment_sort_keys(const int64_t* ids, int64_t n, const int64_t
                "oa_segment_sort_keys: bad arguments");
     segment_sort_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(
         ids, n, seg_off, n_seg, sort_flag, id_minmax, key_lo, key_hi, index);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_merge_event_lists(const int64_t* keys, const int64_t* ids,
+                                    const uint16_t* angles, int64_t n,
+                                    const int64_t* list_off, int n_lists, int64_t* ids_out,
+                                    uint16_t* angles_out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n <= 0) return OA_OK;
+    OA_REQUIRE(keys && ids && angles && list_off && ids_out && angles_out && n_lists >= 1,
+               "oa_merge_event_lists: bad arguments");
+    merge_lists_kernel<<<blocks_for(n, 256), 256, 0, st>>>(keys, ids, angles, n, list_off,
+                                                           n_lists, ids_out, angles_out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

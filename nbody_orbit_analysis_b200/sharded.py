@@ -52,6 +52,7 @@ class Comm:
             device = torch.device('cuda', torch.cuda.current_device()) \
                 if dist.get_backend() == 'nccl' else torch.device('cpu')
         self.device = device
+        self.stream = None           # CUDA stream of the exchange (NCCL path)
 
     # -- catalogue ---------------------------------------------------------------
     def broadcast_catalogue(self, pos, rad, bulk):
@@ -65,9 +66,18 @@ class Comm:
             buf[3 * n_h:4 * n_h] = rad
             if has_bulk:
                 buf[4 * n_h:] = np.asarray(bulk).reshape(-1)
-        t = torch.from_numpy(buf).to(self.device)
-        dist.broadcast(t, src=0)
-        out = t.cpu().numpy()
+        if self.device.type == 'cuda':
+            # on the exchange stream: independent of the kernels in flight
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(self.device)
+            with torch.cuda.stream(self.stream):
+                t = torch.from_numpy(buf).to(self.device)
+                dist.broadcast(t, src=0)
+                out = t.cpu().numpy()
+        else:
+            t = torch.from_numpy(buf)
+            dist.broadcast(t, src=0)
+            out = t.numpy()
         pos_o = out[:3 * n_h].reshape(n_h, 3).astype(pos.dtype)
         rad_o = out[3 * n_h:4 * n_h].astype(rad.dtype)
         bulk_o = out[4 * n_h:].reshape(n_h, 3).astype(
@@ -75,70 +85,108 @@ class Comm:
         return pos_o, rad_o, bulk_o
 
     # -- events --------------------------------------------------------------------
-    def exchange_events(self, keys, ids, angles, local_counts):
-        """All-gather variable-length event records and all-reduce the per-halo
-        counts.  Device-agnostic (tensors live on ``self.device``).
+    def exchange_events(self, keys, ids, angles, local_counts,
+                        return_sizes=False):
+        """Two collectives per snapshot: an all-gather of every rank's
+        ``[per-halo event counts | number of events]`` (summed on the host it
+        is the all-reduce that gives the global ``region_offsets``) and an
+        all-gather of the packed, padded event records.  Device-agnostic
+        (tensors live on ``self.device``).
 
         Returns ``(keys, ids, angles, global_counts)`` with the records of all
-        ranks concatenated in rank order."""
-        n_loc = torch.tensor([keys.numel()], dtype=torch.int64,
-                             device=self.device)
-        sizes = [torch.zeros_like(n_loc) for _ in range(self.world)]
-        dist.all_gather(sizes, n_loc)
-        sizes = [int(s.item()) for s in sizes]
-        cap = max(max(sizes), 1)
-        counts = local_counts.clone()
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-
-        # one all-gather of packed (key, id, angle bits) records
-        rec = torch.zeros((cap, 3), dtype=torch.int64, device=self.device)
+        ranks concatenated in rank order; ``global_counts`` is a host array."""
         m = keys.numel()
+        meta = torch.cat((local_counts.to(torch.int64).reshape(-1),
+                          torch.tensor([m], dtype=torch.int64,
+                                       device=self.device)))
+        meta_all = torch.empty(self.world * meta.numel(), dtype=torch.int64,
+                               device=self.device)
+        dist.all_gather_into_tensor(meta_all, meta)
+        meta_all = meta_all.cpu().numpy().reshape(self.world, -1)  # one sync
+        sizes = [int(v) for v in meta_all[:, -1]]
+        counts = meta_all[:, :-1].sum(axis=0)
+        cap = max(max(sizes), 1)
+
+        rec = torch.empty((cap, 3), dtype=torch.int64, device=self.device)
         rec[:m, 0] = keys
         rec[:m, 1] = ids
         rec[:m, 2] = angles.to(torch.int64)
-        out = [torch.empty_like(rec) for _ in range(self.world)]
-        dist.all_gather(out, rec)
-        rec = torch.cat([o[:s] for o, s in zip(out, sizes)])
-        return (rec[:, 0].contiguous(), rec[:, 1].contiguous(),
-                rec[:, 2].to(angles.dtype).contiguous(), counts)
+        rec_all = torch.empty(self.world * cap * 3, dtype=torch.int64,
+                              device=self.device)
+        dist.all_gather_into_tensor(rec_all, rec.reshape(-1))
+        rec_all = rec_all.reshape(self.world * cap, 3)
+        if any(sz != cap for sz in sizes):          # drop the padding
+            rec = torch.cat([rec_all[r * cap:r * cap + sz]
+                             for r, sz in enumerate(sizes)])
+        else:
+            rec = rec_all
+        out = (rec[:, 0].contiguous(), rec[:, 1].contiguous(),
+               rec[:, 2].to(angles.dtype).contiguous(), counts)
+        return out + (sizes,) if return_sizes else out
 
-    def merge_events(self, tracker, res):
-        """Turn a rank-local ``StepResult`` into the global event lists (same
-        on every rank), ordered like the unsharded reference run."""
+    def merge_events(self, tracker, res, to_host=True):
+        """Turn a rank-local ``StepResult`` (events left in HBM, see
+        ``OrbitTracker.events_on_device``) into the global event lists, ordered
+        like the unsharded reference run.  Every rank's list is already
+        ascending in the order key, so the ordering step is a multi-way merge
+        (``oa_merge_event_lists``), not a sort.  With ``to_host=False`` the
+        merged lists stay on the device (``res.d_ids`` / ``res.d_ang``): only
+        the rank that writes the result file needs them on the host."""
         gen = res.prev_gen
         if gen is None or gen.gpos is None:
             raise _lib.OrbitB200Error(
                 "sharded tracking needs the global block position of every "
                 "particle (pass gpos= to step_device)")
-        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        E = res.n_events
-        sel = res.apsis_prev_index
-        keys = torch.empty(max(E, 1), dtype=torch.int64, device=self.device)
-        check(lib.oa_gather_i64(ptr(gen.gpos), ptr(sel), E, None, ptr(keys), st))
-        ids = torch.from_numpy(
-            res.apsis_ids.astype(np.int64, copy=False)).to(self.device)
-        ang = torch.from_numpy(
-            res.apsis_angles.view(np.int16)).to(self.device)
-        local_counts = torch.from_numpy(
-            np.diff(res.apsis_offsets)).to(self.device)
-        def order(keys_all):
-            _, perm = self.sort_keys(keys_all, st)
-            return perm
-
-        def take(src, perm):
-            out = torch.empty(max(perm.numel(), 1), dtype=src.dtype,
-                              device=self.device)
-            fn = lib.oa_gather_i64 if src.dtype == torch.int64 else \
-                lib.oa_gather_u16
-            check(fn(ptr(src), ptr(perm), perm.numel(), None, ptr(out), st))
-            return out[:perm.numel()]
-        ids_o, ang_o, offsets = self.merge(keys[:E], ids, ang, local_counts,
-                                           order, take)
-        tracker.launches += 3
-        res.apsis_ids = ids_o.cpu().numpy().astype(gen.ids_dtype, copy=False)
-        res.apsis_angles = ang_o.cpu().numpy().view(np.float16)
-        res.apsis_offsets = offsets
-        res.n_events = int(ids_o.numel())
+        # The exchange runs on its own stream, after this snapshot's compaction
+        # only: it overlaps the kernels of the NEXT snapshot, which the caller
+        # has already submitted on the main stream.
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(self.device)
+        self.stream.wait_event(res.compacted)
+        with torch.cuda.stream(self.stream):
+            st = C.c_void_p(self.stream.cuda_stream)
+            E = res.n_events
+            if res.d_ids is None:
+                res.d_ids = torch.from_numpy(
+                    res.apsis_ids.astype(np.int64, copy=False)).to(self.device)
+                res.d_ang = torch.from_numpy(
+                    res.apsis_angles.view(np.int16)).to(self.device)
+            keys = torch.empty(max(E, 1), dtype=torch.int64,
+                               device=self.device)
+            check(lib.oa_gather_i64(ptr(gen.gpos), ptr(res.apsis_prev_index),
+                                    E, None, ptr(keys), st))
+            local_counts = torch.from_numpy(
+                np.diff(res.apsis_offsets)).to(self.device, non_blocking=True)
+            k_all, i_all, a_all, counts, sizes = self.exchange_events(
+                keys[:E], res.d_ids[:E], res.d_ang[:E], local_counts,
+                return_sizes=True)
+            total = int(k_all.numel())
+            ids_o = torch.empty(max(total, 1), dtype=torch.int64,
+                                device=self.device)
+            ang_o = torch.empty(max(total, 1), dtype=torch.int16,
+                                device=self.device)
+            list_off = torch.from_numpy(np.concatenate(
+                ([0], np.cumsum(sizes))).astype(np.int64)).to(
+                    self.device, non_blocking=True)
+            check(lib.oa_merge_event_lists(
+                ptr(k_all), ptr(i_all), ptr(a_all), total, ptr(list_off),
+                self.world, ptr(ids_o), ptr(ang_o), st))
+            tracker.launches += 2
+            res.d_ids, res.d_ang = ids_o[:total], ang_o[:total]
+            res.n_events = total
+            res.apsis_offsets = np.concatenate(
+                ([0], np.cumsum(counts))).astype(np.int64)
+            # the ring buffers read above may be rewritten only after this
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            tracker.wait_before_submit = done
+        if to_host:
+            # asynchronous: res.wait_host() before reading apsis_ids / angles
+            h_ids, h_ang, ready = tracker.to_host_async(
+                res.d_ids, res.d_ang, stream=self.stream)
+            res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
+            res.apsis_angles = h_ang.numpy().view(np.float16)
+            res.host_ready = ready
         return res
 
     def merge(self, keys, ids, angles, local_counts, order, take):
@@ -155,22 +203,5 @@ class Comm:
         if keys.numel():
             perm = order(keys)
             ids, angles = take(ids, perm), take(angles, perm)
-        offsets = np.concatenate(
-            ([0], np.cumsum(counts.cpu().numpy()))).astype(np.int64)
+        offsets = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
         return ids, angles, offsets
-
-    def sort_keys(self, keys, st):
-        """Radix sort of int64 order keys; returns (sorted keys, permutation)."""
-        n = keys.numel()
-        if n == 0:
-            return keys, torch.empty(0, dtype=torch.int64, device=self.device)
-        idx = torch.arange(n, dtype=torch.int64, device=self.device)
-        k_out, v_out = torch.empty_like(keys), torch.empty_like(idx)
-        ws_bytes = lib.oa_sort_workspace_bytes(n)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        hi = int(keys.max().item())
-        bits = max(hi.bit_length(), 1)
-        check(lib.oa_sort_pairs_u64(ptr(keys), ptr(idx), ptr(k_out),
-                                    ptr(v_out), n, 0, bits, ptr(ws), ws_bytes,
-                                    st))
-        return k_out, v_out

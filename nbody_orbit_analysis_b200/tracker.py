@@ -39,9 +39,11 @@ class Generation:
 
 
 class StepResult:
-    __slots__ = ('n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
+    """Results of one snapshot.  ``host_ready`` (multi-GPU merge only) is the
+    event after which ``apsis_ids`` / ``apsis_angles`` are valid on the host."""
+    __slots__ = ('host_ready', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
-                 'apsis_prev_index', 'prev_gen')
+                 'apsis_prev_index', 'prev_gen', 'd_ids', 'd_ang', 'compacted')
 
 
 class Pending:
@@ -87,9 +89,14 @@ class OrbitTracker:
         self.copy_stream = torch.cuda.Stream(self.device)   # device -> host
         self.h2d_stream = torch.cuda.Stream(self.device)    # host -> device
         self._pool = {}
+        self._hpool = {}
         self._step = 0             # submitted snapshots
         self._consumed = {}        # ring slot -> event: inputs read by the kernel
         self._last_events = 0      # event count of the last collected snapshot
+        # multi-GPU: the event lists stay in HBM (StepResult.d_ids / d_ang) for
+        # the NCCL exchange instead of being copied to the host per rank
+        self.events_on_device = False
+        self.wait_before_submit = None   # event the next submit must wait for
 
     # -- buffers -------------------------------------------------------------
     RING = 3      # generations / in-flight steps a buffer name cycles through
@@ -114,9 +121,15 @@ class OrbitTracker:
         key = (name, slot)
         raw = self._pool.get(key)
         if raw is None or raw.numel() < nbytes:
+            # (re)allocate the whole ring of this name at once, so that every
+            # allocation happens in the first step that needs it
             cap = -(-int(nbytes * 1.25) // 512) * 512
-            raw = torch.empty(cap, dtype=torch.uint8, device=self.device)
-            self._pool[key] = raw
+            for k in range(self.RING):
+                old = self._pool.get((name, k))
+                if old is None or old.numel() < nbytes:
+                    self._pool[(name, k)] = torch.empty(
+                        cap, dtype=torch.uint8, device=self.device)
+            raw = self._pool[key]
         return raw[:int(n) * item].view(dtype)
 
     def _main(self):
@@ -138,9 +151,12 @@ class OrbitTracker:
         if t.numel() == 0:
             return torch.empty(0, dtype=t.dtype, device=self.device)
         if not t.is_pinned():
-            # torch's caching host allocator hands the block back only after
-            # the copy that reads it has completed on its stream
-            buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+            # pageable memory: stage through pinned memory (the tracker's own
+            # ring when the destination is one of its buffers)
+            if name is None:
+                buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+            else:
+                buf = self._hbuf('stage_' + name, t.numel(), t.dtype)
             buf.copy_(t)
             t = buf
         if name is None:
@@ -150,15 +166,62 @@ class OrbitTracker:
             dst.copy_(t, non_blocking=True)
         return dst
 
-    def _to_host_async(self, t, n=None):
+    HOST_RING = 4   # result buffers stay valid until two further submits
+
+    def _hbuf(self, name, n, dtype, step=None, reserve=0):
+        """Persistent PINNED host buffer ``name`` of a ring slot (cudaHostAlloc
+        costs ~0.5 ms per call, so nothing is pinned in steady state).  Result
+        arrays handed to the caller are views into these buffers: they stay
+        valid until ``HOST_RING - 2`` further snapshots have been submitted."""
+        step = self._step if step is None else step
+        item = torch.empty(0, dtype=dtype).element_size()
+        nbytes = max(int(n), 1) * item
+        key = (name, step % self.HOST_RING)
+        raw = self._hpool.get(key)
+        if raw is None or raw.numel() < nbytes:
+            cap = -(-int(max(nbytes, reserve * item) * 1.25) // 4096) * 4096
+            for k in range(self.HOST_RING):     # whole ring at once (see _buf)
+                old = self._hpool.get((name, k))
+                if old is None or old.numel() < nbytes:
+                    self._hpool[(name, k)] = torch.empty(
+                        cap, dtype=torch.uint8, pin_memory=True)
+            raw = self._hpool[key]
+        return raw[:int(n) * item].view(dtype)
+
+    def _to_host_async(self, t, n=None, name=None, step=None, reserve=0):
         """Device tensor -> pinned host tensor on the copy stream (the caller
-        synchronises before reading)."""
+        synchronises before reading).  With ``name`` the destination is the
+        tracker's pinned ring buffer of that name."""
         n = t.numel() if n is None else int(n)
-        h = torch.empty(n, dtype=t.dtype, pin_memory=True)
+        if name is None:
+            h = torch.empty(n, dtype=t.dtype, pin_memory=True)
+        else:
+            h = self._hbuf(name, n, t.dtype, step, reserve)
         if n:
             with torch.cuda.stream(self.copy_stream):
                 h.copy_(t[:n], non_blocking=True)
         return h
+
+    def to_host(self, *tensors, stream=None):
+        """Device tensors produced on ``stream`` (default: the main stream) ->
+        pinned host tensors (one synchronisation for all of them)."""
+        done = torch.cuda.Event()
+        done.record(stream if stream is not None else self._main())
+        self.copy_stream.wait_event(done)
+        out = [self._to_host_async(t) for t in tensors]
+        self.copy_stream.synchronize()
+        return out
+
+    def to_host_async(self, *tensors, stream=None):
+        """Like ``to_host`` without the synchronisation: returns the pinned
+        tensors and the event that marks their completion."""
+        done = torch.cuda.Event()
+        done.record(stream if stream is not None else self._main())
+        self.copy_stream.wait_event(done)
+        out = [self._to_host_async(t) for t in tensors]
+        ready = torch.cuda.Event()
+        ready.record(self.copy_stream)
+        return out + [ready]
 
     # -- one snapshot ----------------------------------------------------------
     def step(self, snapshot, halo_exists, region_positions, region_bulk_vels,
@@ -222,6 +285,10 @@ class OrbitTracker:
         (``dev`` = dict of flat torch tensors ``pos``, ``vel``, ``ids``,
         optional ``mass``)."""
         st = self._stream()
+        if self.wait_before_submit is not None:
+            # e.g. the multi-GPU exchange still reading the ring's event buffers
+            self._main().wait_event(self.wait_before_submit)
+            self.wait_before_submit = None
         data_dtype = np.dtype(data_dtype)
         halo_exists = np.asarray(halo_exists)
         n_h = len(halo_exists)
@@ -278,8 +345,8 @@ class OrbitTracker:
 
         # one packed host->device copy: [rows | offsets | seg_begin]
         nb_rows, nb_off = 128 * n_h, 8 * (n_h + 1)
-        pack = torch.empty(nb_rows + nb_off + 8 * max(n_m, 1),
-                           dtype=torch.uint8, pin_memory=True)
+        pack = self._hbuf('pack', nb_rows + nb_off + 8 * max(n_m, 1),
+                          torch.uint8)
         hp = pack.numpy()
         hp[:nb_rows] = rows.view(np.uint8)
         hp[nb_rows:nb_rows + nb_off] = offsets.view(np.uint8)
@@ -389,6 +456,7 @@ class OrbitTracker:
         self._consumed[self._step % self.RING] = consumed
 
         p = Pending()
+        p.step = self._step
         p.n, p.n_h, p.n_m = n, n_h, n_m
         p.gen, p.prev, p.matched = gen, prev, matched
         p.diag, p.dangle = diag, dangle
@@ -431,22 +499,28 @@ class OrbitTracker:
         # ---- small device->host copies on the copy stream ----------------------
         done = torch.cuda.Event()
         done.record(self._main())
+        p.compacted = done
         self.copy_stream.wait_event(done)
         p.h_ids = p.h_ang = None
         p.n_spec = 0
         if d_small is not None:
-            p.h_small = self._to_host_async(d_small)
+            p.h_small = self._to_host_async(d_small, name='h_small')
             # speculative copy of the event lists: their exact length is only
             # known on the device, so copy as many records as the last snapshot
             # produced (+25 %) now and the remainder, if any, in collect()
-            p.n_spec = min(cap, int(self._last_events * 1.25) + 1024)
-            p.h_ids = self._to_host_async(p.d_ids, p.n_spec)
-            p.h_ang = self._to_host_async(p.d_ang, p.n_spec)
+            if not self.events_on_device:
+                p.n_spec = min(cap, int(self._last_events * 1.25) + 1024)
+                # (pinned capacity for one event per six particles up front:
+                # re-pinning costs milliseconds)
+                p.h_ids = self._to_host_async(p.d_ids, p.n_spec, 'h_ids',
+                                              reserve=cap // 6)
+                p.h_ang = self._to_host_async(p.d_ang, p.n_spec, 'h_ang',
+                                              reserve=cap // 6)
         if derive_bulk:
-            p.h_bulk = self._to_host_async(d_bulk_out, 3 * n_h)
+            p.h_bulk = self._to_host_async(d_bulk_out, 3 * n_h, 'h_bulk')
             p.keep += (d_bulk_out,)
         if out_angle is not None:
-            p.h_angle = self._to_host_async(out_angle, n)
+            p.h_angle = self._to_host_async(out_angle, n, 'h_angle')
             p.keep += (out_angle,)
         p.small_done = torch.cuda.Event()
         p.small_done.record(self.copy_stream)
@@ -469,6 +543,9 @@ class OrbitTracker:
         res.apsis_prev_index = None
         res.n_events = 0
         res.angles = None
+        res.d_ids = res.d_ang = None
+        res.host_ready = None
+        res.compacted = p.compacted
         res.prev_gen = p.prev
         p.small_done.synchronize()
         if p.derive_bulk:
@@ -483,9 +560,16 @@ class OrbitTracker:
             total = int(small[p.n_m])
             res.apsis_offsets = small.copy()
             self._last_events = total
+            res.n_events = total
+            res.apsis_prev_index = p.sel[:total]
+            res.d_ids, res.d_ang = p.d_ids[:total], p.d_ang[:total]
+            if self.events_on_device:
+                if release:
+                    p.keep = None
+                return res
             if total > p.n_spec:          # the speculative copy fell short
-                p.h_ids = self._to_host_async(p.d_ids, total)
-                p.h_ang = self._to_host_async(p.d_ang, total)
+                p.h_ids = self._to_host_async(p.d_ids, total, 'h_ids', p.step)
+                p.h_ang = self._to_host_async(p.d_ang, total, 'h_ang', p.step)
                 self.copy_stream.synchronize()
             res.n_events = total
             ids = p.h_ids.numpy()[:total]

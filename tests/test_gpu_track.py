@@ -218,3 +218,64 @@ def test_argument_errors_come_first():
     with pytest.raises(ValueError):
         track_orbits.track_orbits([1], [[1]], None, None, 'x', mode='both',
                                   verbose=False)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_id_sharding_emulated_on_one_gpu(world, tmp_path):
+    """The multi-GPU decomposition without NCCL: `world` trackers on one GPU,
+    each fed the particles with id mod world == rank; their local event lists
+    (left in HBM) are concatenated in rank order and merged by order key with
+    oa_merge_event_lists -- the result must equal the unsharded oracle run."""
+    import ctypes as C
+    import torch
+    from nbody_orbit_analysis_b200 import sharded, _lib
+    _, _, _, OrbitTracker, SynthSim, oracle = _imports()
+    lib, ptr, check = _lib.lib, _lib.ptr, _lib.check
+    sim = SynthSim(50000, 17, 5, dtype=np.float32, catalogue_dtype=np.float32)
+    exists = np.arange(17)
+    trks = [OrbitTracker() for _ in range(world)]
+    for trk in trks:
+        trk.events_on_device = True
+    prev = None
+    dev = torch.device('cuda')
+    n_events = 0
+    for t, snap_no in enumerate(sim.snapshot_numbers):
+        pos, rad, bulk = sim.regions(snap_no, sim.main_branches[t])
+        full = sim.load_snapshot_data(snap_no, pos, rad)
+        state, exp = oracle.track_snapshot(full, exists, pos, bulk, 0.0,
+                                           'pericentric', prev)
+        prev = state
+        results = []
+        for r, trk in enumerate(trks):
+            local, gpos = sharded.shard_snapshot(full, r, world)
+            results.append(trk.step(local, exists, pos, bulk, 0.0, gpos=gpos))
+        if t == 0:
+            continue
+        keys, ids, angs, sizes = [], [], [], []
+        counts = np.zeros(17, dtype=np.int64)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for res in results:
+            E = res.n_events
+            k = torch.empty(max(E, 1), dtype=torch.int64, device=dev)
+            check(lib.oa_gather_i64(ptr(res.prev_gen.gpos),
+                                    ptr(res.apsis_prev_index), E, None, ptr(k),
+                                    st))
+            keys.append(k[:E]); ids.append(res.d_ids); angs.append(res.d_ang)
+            sizes.append(E)
+            counts += np.diff(res.apsis_offsets)
+        k_all, i_all, a_all = torch.cat(keys), torch.cat(ids), torch.cat(angs)
+        total = int(k_all.numel())
+        list_off = torch.tensor(np.concatenate(([0], np.cumsum(sizes))),
+                                dtype=torch.int64, device=dev)
+        ids_o = torch.empty(total, dtype=torch.int64, device=dev)
+        ang_o = torch.empty(total, dtype=torch.int16, device=dev)
+        check(lib.oa_merge_event_lists(ptr(k_all), ptr(i_all), ptr(a_all),
+                                       total, ptr(list_off), world, ptr(ids_o),
+                                       ptr(ang_o), st))
+        assert np.array_equal(ids_o.cpu().numpy(), exp['apsis_ids'])
+        assert np.array_equal(np.concatenate(([0], np.cumsum(counts))),
+                              exp['apsis_offsets'])
+        u = f16_ulps(ang_o.cpu().numpy().view(np.float16), exp['apsis_angles'])
+        assert u.size == 0 or u.max() <= 2
+        n_events += total
+    assert n_events > 0
