@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 8
+#define OA_ABI_VERSION 9
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -271,6 +271,51 @@ int oa_merge_event_lists(const int64_t* keys, const int64_t* ids,
                          uint16_t* angles_out, void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Consumers of the tracking path: progenitors.py and postprocessing.py.
+ * All joins are binary searches into lists sorted with oa_sort_pairs_u64.
+ * ------------------------------------------------------------------------- */
+/* r_out[i] = |wrap(pos[i] - centre of i's region)| in float64 with numpy's
+ * rounding points: get_central_particle_ids, progenitors.py:41-51.
+ * `centres` is (n_regions,3) float64 on the device, `box_host` 3 doubles on the
+ * HOST (ignored unless periodic). */
+int oa_central_radii(const void* pos, int data_dtype, const int64_t* cur_off,
+                     int n_regions, const double* centres, int centre_f32,
+                     int periodic, const double* box_host, int64_t n,
+                     double* r_out, void* stream);
+/* out[q] = src[order[seg_off[j] + q - out_off[j]]] for q in output segment j:
+ * the first entries of every sorted segment (argsort(...)[:n], :52-53). */
+int oa_segment_heads(const int64_t* src, const uint64_t* order,
+                     const int64_t* seg_off, const int64_t* out_off, int n_seg,
+                     int64_t n_out, int64_t* out, void* stream);
+/* flags[order[i]] = head[i] (first occurrences back in original order:
+ * np.unique(return_index=True), progenitors.py:82-84). */
+int oa_scatter_flags(const uint16_t* head, const uint64_t* order, int64_t n,
+                     uint16_t* flags, void* stream);
+/* pos_out[i] = vals[k] (or k when vals is NULL) with keys[k] == query[i]-bias,
+ * -1 if absent or flags[i] == 0; keys ascending and unique.  With q_seg/key_off
+ * the search is confined to segment q_seg[i] of the keys (-1: skip).
+ * np.in1d + utils.myin1d: progenitors.py:95-99, postprocessing.py:222-232. */
+int oa_lookup_sorted(const uint64_t* keys, const uint64_t* vals, int64_t n_keys,
+                     const int64_t* query, const uint16_t* flags, int64_t bias,
+                     const int32_t* q_seg, const int64_t* key_off, int64_t m,
+                     int64_t* pos_out, void* stream);
+/* keys[i] = descendant(i) << 32 | halo(where[i]), ~0 when where[i] < 0
+ * (progenitors.py:92-106); oa_vote_reduce on the SORTED keys gives the
+ * plurality halo per descendant, ties to the smallest index, -1 if none
+ * (:107-115).  best_ws: n_desc uint64. */
+int oa_vote_keys(const int64_t* where, const int64_t* halo_off, int n_halos,
+                 const int64_t* tracked_off, int n_desc, int64_t m,
+                 uint64_t* keys, void* stream);
+int oa_vote_reduce(const uint64_t* sorted_keys, int64_t m, int n_desc,
+                   uint64_t* best_ws, int64_t* out, void* stream);
+/* marks[i] = float16(angles[i]) > cut  (postprocessing.py:124-127). */
+int oa_angle_cut(const uint16_t* angles, int64_t n, double cut, uint16_t* marks,
+                 void* stream);
+/* seg_out[i] = table[segment of i] (segment index itself if table is NULL). */
+int oa_expand_segments(const int64_t* seg_off, int n_seg, const int32_t* table,
+                       int64_t n, int32_t* seg_out, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Benchmark workload generator (not a reference function):

@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 8
+ABI_VERSION = 9
 BUCKET_LOAD = 3          # OA_BUCKET_LOAD
 
 
@@ -138,6 +138,16 @@ _sig('oa_merge_event_lists', C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, _vp,
      _vp, _vp)
 _sig('oa_run_heads', C.c_int, _vp, _vp, _i64, _vp, _vp)
 _sig('oa_run_lengths', C.c_int, _vp, _i64, _i64, _vp, _vp)
+_sig('oa_central_radii', C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
+     C.c_int, C.POINTER(C.c_double), _i64, _vp, _vp)
+_sig('oa_segment_heads', C.c_int, _vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp)
+_sig('oa_scatter_flags', C.c_int, _vp, _vp, _i64, _vp, _vp)
+_sig('oa_lookup_sorted', C.c_int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp,
+     _i64, _vp, _vp)
+_sig('oa_vote_keys', C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, _i64, _vp, _vp)
+_sig('oa_vote_reduce', C.c_int, _vp, _i64, C.c_int, _vp, _vp, _vp)
+_sig('oa_angle_cut', C.c_int, _vp, _i64, C.c_double, _vp, _vp)
+_sig('oa_expand_segments', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp)
 _sig('oa_synth_keys', C.c_int, C.POINTER(SynthParams), _vp, _vp, _vp, _vp)
 _sig('oa_synth_fill', C.c_int, C.POINTER(SynthParams), _vp, _i64, C.c_int,
      _vp, _vp, _vp, _vp)
@@ -157,7 +167,9 @@ EXPORTS = [
     'oa_sort_workspace_bytes',
     'oa_sort_pairs_u64', 'oa_minmax_i64', 'oa_synth_keys', 'oa_synth_fill',
     'oa_synth_params_size', 'oa_segment_sort_keys', 'oa_run_heads',
-    'oa_run_lengths', 'oa_merge_event_lists',
+    'oa_run_lengths', 'oa_merge_event_lists', 'oa_central_radii',
+    'oa_segment_heads', 'oa_scatter_flags', 'oa_lookup_sorted', 'oa_vote_keys',
+    'oa_vote_reduce', 'oa_angle_cut', 'oa_expand_segments',
 ]
 
 
