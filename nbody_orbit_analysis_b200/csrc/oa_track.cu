@@ -196,7 +196,9 @@ OA_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
 //   [off/3 + j, off/3 + j + len/3 + 1): mean fill <= 3 of 8 slots, so that only
 // 0.4 % of the buckets overflow (Poisson) -- an overflow costs its whole warp a
 // second, serialised round trip.
-OA_HD uint32_t bucket_count(int64_t len) { return (uint32_t)(len / OA_BUCKET_LOAD + 1); }
+OA_HD uint32_t bucket_count(int64_t len) {          // len < 2^31 on one GPU
+    return (uint32_t)len / (uint32_t)OA_BUCKET_LOAD + 1u;
+}
 OA_HD int64_t bucket_begin(int64_t block_start, int64_t region) {
     return block_start / OA_BUCKET_LOAD + region;
 }
@@ -228,6 +230,11 @@ OA_D int find_region(const int64_t* __restrict__ off, int lo, int hi, int64_t c)
     }
     return lo;
 }
+
+// L2 eviction policies, created once per thread (warp-uniform values)
+struct Policies {
+    uint64_t first, normal, last;
+};
 
 struct ChunkMeta {
     int jlo, jhi;        // regions the chunk touches
@@ -335,11 +342,12 @@ struct Particle {
 // Frame, hash, insert atomic and bucket load of one particle.  `R` is the row of
 // the particle's region (shared memory, or a private copy on the rare path).
 template <typename TX, typename TF, typename TVR, bool HUBBLE>
-OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Row* R,
-                      const Vec3<TX> xin, const Vec3<TX> vin, Particle<TF, TVR>& P) {
+OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Policies& pol,
+                      const Row* R, const Vec3<TX> xin, const Vec3<TX> vin,
+                      Particle<TF, TVR>& P) {
     using AF = Ar<TF>;
     const TX x[3] = {xin.x, xin.y, xin.z}, v[3] = {vin.x, vin.y, vin.z};
-    const uint64_t pol_keep = policy_evict_last();
+    const uint64_t pol_keep = pol.last;
     // halo frame (region_frame)
     TF d[3];
 #pragma unroll
@@ -353,14 +361,24 @@ OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Row* R,
             }
             d[q] = (TF)dd;
         } else {
-            // float frame: `(double)df > L/2` <=> `df > rd_float(L/2)`
-            float df = __fsub_rn((float)x[q], R->centre_f[q]);
-            if (a.periodic) {
+            d[q] = (TF)__fsub_rn((float)x[q], R->centre_f[q]);
+        }
+    }
+    if (!(std::is_same<TX, double>::value || !a.centre_f32) && a.periodic) {
+        // float frame: `(double)df > L/2` <=> `df > rd_float(L/2)`; only the few
+        // particles of a halo that straddles a box face take the branch
+        const bool out = fabsf((float)d[0]) > k.half_box[0] ||
+                         fabsf((float)d[1]) > k.half_box[1] ||
+                         fabsf((float)d[2]) > k.half_box[2];
+        if (out) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float df = (float)d[q];
                 const float hf = k.half_box[q];
                 if (df > hf) df = (float)__dsub_rn((double)df, a.box[q]);
                 if (df < -hf) df = (float)__dadd_rn((double)df, a.box[q]);
+                d[q] = (TF)df;
             }
-            d[q] = (TF)df;
         }
     }
     P.r = AF::sqrt(AF::dot3(d[0], d[1], d[2], d[0], d[1], d[2]));
@@ -408,12 +426,13 @@ OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Row* R,
 
 // Candidate record, exact ID check, apsis test, angle accumulator, outputs.
 template <typename TF, typename TVR, bool DIAG>
-OA_D void track_finish(const oa_track_args& a, const TrackConst& k, Particle<TF, TVR>& P) {
+OA_D void track_finish(const oa_track_args& a, const TrackConst& k, const Policies& pol,
+                       Particle<TF, TVR>& P) {
     using AF = Ar<TF>;
     const OaRec<TF>* __restrict__ rec_prev = static_cast<const OaRec<TF>*>(a.rec_prev);
     OaRec<TF>* __restrict__ rec_cur = static_cast<OaRec<TF>*>(a.rec_cur);
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_gather = policy_evict_normal();
+    const uint64_t pol_stream = pol.first;
+    const uint64_t pol_gather = pol.normal;
     const uint32_t c = P.c;
 
     int64_t p = -1;
@@ -502,7 +521,11 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[TRACK_WARPS * D];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform
+    // and keeps the chunk / slot / TMA address arithmetic on the uniform datapath
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+    const Policies pol = {policy_evict_first(), policy_evict_normal(), policy_evict_last()};
     unsigned char* const wsm = smem + (size_t)warp * D * L::BYTES;
     uint64_t* const full = bars + warp * D;
     const int64_t n = a.n_cur;
@@ -529,7 +552,7 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
         m->tma = tma ? 1 : 0;
         constexpr uint32_t B_IDS = 8u * CHUNK, B_X = (uint32_t)sizeof(TX) * 3u * CHUNK;
         const uint32_t b_rows = nrows <= RW ? (uint32_t)sizeof(Row) * nrows : 0u;
-        const uint64_t pol_stream = policy_evict_first();
+        const uint64_t pol_stream = pol.first;
         mbar_arrive_expect_tx(&full[s], (tma ? B_IDS + 2u * B_X : 0u) + b_rows);
         if (tma) {
             tma_load_1d(st + L::IDS, a.ids + base, B_IDS, &full[s], pol_stream);
@@ -539,7 +562,7 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
                         pol_stream);
         }
         if (b_rows)
-            tma_load_1d(st + L::ROWS, a.regions + jr.x, b_rows, &full[s], policy_evict_last());
+            tma_load_1d(st + L::ROWS, a.regions + jr.x, b_rows, &full[s], pol.last);
     };
 
     // ---- prologue: D chunks in flight -------------------------------------------------------
@@ -573,7 +596,7 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
             x.x = sp[0]; x.y = sp[1]; x.z = sp[2];
             v.x = sv[0]; v.y = sv[1]; v.z = sv[2];
         } else if (active) {
-            const uint64_t pol_stream = policy_evict_first();
+            const uint64_t pol_stream = pol.first;
             P.id = ld8_nc(a.ids + c, pol_stream);
             const TX* gp = static_cast<const TX*>(a.pos) + 3 * c;
             const TX* gv = static_cast<const TX*>(a.vel) + 3 * c;
@@ -594,7 +617,7 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
                 load_row(a.regions, find_region(a.cur_off, meta.jlo, meta.jhi, c), &own);
                 R = &own;
             }
-            track_begin<TX, TF, TVR, HUBBLE>(a, k, R, x, v, P);
+            track_begin<TX, TF, TVR, HUBBLE>(a, k, pol, R, x, v, P);
         }
         // the slot has been consumed: refill it with the chunk D steps ahead
         __syncwarp();
@@ -603,7 +626,7 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
             if (lane == 0) issue(ahead, s, jr_next);
             if (ahead + stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + ahead + stride);
         }
-        if (active) track_finish<TF, TVR, DIAG>(a, k, P);
+        if (active) track_finish<TF, TVR, DIAG>(a, k, pol, P);
         if (++s == D) { s = 0; phase ^= 1u; }
     }
 }
