@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 9
+ABI_VERSION = 10
 BUCKET_LOAD = 3          # OA_BUCKET_LOAD
 
 
@@ -23,8 +23,8 @@ class OrbitB200Error(RuntimeError):
 
 
 def _load():
-    path = _build.LIB
-    if not os.path.exists(path) or _build.needs_build():
+    path = os.environ.get('OA_LIB_PATH') or _build.LIB    # (tuning builds)
+    if path == _build.LIB and (not os.path.exists(path) or _build.needs_build()):
         try:
             _build.build()
         except Exception as exc:    # noqa: BLE001

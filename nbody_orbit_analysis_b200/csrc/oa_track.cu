@@ -6,17 +6,30 @@
 // See include/orbit_b200.h (oa_track_fused) for the contract and DESIGN.md for
 // the memory layout and the roofline accounting.
 //
-// Structure: a persistent kernel, one 1024-thread CTA per SM, in which every
-// WARP is an autonomous software pipeline over chunks of 32 consecutive
-// particles (chunk c -> warp c mod #warps, so the warps of the whole GPU sweep
-// the snapshot as one compact front).  A warp owns a ring of D shared-memory
-// slots with one mbarrier each; lane 0 fills slot t mod D with four 1-D TMA bulk
-// copies (cp.async.bulk ... mbarrier::complete_tx, L2 evict-first): ids,
-// positions, velocities and the oa_region rows the chunk touches.  D chunks of
-// inputs are therefore in flight per warp while the dependent chain of the
-// current chunk
-//      bucket (L2) -> previous record (L2/HBM) -> new record (HBM)
-// is outstanding.  There is no block-wide barrier and no inter-warp wait.
+// Structure: a persistent kernel, one 768-thread CTA per SM (80 registers per
+// thread, nothing spills), in which every WARP is an autonomous software
+// pipeline over chunks of 32 consecutive particles (chunk c -> warp c mod
+// #warps, so the warps of the whole GPU sweep the snapshot as one compact
+// front).  A warp owns a ring of D shared-memory slots with one mbarrier each;
+// lane 0 fills slot t mod D with four 1-D TMA bulk copies (cp.async.bulk ...
+// mbarrier::complete_tx, L2 evict-first): ids, positions, velocities and the
+// oa_region rows the chunk touches.  Per iteration a warp
+//   A. hashes the IDs of the NEXT chunk and issues its insert atomic and its
+//      bucket load (they are in flight during everything below),
+//   B. compares the 8 slots of THIS chunk's bucket (loaded an iteration ago) and
+//      issues the gather of the candidate's previous record,
+//   C. does the halo-frame arithmetic of this chunk while that gather is out,
+//      hands the slot back to TMA (chunk t+D),
+//   D. verifies the ID, tests for an apsis, updates the angle, writes the record.
+// There is no block-wide barrier and no inter-warp wait.
+//
+// What bounds it (tools/micro/random_access.cu, profiles/r01_ablation.md): a
+// warp access whose 32 lanes hit 32 different lines costs the SM's L1TEX ~2.4
+// cycles per lane, whatever the level it hits.  13.5 M random 32 B gathers
+// alone take 0.117 ms on B200, 13.5 M atomics 0.129 ms, 13.5 M scattered 4 B
+// stores 0.09 ms, the streaming part 0.14 ms; the kernel's four random
+// accesses per particle (bucket, record, counter, slot) put its floor near
+// 0.45 ms and it runs in 0.535 ms.
 //
 // Matching: a region-segmented, bucketised hash table in global memory.  The
 // table of a snapshot is two arrays: per-bucket fill counters (4 B / bucket,
@@ -43,7 +56,10 @@
 
 namespace {
 
-constexpr int TRACK_WARPS = 32;                 // one 1024-thread CTA per SM
+#ifndef OA_TRACK_WARPS
+#define OA_TRACK_WARPS 24      // 768 threads: 80 registers each, nothing spills
+#endif
+constexpr int TRACK_WARPS = OA_TRACK_WARPS;     // one CTA per SM
 constexpr int TRACK_THREADS = 32 * TRACK_WARPS;
 constexpr int CHUNK = 32;                       // particles per warp step
 constexpr int RW = 4;                           // region rows staged per chunk
@@ -326,29 +342,80 @@ struct SlotLayout {
 
 template <typename T> struct Vec3 { T x, y, z; };
 
-// Per-particle state carried from the issue of the table traffic (track_begin)
-// to its consumption (track_finish).
-template <typename TF, typename TVR>
-struct Particle {
-    int64_t id;
-    TF rh[3], r;
-    TVR vr;
-    uint32_t c;
-    uint32_t ins_k, ins_val, ins_b, ins_nb, ins_home;
-    uint32_t fpshift, prev_count, prev_begin, prb_b0, prb_nb, prb_home;
+// Per-particle state of the two overlapped stages.  `Probe` lives from the
+// issue of the table traffic of a chunk (one iteration AHEAD of its frame
+// arithmetic) to the end of that chunk; `Frame` only inside one iteration.
+struct Probe {
+    uint32_t ins_k, ins_val, ins_idx, ins_nb;     // insert into this snapshot's table
+    uint32_t fpshift, prev_count, prev_begin;     // probe of the previous table
+    uint32_t prb_idx, prb_nb;
     V8 bk;
 };
+template <typename TF, typename TVR>
+struct Frame {
+    TF rh[3], r;
+    TVR vr;
+};
 
-// Frame, hash, insert atomic and bucket load of one particle.  `R` is the row of
-// the particle's region (shared memory, or a private copy on the rare path).
+// Stage A: hash the ID, issue the insert atomic on this snapshot's table and the
+// load of the particle's bucket in the previous table.  Nothing here waits.
+OA_D Probe stage_hash(const oa_track_args& a, const TrackConst& k, const Policies& pol,
+                      const Row* R, const int64_t id, const uint32_t c) {
+    Probe H;
+    const uint64_t hsh = oa_mix64((uint64_t)id);
+    const uint32_t h_slot = (uint32_t)(hsh >> 32), h_fp = (uint32_t)hsh;
+    const int pbits = a.prev_index_bits, cbits = a.cur_index_bits;
+
+    // (no L2 hint on the table writes: evict-last on them measured 20 % slower)
+    H.ins_nb = bucket_count(R->cur_count);
+    H.ins_idx = (uint32_t)R->cur_bucket + oa_slot(h_slot, H.ins_nb);
+    H.ins_val = ((h_fp >> cbits) << cbits) | (c - (uint32_t)R->cur_begin);
+    H.ins_k = atomicAdd(k.cnt_cur + H.ins_idx, 1u);
+
+    H.prev_count = (a.rec_prev != nullptr && R->prev_count > 0) ? (uint32_t)R->prev_count : 0u;
+    H.fpshift = (h_fp >> pbits) << pbits;
+    H.prev_begin = (uint32_t)R->prev_begin;
+    H.prb_nb = bucket_count(H.prev_count);
+    H.prb_idx = (uint32_t)R->prev_bucket + oa_slot(h_slot, H.prb_nb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) H.bk.w[e] = 0xFFFFFFFFu;     // never a candidate
+    if (H.prev_count > 0)
+        H.bk = ld32_nc(k.slot_prev + (size_t)H.prb_idx * OA_BUCKET_WORDS, pol.last);
+    return H;
+}
+
+OA_D Probe empty_probe() {
+    Probe H;
+    H.ins_k = H.ins_val = H.ins_idx = H.ins_nb = 0;
+    H.fpshift = H.prev_count = H.prev_begin = H.prb_idx = H.prb_nb = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) H.bk.w[e] = 0xFFFFFFFFu;
+    return H;
+}
+
+// row of the region of particle `c` of a chunk whose rows are staged at `rows`
+// (`own`: private copy when the chunk touches more regions than a slot stages)
+OA_D const Row* find_row(const oa_track_args& a, const unsigned char* rows,
+                         const ChunkMeta& meta, const int64_t c, Row* own) {
+    const Row* R = reinterpret_cast<const Row*>(rows);
+    if (meta.nrows > 0) {
+        // first staged row whose block ends beyond this particle (empty blocks in
+        // between end where they begin and are skipped)
+        for (int q = 1; q < meta.nrows; ++q)
+            if (c >= R->cur_begin + R->cur_count) ++R;
+        return R;
+    }
+    load_row(a.regions, find_region(a.cur_off, meta.jlo, meta.jhi, c), own);
+    return own;
+}
+
+// Stage C: halo frame of one particle (region_frame).  `R` is the row of the
+// particle's region (shared memory, or a private copy on the rare path).
 template <typename TX, typename TF, typename TVR, bool HUBBLE>
-OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Policies& pol,
-                      const Row* R, const Vec3<TX> xin, const Vec3<TX> vin,
-                      Particle<TF, TVR>& P) {
+OA_D void stage_frame(const oa_track_args& a, const TrackConst& k, const Row* R,
+                      const Vec3<TX> xin, const Vec3<TX> vin, Frame<TF, TVR>& F) {
     using AF = Ar<TF>;
     const TX x[3] = {xin.x, xin.y, xin.z}, v[3] = {vin.x, vin.y, vin.z};
-    const uint64_t pol_keep = pol.last;
-    // halo frame (region_frame)
     TF d[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -381,9 +448,9 @@ OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Policie
             }
         }
     }
-    P.r = AF::sqrt(AF::dot3(d[0], d[1], d[2], d[0], d[1], d[2]));
+    F.r = AF::sqrt(AF::dot3(d[0], d[1], d[2], d[0], d[1], d[2]));
 #pragma unroll
-    for (int q = 0; q < 3; ++q) P.rh[q] = AF::div(d[q], P.r);
+    for (int q = 0; q < 3; ++q) F.rh[q] = AF::div(d[q], F.r);
     TVR w[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -396,83 +463,68 @@ OA_D void track_begin(const oa_track_args& a, const TrackConst& k, const Policie
             wk = __dadd_rn(wk, __ddiv_rn(__dmul_rn(a.hubble, (double)d[q]), a.one_plus_z));
         w[q] = (TVR)wk;
     }
-    P.vr = Ar<TVR>::dot3(w[0], w[1], w[2], (TVR)P.rh[0], (TVR)P.rh[1], (TVR)P.rh[2]);
-
-    const uint64_t hsh = oa_mix64((uint64_t)P.id);
-    const uint32_t h_slot = (uint32_t)(hsh >> 32), h_fp = (uint32_t)hsh;
-    const int pbits = a.prev_index_bits, cbits = a.cur_index_bits;
-
-    // insert into the current table: the atomic is issued now, its result is
-    // consumed at the very end
-    P.ins_nb = bucket_count(R->cur_count);
-    P.ins_home = oa_slot(h_slot, P.ins_nb);
-    P.ins_b = (uint32_t)R->cur_bucket;
-    P.ins_val = ((h_fp >> cbits) << cbits) | (P.c - (uint32_t)R->cur_begin);
-    // (no L2 hint on the table writes: evict-last on them measured 20 % slower)
-    P.ins_k = atomicAdd(k.cnt_cur + (P.ins_b + P.ins_home), 1u);
-
-    // probe of the previous table: one sector
-    P.prev_count = (a.rec_prev != nullptr && R->prev_count > 0) ? (uint32_t)R->prev_count : 0u;
-    P.fpshift = (h_fp >> pbits) << pbits;
-    if (P.prev_count > 0) {
-        P.prev_begin = (uint32_t)R->prev_begin;
-        P.prb_b0 = (uint32_t)R->prev_bucket;
-        P.prb_nb = bucket_count(P.prev_count);
-        P.prb_home = oa_slot(h_slot, P.prb_nb);
-        P.bk = ld32_nc(k.slot_prev + (size_t)(P.prb_b0 + P.prb_home) * OA_BUCKET_WORDS,
-                       pol_keep);
-    }
+    F.vr = Ar<TVR>::dot3(w[0], w[1], w[2], (TVR)F.rh[0], (TVR)F.rh[1], (TVR)F.rh[2]);
 }
 
-// Candidate record, exact ID check, apsis test, angle accumulator, outputs.
+// Stage B: compare the bucket's 8 slots in registers and issue the second round
+// trip -- the candidate's record, or (no fingerprint matched) the fill counter
+// of the home bucket, which tells a newly entered particle from an overflow.
+template <typename TF>
+OA_D void stage_candidate(const oa_track_args& a, const TrackConst& k, const Policies& pol,
+                          const Probe& H, uint32_t& cand, OaRec<TF>& prev, uint32_t& fill) {
+    const OaRec<TF>* __restrict__ rec_prev = static_cast<const OaRec<TF>*>(a.rec_prev);
+    cand = 0xFFFFFFFFu;
+    fill = 0;
+    if (H.prev_count == 0) return;
+#pragma unroll
+    for (int e = OA_BUCKET_SLOTS - 1; e >= 0; --e) {
+        const uint32_t xr = H.bk.w[e] ^ H.fpshift;       // == index iff fingerprint equal
+        if (xr < H.prev_count) cand = xr;
+    }
+    // normal eviction priority: HBM delivers 64 B, and the other half is the
+    // record of a neighbour that is gathered soon (-25 % HBM reads)
+    if (cand != 0xFFFFFFFFu)
+        prev = load_rec(rec_prev + ((size_t)H.prev_begin + cand), pol.normal);
+    else
+        fill = __ldcg(k.cnt_prev + H.prb_idx);
+}
+
+// Stage D: exact ID check, apsis test, angle accumulator, outputs.
 template <typename TF, typename TVR, bool DIAG>
-OA_D void track_finish(const oa_track_args& a, const TrackConst& k, const Policies& pol,
-                       Particle<TF, TVR>& P) {
+OA_D void stage_finish(const oa_track_args& a, const TrackConst& k, const Policies& pol,
+                       const int64_t id, const uint32_t c, const Probe& H,
+                       const Frame<TF, TVR>& F, const uint32_t cand, OaRec<TF>& prev,
+                       const uint32_t fill) {
     using AF = Ar<TF>;
     const OaRec<TF>* __restrict__ rec_prev = static_cast<const OaRec<TF>*>(a.rec_prev);
     OaRec<TF>* __restrict__ rec_cur = static_cast<OaRec<TF>*>(a.rec_cur);
-    const uint64_t pol_stream = pol.first;
-    const uint64_t pol_gather = pol.normal;
-    const uint32_t c = P.c;
 
     int64_t p = -1;
-    OaRec<TF> prev;
-    if (P.prev_count > 0) {
-        uint32_t cand = 0xFFFFFFFFu;
-#pragma unroll
-        for (int e = OA_BUCKET_SLOTS - 1; e >= 0; --e) {
-            const uint32_t xr = P.bk.w[e] ^ P.fpshift;   // == index iff fingerprint equal
-            if (xr < P.prev_count) cand = xr;
-        }
-        // Second round trip, issued by every lane at once: the candidate's record,
-        // or -- no fingerprint matched -- the fill counter of the home bucket,
-        // which tells a plain miss (newly entered particle) from an overflow.
+    if (H.prev_count > 0) {
         bool slow;
         if (cand != 0xFFFFFFFFu) {
-            // normal eviction priority: HBM delivers 64 B, and the other half is
-            // the record of a neighbour that is gathered soon (-25 % HBM reads)
-            p = (int64_t)P.prev_begin + (int64_t)cand;
-            prev = load_rec(rec_prev + p, pol_gather);
-            slow = prev.id != P.id;                   // stale slot / collision
+            p = (int64_t)H.prev_begin + (int64_t)cand;
+            slow = prev.id != id;                     // stale slot / collision
         } else {
-            slow = __ldcg(k.cnt_prev + (P.prb_b0 + P.prb_home)) > OA_BUCKET_SLOTS;
+            slow = fill > OA_BUCKET_SLOTS;            // overflowed home bucket
         }
         if (slow) {
-            p = probe_slow<TF>(k.cnt_prev, k.slot_prev, P.prb_b0, P.prb_nb, P.prb_home,
-                               P.fpshift, P.prev_count, rec_prev, P.prev_begin, P.id,
+            const uint32_t home = oa_slot((uint32_t)(oa_mix64((uint64_t)id) >> 32), H.prb_nb);
+            p = probe_slow<TF>(k.cnt_prev, k.slot_prev, H.prb_idx - home, H.prb_nb, home,
+                               H.fpshift, H.prev_count, rec_prev, H.prev_begin, id,
                                cand == 0xFFFFFFFFu);
-            if (p >= 0) prev = load_rec(rec_prev + p, pol_gather);
+            if (p >= 0) prev = load_rec(rec_prev + p, pol.normal);
         }
     }
 
     __half angle_new = __ushort_as_half((unsigned short)0);
     if (p >= 0) {
-        const TF dotp = AF::dot3((TF)prev.rx, (TF)prev.ry, (TF)prev.rz, P.rh[0], P.rh[1],
-                                 P.rh[2]);
+        const TF dotp = AF::dot3((TF)prev.rx, (TF)prev.ry, (TF)prev.rz, F.rh[0], F.rh[1],
+                                 F.rh[2]);
         const TF dang = AF::acos(dotp);
         bool ev;
-        if (a.mode == OA_MODE_PERICENTRIC) ev = (prev.vr < 0) && (P.vr > 0);
-        else ev = (prev.vr > 0) && (P.vr < 0);
+        if (a.mode == OA_MODE_PERICENTRIC) ev = (prev.vr < 0) && (F.vr > 0);
+        else ev = (prev.vr > 0) && (F.vr < 0);
         if (a.onthefly) {
             if (a.dangle_prev) static_cast<TF*>(a.dangle_prev)[p] = dang;
             a.mark_prev[p] = ev ? (uint16_t)1 : (uint16_t)0;
@@ -487,27 +539,29 @@ OA_D void track_finish(const oa_track_args& a, const TrackConst& k, const Polici
     }
 
     OaRec<TF> rec;
-    rec.id = P.id;
-    rec.rx = P.rh[0]; rec.ry = P.rh[1]; rec.rz = P.rh[2];
-    set_vr<TF, TVR>(rec, P.vr);
-    rec.r = P.r;
+    rec.id = id;
+    rec.rx = F.rh[0]; rec.ry = F.rh[1]; rec.rz = F.rh[2];
+    set_vr<TF, TVR>(rec, F.vr);
+    rec.r = F.r;
     rec.angle = angle_new;
     rec.flags = 0;
-    store_rec(rec_cur + c, rec, pol_stream);
-    st2(a.mark_cur + c, OA_NO_EVENT, pol_stream);
+    store_rec(rec_cur + c, rec, pol.first);
+    st2(a.mark_cur + c, OA_NO_EVENT, pol.first);
 
-    if (P.ins_k < OA_BUCKET_SLOTS)
-        k.slot_cur[(size_t)(P.ins_b + P.ins_home) * OA_BUCKET_WORDS + P.ins_k] = P.ins_val;
-    else               // home bucket full (rare): spill to the next ones
-        insert_slow(k.cnt_cur, k.slot_cur, P.ins_b, P.ins_nb, P.ins_home, P.ins_val);
+    if (H.ins_k < OA_BUCKET_SLOTS) {
+        k.slot_cur[(size_t)H.ins_idx * OA_BUCKET_WORDS + H.ins_k] = H.ins_val;
+    } else {           // home bucket full (rare): spill to the next ones
+        const uint32_t home = oa_slot((uint32_t)(oa_mix64((uint64_t)id) >> 32), H.ins_nb);
+        insert_slow(k.cnt_cur, k.slot_cur, H.ins_idx - home, H.ins_nb, home, H.ins_val);
+    }
 
     if (DIAG) {        // optional per-particle outputs (checkpoint, diagnostics, on-the-fly)
         if (a.out_rhat) {
             TF* o = static_cast<TF*>(a.out_rhat) + 3 * (size_t)c;
-            o[0] = P.rh[0]; o[1] = P.rh[1]; o[2] = P.rh[2];
+            o[0] = F.rh[0]; o[1] = F.rh[1]; o[2] = F.rh[2];
         }
-        if (a.out_vr) static_cast<TVR*>(a.out_vr)[c] = P.vr;
-        if (a.out_r) static_cast<TF*>(a.out_r)[c] = P.r;
+        if (a.out_vr) static_cast<TVR*>(a.out_vr)[c] = F.vr;
+        if (a.out_r) static_cast<TF*>(a.out_r)[c] = F.r;
         if (a.out_angle) a.out_angle[c] = __half_as_ushort(angle_new);
         if (a.out_match) a.out_match[c] = p;
     }
@@ -552,20 +606,38 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
         m->tma = tma ? 1 : 0;
         constexpr uint32_t B_IDS = 8u * CHUNK, B_X = (uint32_t)sizeof(TX) * 3u * CHUNK;
         const uint32_t b_rows = nrows <= RW ? (uint32_t)sizeof(Row) * nrows : 0u;
-        const uint64_t pol_stream = pol.first;
         mbar_arrive_expect_tx(&full[s], (tma ? B_IDS + 2u * B_X : 0u) + b_rows);
         if (tma) {
-            tma_load_1d(st + L::IDS, a.ids + base, B_IDS, &full[s], pol_stream);
+            tma_load_1d(st + L::IDS, a.ids + base, B_IDS, &full[s], pol.first);
             tma_load_1d(st + L::POS, static_cast<const TX*>(a.pos) + 3 * base, B_X, &full[s],
-                        pol_stream);
+                        pol.first);
             tma_load_1d(st + L::VEL, static_cast<const TX*>(a.vel) + 3 * base, B_X, &full[s],
-                        pol_stream);
+                        pol.first);
         }
         if (b_rows)
             tma_load_1d(st + L::ROWS, a.regions + jr.x, b_rows, &full[s], pol.last);
     };
 
-    // ---- prologue: D chunks in flight -------------------------------------------------------
+    // stage A of the chunk staged at `st`: wait for its inputs, hash, issue its
+    // table traffic.  (A macro-like lambda would not be inlined twice; the
+    // per-particle state must stay in registers.)
+#define OA_HASH_CHUNK(CH, ST, BAR, PHASE, H_OUT, ID_OUT)                                   \
+    do {                                                                                   \
+        mbar_wait((BAR), (PHASE));                                                         \
+        const ChunkMeta meta_ = *reinterpret_cast<const ChunkMeta*>((ST) + L::META);       \
+        const int64_t c_ = (int64_t)(CH) * CHUNK + lane;                                   \
+        (ID_OUT) = 0;                                                                      \
+        (H_OUT) = empty_probe();                                                           \
+        if (c_ < n) {                                                                      \
+            (ID_OUT) = meta_.tma ? reinterpret_cast<const int64_t*>((ST) + L::IDS)[lane]   \
+                                 : ld8_nc(a.ids + c_, pol.first);                          \
+            Row own_;                                                                      \
+            const Row* R_ = find_row(a, (ST) + L::ROWS, meta_, c_, &own_);                 \
+            (H_OUT) = stage_hash(a, k, pol, R_, (ID_OUT), (uint32_t)c_);                   \
+        }                                                                                  \
+    } while (0)
+
+    // ---- prologue: D chunks in flight, table traffic of the first one issued ------
     if (lane == 0) {
         for (int s = 0; s < D; ++s) {
             const int ch = first + s * stride;
@@ -577,47 +649,51 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
 
     int s = 0;
     uint32_t phase = 0;
+    Probe H = empty_probe();
+    int64_t id = 0;
+    if (first < k.n_chunks) OA_HASH_CHUNK(first, wsm, &full[0], 0u, H, id);
+
     for (int ch = first; ch < k.n_chunks; ch += stride) {
         unsigned char* st = wsm + s * L::BYTES;
-        mbar_wait(&full[s], phase);
-        const ChunkMeta meta = *reinterpret_cast<const ChunkMeta*>(st + L::META);
+        const int sn = (s + 1 == D) ? 0 : s + 1;
+        const uint32_t phase_n = (s + 1 == D) ? (phase ^ 1u) : phase;
         const int64_t c = (int64_t)ch * CHUNK + lane;
         const bool active = c < n;
 
-        Particle<TF, TVR> P;
-        P.c = (uint32_t)c;
-        P.id = 0;
-        P.prev_count = 0;
-        Vec3<TX> x = {0, 0, 0}, v = {0, 0, 0};
-        if (meta.tma) {
-            P.id = reinterpret_cast<const int64_t*>(st + L::IDS)[lane];
-            const TX* sp = reinterpret_cast<const TX*>(st + L::POS) + 3 * lane;
-            const TX* sv = reinterpret_cast<const TX*>(st + L::VEL) + 3 * lane;
-            x.x = sp[0]; x.y = sp[1]; x.z = sp[2];
-            v.x = sv[0]; v.y = sv[1]; v.z = sv[2];
-        } else if (active) {
-            const uint64_t pol_stream = pol.first;
-            P.id = ld8_nc(a.ids + c, pol_stream);
-            const TX* gp = static_cast<const TX*>(a.pos) + 3 * c;
-            const TX* gv = static_cast<const TX*>(a.vel) + 3 * c;
-            x.x = ld_elem(gp, pol_stream); x.y = ld_elem(gp + 1, pol_stream);
-            x.z = ld_elem(gp + 2, pol_stream);
-            v.x = ld_elem(gv, pol_stream); v.y = ld_elem(gv + 1, pol_stream);
-            v.z = ld_elem(gv + 2, pol_stream);
-        }
+        // ---- stage A of the NEXT chunk: its bucket load and insert atomic are in
+        //      flight during everything below ---------------------------------------
+        Probe Hn = empty_probe();
+        int64_t id_n = 0;
+        if (ch + stride < k.n_chunks)
+            OA_HASH_CHUNK(ch + stride, wsm + sn * L::BYTES, &full[sn], phase_n, Hn, id_n);
+
+        // ---- stage B: candidate of THIS chunk (its bucket arrived an iteration ago)
+        uint32_t cand = 0xFFFFFFFFu, fill = 0;
+        OaRec<TF> prev;
+        if (active) stage_candidate<TF>(a, k, pol, H, cand, prev, fill);
+
+        // ---- stage C: frame arithmetic, overlapping the record round trip -----------
+        Frame<TF, TVR> F;
+        F.r = 0; F.vr = 0; F.rh[0] = F.rh[1] = F.rh[2] = 0;
         if (active) {
-            Row own;              // rare path only: more regions than a slot stages
-            const Row* R = reinterpret_cast<const Row*>(st + L::ROWS);
-            if (meta.nrows > 0) {
-                // first staged row whose block ends beyond this particle (empty
-                // blocks in between end where they begin and are skipped)
-                for (int q = 1; q < meta.nrows; ++q)
-                    if (c >= R->cur_begin + R->cur_count) ++R;
+            const ChunkMeta meta = *reinterpret_cast<const ChunkMeta*>(st + L::META);
+            Vec3<TX> x, v;
+            if (meta.tma) {
+                const TX* sp = reinterpret_cast<const TX*>(st + L::POS) + 3 * lane;
+                const TX* sv = reinterpret_cast<const TX*>(st + L::VEL) + 3 * lane;
+                x.x = sp[0]; x.y = sp[1]; x.z = sp[2];
+                v.x = sv[0]; v.y = sv[1]; v.z = sv[2];
             } else {
-                load_row(a.regions, find_region(a.cur_off, meta.jlo, meta.jhi, c), &own);
-                R = &own;
+                const TX* gp = static_cast<const TX*>(a.pos) + 3 * c;
+                const TX* gv = static_cast<const TX*>(a.vel) + 3 * c;
+                x.x = ld_elem(gp, pol.first); x.y = ld_elem(gp + 1, pol.first);
+                x.z = ld_elem(gp + 2, pol.first);
+                v.x = ld_elem(gv, pol.first); v.y = ld_elem(gv + 1, pol.first);
+                v.z = ld_elem(gv + 2, pol.first);
             }
-            track_begin<TX, TF, TVR, HUBBLE>(a, k, pol, R, x, v, P);
+            Row own;
+            const Row* R = find_row(a, st + L::ROWS, meta, c, &own);
+            stage_frame<TX, TF, TVR, HUBBLE>(a, k, R, x, v, F);
         }
         // the slot has been consumed: refill it with the chunk D steps ahead
         __syncwarp();
@@ -626,9 +702,16 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
             if (lane == 0) issue(ahead, s, jr_next);
             if (ahead + stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + ahead + stride);
         }
-        if (active) track_finish<TF, TVR, DIAG>(a, k, pol, P);
-        if (++s == D) { s = 0; phase ^= 1u; }
+
+        // ---- stage D ------------------------------------------------------------------
+        if (active) stage_finish<TF, TVR, DIAG>(a, k, pol, id, (uint32_t)c, H, F, cand, prev, fill);
+
+        H = Hn;
+        id = id_n;
+        s = sn;
+        phase = phase_n;
     }
+#undef OA_HASH_CHUNK
 }
 
 template <typename TX, typename TF, typename TVR, bool HUBBLE, bool DIAG>
