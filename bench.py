@@ -321,10 +321,20 @@ def run_b200(args):
 
     comm = sharded.Comm(world, rank) if world > 1 else None
 
+    cat_ahead = {}
+
+    def catalogue(t):
+        """This snapshot's catalogue; multi-GPU: broadcast from rank 0, started
+        one snapshot ahead so that it never stalls the submission."""
+        if comm is None:
+            return cats[t]
+        h = cat_ahead.pop(t, None) or comm.start_broadcast(*cats[t])
+        if t + 1 < n_snap:
+            cat_ahead[t + 1] = comm.start_broadcast(*cats[t + 1])
+        return comm.finish_broadcast(h)
+
     def submit_step(trk, t, host=None):
-        pos, rad, bulk = cats[t]
-        if comm is not None:
-            pos, rad, bulk = comm.broadcast_catalogue(pos, rad, bulk)
+        pos, rad, bulk = catalogue(t)
         if host is None:
             dev, n, offsets = snaps[t]
             return trk.submit_device(
@@ -333,12 +343,27 @@ def run_b200(args):
         return trk.submit(host[t], exists, pos, bulk, 0.0,
                           gpos=host[t].get('_gpos'))
 
+    exchange = {'inflight': None}
+
     def collect_step(trk, pending):
+        """Results of one snapshot.  Multi-GPU: its event exchange is started
+        here and finished one snapshot later (it overlaps the next kernels);
+        returns (local result, finished global result or None)."""
         res = trk.collect(pending)
+        done = None
         if comm is not None and res.apsis_offsets is not None:
             # the merged lists are needed on the host by the writing rank only
-            res = comm.merge_events(trk, res, to_host=(rank == 0))
-        return res
+            h = comm.start_merge(trk, res, to_host=(rank == 0))
+            prev, exchange['inflight'] = exchange['inflight'], h
+            if prev is not None:
+                done = comm.finish_merge(prev)
+        elif comm is None:
+            done = res
+        return res, done
+
+    def flush_exchange():
+        h, exchange['inflight'] = exchange['inflight'], None
+        return comm.finish_merge(h) if h is not None else None
 
     def timed_run(host=None):
         """W+1 untimed snapshots, then K timed ones.  Up to `depth` snapshots
@@ -361,6 +386,7 @@ def run_b200(args):
                 collect_step(trk, queue.popleft())
         while queue:
             collect_step(trk, queue.popleft())
+        flush_exchange()
         trk.timing = []
         launches0 = trk.launches
         barrier()
@@ -373,9 +399,10 @@ def run_b200(args):
 
         def take(p):
             nonlocal n_part, n_events, last
-            last = collect_step(trk, p)
+            last, done = collect_step(trk, p)
             n_part += last.n
-            n_events += last.n_events
+            if done is not None:
+                n_events += done.n_events
         prof = None
         if args.profile and rank == 0:
             import cProfile
@@ -387,6 +414,9 @@ def run_b200(args):
                 take(queue.popleft())
         while queue:
             take(queue.popleft())
+        done = flush_exchange()
+        if done is not None:
+            n_events += done.n_events
         if prof is not None:
             import pstats
             prof.disable()

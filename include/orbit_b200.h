@@ -269,6 +269,22 @@ int oa_merge_event_lists(const int64_t* keys, const int64_t* ids,
                          const uint16_t* angles, int64_t n,
                          const int64_t* list_off, int n_lists, int64_t* ids_out,
                          uint16_t* angles_out, void* stream);
+/* The same exchange without host round trips (every rank, every snapshot):
+ *   oa_pack_events    -> this rank's send buffer: true event count, per-halo
+ *                        counts, then up to `cap` (key, ID, angle) records;
+ *                        `small` = [offsets[n_seg] | total] as left on the device
+ *                        by oa_segment_offsets / oa_select_count;
+ *   (one NCCL all-gather of oa_exchange_bytes(n_seg, cap) bytes per rank)
+ *   oa_merge_gathered -> merged ID / angle lists in key order and
+ *                        info = [total | global offsets[n_seg+1] | sizes[world] |
+ *                        overflow flag (some rank had more than `cap` events)]. */
+size_t oa_exchange_bytes(int n_seg, int64_t cap);
+int oa_pack_events(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
+                   const uint16_t* angles, const int64_t* small, int n_seg,
+                   int64_t cap, void* out, void* stream);
+int oa_merge_gathered(const void* gathered, int world, int n_seg, int64_t cap,
+                      int64_t* ids_out, uint16_t* angles_out, int64_t* info,
+                      void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
 

@@ -136,6 +136,9 @@ _sig('oa_segment_sort_keys', C.c_int, _vp, _i64, _vp, C.c_int, _vp, _vp, _vp,
      _vp, _vp, _vp)
 _sig('oa_merge_event_lists', C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, _vp,
      _vp, _vp)
+_sig('oa_exchange_bytes', _sz, C.c_int, _i64)
+_sig('oa_pack_events', C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp)
+_sig('oa_merge_gathered', C.c_int, _vp, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp)
 _sig('oa_run_heads', C.c_int, _vp, _vp, _i64, _vp, _vp)
 _sig('oa_run_lengths', C.c_int, _vp, _i64, _i64, _vp, _vp)
 _sig('oa_central_radii', C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
@@ -169,7 +172,8 @@ EXPORTS = [
     'oa_synth_params_size', 'oa_segment_sort_keys', 'oa_run_heads',
     'oa_run_lengths', 'oa_merge_event_lists', 'oa_central_radii',
     'oa_segment_heads', 'oa_scatter_flags', 'oa_lookup_sorted', 'oa_vote_keys',
-    'oa_vote_reduce', 'oa_angle_cut', 'oa_expand_segments',
+    'oa_vote_reduce', 'oa_angle_cut', 'oa_expand_segments', 'oa_exchange_bytes',
+    'oa_pack_events', 'oa_merge_gathered',
 ]
 
 

@@ -79,6 +79,130 @@ __global__ void merge_lists_kernel(const int64_t* __restrict__ keys,
     angles_out[pos] = angles[i];
 }
 
+// ---- multi-GPU event exchange without host round trips ---------------------------------
+// Send buffer of one rank (bytes, 16-aligned sections):
+//   [ int64 size | int64 counts[n_seg] | pad | int64 keys[cap] | int64 ids[cap] |
+//     uint16 angles[cap] | pad ]
+// all ranks use the same n_seg and cap, so the all-gathered buffer is `world`
+// such chunks back to back.
+struct ExchangeLayout {
+    int64_t keys, ids, angles, bytes;
+};
+__host__ __device__ inline ExchangeLayout exchange_layout(int n_seg, int64_t cap) {
+    ExchangeLayout L;
+    int64_t o = 8 * (1 + (int64_t)n_seg);
+    o = (o + 15) & ~15ll;
+    L.keys = o;
+    o += 8 * cap;
+    L.ids = o;
+    o += 8 * cap;
+    L.angles = o;
+    o += 2 * cap;
+    L.bytes = (o + 15) & ~15ll;
+    return L;
+}
+
+// small[0..n_seg) = per-segment offsets of the local event list, small[n_seg] =
+// its length (as written by oa_segment_offsets / oa_select_count)
+__global__ void pack_events_kernel(const int64_t* __restrict__ gpos,
+                                   const int64_t* __restrict__ sel,
+                                   const int64_t* __restrict__ ids,
+                                   const uint16_t* __restrict__ angles,
+                                   const int64_t* __restrict__ small, int n_seg, int64_t cap,
+                                   unsigned char* __restrict__ out) {
+    const ExchangeLayout L = exchange_layout(n_seg, cap);
+    const int64_t total = small[n_seg];
+    const int64_t m = total < cap ? total : cap;
+    int64_t* hdr = reinterpret_cast<int64_t*>(out);
+    int64_t* okeys = reinterpret_cast<int64_t*>(out + L.keys);
+    int64_t* oids = reinterpret_cast<int64_t*>(out + L.ids);
+    uint16_t* oang = reinterpret_cast<uint16_t*>(out + L.angles);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 == 0) hdr[0] = total;                       // true size, even if truncated
+    for (int64_t s = t0; s < n_seg; s += stride)
+        hdr[1 + s] = (s + 1 < n_seg ? small[s + 1] : total) - small[s];
+    for (int64_t i = t0; i < m; i += stride) {
+        okeys[i] = gpos[sel[i]];
+        oids[i] = ids[i];
+        oang[i] = angles[i];
+    }
+}
+
+// global per-segment offsets = exclusive scan of the summed per-rank counts
+// (one block; n_seg is the number of halos), total and per-rank sizes
+__global__ void merge_offsets_kernel(const unsigned char* __restrict__ gathered, int world,
+                                     int n_seg, int64_t cap, int64_t* __restrict__ info) {
+    // info: [total | offsets[n_seg + 1] | sizes[world] | overflow]
+    const ExchangeLayout L = exchange_layout(n_seg, cap);
+    __shared__ int64_t s_carry;
+    __shared__ int64_t s_part[1024];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_seg; base += blockDim.x) {
+        const int s = base + threadIdx.x;
+        int64_t v = 0;
+        if (s < n_seg)
+            for (int r = 0; r < world; ++r)
+                v += reinterpret_cast<const int64_t*>(gathered + (size_t)r * L.bytes)[1 + s];
+        s_part[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < (int)blockDim.x; d <<= 1) {        // inclusive scan
+            const int64_t t = threadIdx.x >= (unsigned)d ? s_part[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (s < n_seg) info[1 + s] = s_carry + s_part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry += s_part[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int64_t total = 0, overflow = 0;
+        for (int r = 0; r < world; ++r) {
+            const int64_t sz = reinterpret_cast<const int64_t*>(gathered + (size_t)r * L.bytes)[0];
+            info[2 + n_seg + r] = sz;
+            if (sz > cap) overflow = 1;
+            total += sz < cap ? sz : cap;
+        }
+        info[0] = total;
+        info[1 + n_seg] = s_carry;
+        info[2 + n_seg + world] = overflow;
+    }
+}
+
+// every gathered record finds its place: own rank + number of smaller keys in
+// the other ranks' (ascending) lists
+__global__ void merge_gathered_kernel(const unsigned char* __restrict__ gathered, int world,
+                                      int n_seg, int64_t cap, int64_t* __restrict__ ids_out,
+                                      uint16_t* __restrict__ angles_out) {
+    const ExchangeLayout L = exchange_layout(n_seg, cap);
+    const int r = blockIdx.y;
+    const unsigned char* mine = gathered + (size_t)r * L.bytes;
+    int64_t size = reinterpret_cast<const int64_t*>(mine)[0];
+    if (size > cap) size = cap;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const int64_t key = reinterpret_cast<const int64_t*>(mine + L.keys)[i];
+    int64_t pos = i;
+    for (int q = 0; q < world; ++q) {
+        if (q == r) continue;
+        const unsigned char* other = gathered + (size_t)q * L.bytes;
+        int64_t hi = reinterpret_cast<const int64_t*>(other)[0];
+        if (hi > cap) hi = cap;
+        const int64_t* keys = reinterpret_cast<const int64_t*>(other + L.keys);
+        int64_t lo = 0;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        pos += lo;
+    }
+    ids_out[pos] = reinterpret_cast<const int64_t*>(mine + L.ids)[i];
+    angles_out[pos] = reinterpret_cast<const uint16_t*>(mine + L.angles)[i];
+}
+
 inline unsigned blocks_for(int64_t n, int threads) {
     return (unsigned)((n + threads - 1) / threads);
 }
@@ -109,6 +233,40 @@ extern "C" int oa_merge_event_lists(const int64_t* keys, const int64_t* ids,
                "oa_merge_event_lists: bad arguments");
     merge_lists_kernel<<<blocks_for(n, 256), 256, 0, st>>>(keys, ids, angles, n, list_off,
                                                            n_lists, ids_out, angles_out);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" size_t oa_exchange_bytes(int n_seg, int64_t cap) {
+    return (size_t)exchange_layout(n_seg, cap).bytes;
+}
+
+extern "C" int oa_pack_events(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
+                              const uint16_t* angles, const int64_t* small, int n_seg,
+                              int64_t cap, void* out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(gpos && sel && ids && angles && small && out && n_seg >= 0 && cap >= 1,
+               "oa_pack_events: bad arguments");
+    int64_t blocks = (cap + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    pack_events_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        gpos, sel, ids, angles, small, n_seg, cap, static_cast<unsigned char*>(out));
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_merge_gathered(const void* gathered, int world, int n_seg, int64_t cap,
+                                 int64_t* ids_out, uint16_t* angles_out, int64_t* info,
+                                 void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(gathered && ids_out && angles_out && info && world >= 1 && n_seg >= 0 && cap >= 1,
+               "oa_merge_gathered: bad arguments");
+    merge_offsets_kernel<<<1, 1024, 0, st>>>(static_cast<const unsigned char*>(gathered), world,
+                                             n_seg, cap, info);
+    OA_LAUNCH_CHECK();
+    dim3 grid(blocks_for(cap, 256), (unsigned)world);
+    merge_gathered_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(gathered),
+                                                world, n_seg, cap, ids_out, angles_out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

@@ -42,6 +42,11 @@ def shard_snapshot(snapshot, rank, world):
     return local, keep.astype(np.int64)
 
 
+class _Exchange:
+    """Handle of an exchange in flight (``Comm.start_merge``)."""
+    pass
+
+
 class Comm:
     """Collectives of one tracking step."""
 
@@ -53,36 +58,73 @@ class Comm:
                 if dist.get_backend() == 'nccl' else torch.device('cpu')
         self.device = device
         self.stream = None           # CUDA stream of the exchange (NCCL path)
+        self.cat_stream = None       # stream / communicator of the catalogue
+        self.cat_group = None
+        self._cat_pinned, self._cat_turn = {}, 0
+        self._cap = None             # records per rank in the send buffers
+        self._last_total = 0
 
     # -- catalogue ---------------------------------------------------------------
-    def broadcast_catalogue(self, pos, rad, bulk):
-        """Rank 0's (centres, radii, bulk velocities) to every rank."""
+    def start_broadcast(self, pos, rad, bulk):
+        """Begin broadcasting rank 0's (centres, radii, bulk velocities).  On the
+        NCCL path the broadcast has its own communicator and stream, so it does
+        not queue behind the event exchange; call it one snapshot ahead and
+        ``finish_broadcast`` costs nothing."""
         pos, rad = np.asarray(pos), np.asarray(rad)
         has_bulk = bulk is not None
         n_h = len(rad)
-        buf = np.zeros(7 * n_h, dtype=np.float64)
+        h = _Exchange()
+        h.meta = (pos.dtype, rad.dtype,
+                  np.asarray(bulk).dtype if has_bulk else None, n_h)
+        if self.device.type == 'cuda':
+            if self.cat_stream is None:
+                self.cat_stream = torch.cuda.Stream(self.device)
+                self.cat_group = dist.new_group(backend='nccl')
+            # a small ring of pinned staging buffers (pinning costs ~0.1 ms)
+            ring = self._cat_pinned.setdefault(n_h, [])
+            if len(ring) < 4:
+                ring.append(torch.zeros(7 * n_h, dtype=torch.float64,
+                                        pin_memory=True))
+            self._cat_turn = (self._cat_turn + 1) % 4
+            host = ring[self._cat_turn % len(ring)]
+            buf = host.numpy()
+            buf[:] = 0
+        else:
+            host = None
+            buf = np.zeros(7 * n_h, dtype=np.float64)
         if self.rank == 0:
             buf[:3 * n_h] = pos.reshape(-1)
             buf[3 * n_h:4 * n_h] = rad
             if has_bulk:
                 buf[4 * n_h:] = np.asarray(bulk).reshape(-1)
-        if self.device.type == 'cuda':
-            # on the exchange stream: independent of the kernels in flight
-            if self.stream is None:
-                self.stream = torch.cuda.Stream(self.device)
-            with torch.cuda.stream(self.stream):
-                t = torch.from_numpy(buf).to(self.device)
-                dist.broadcast(t, src=0)
-                out = t.cpu().numpy()
+        if host is not None:
+            with torch.cuda.stream(self.cat_stream):
+                t = host.to(self.device, non_blocking=True)
+                dist.broadcast(t, src=0, group=self.cat_group)
+                host.copy_(t, non_blocking=True)
+                h.ready = torch.cuda.Event()
+                h.ready.record(self.cat_stream)
+            h.host, h.keep = host, t
         else:
             t = torch.from_numpy(buf)
             dist.broadcast(t, src=0)
-            out = t.numpy()
-        pos_o = out[:3 * n_h].reshape(n_h, 3).astype(pos.dtype)
-        rad_o = out[3 * n_h:4 * n_h].astype(rad.dtype)
-        bulk_o = out[4 * n_h:].reshape(n_h, 3).astype(
-            np.asarray(bulk).dtype) if has_bulk else None
+            h.host, h.ready = t, None
+        return h
+
+    def finish_broadcast(self, h):
+        if h.ready is not None:
+            h.ready.synchronize()
+        out = h.host.numpy()
+        pdt, rdt, bdt, n_h = h.meta
+        pos_o = out[:3 * n_h].reshape(n_h, 3).astype(pdt)
+        rad_o = out[3 * n_h:4 * n_h].astype(rdt)
+        bulk_o = out[4 * n_h:].reshape(n_h, 3).astype(bdt) \
+            if bdt is not None else None
         return pos_o, rad_o, bulk_o
+
+    def broadcast_catalogue(self, pos, rad, bulk):
+        """Rank 0's (centres, radii, bulk velocities) to every rank."""
+        return self.finish_broadcast(self.start_broadcast(pos, rad, bulk))
 
     # -- events --------------------------------------------------------------------
     def exchange_events(self, keys, ids, angles, local_counts,
@@ -124,70 +166,116 @@ class Comm:
                rec[:, 2].to(angles.dtype).contiguous(), counts)
         return out + (sizes,) if return_sizes else out
 
-    def merge_events(self, tracker, res, to_host=True):
-        """Turn a rank-local ``StepResult`` (events left in HBM, see
-        ``OrbitTracker.events_on_device``) into the global event lists, ordered
-        like the unsharded reference run.  Every rank's list is already
-        ascending in the order key, so the ordering step is a multi-way merge
-        (``oa_merge_event_lists``), not a sort.  With ``to_host=False`` the
-        merged lists stay on the device (``res.d_ids`` / ``res.d_ang``): only
-        the rank that writes the result file needs them on the host."""
+    # -- events: asynchronous exchange (NCCL path) ---------------------------------
+    HEADROOM = 1.5       # send-buffer capacity / largest event list last snapshot
+
+    def start_merge(self, tracker, res, to_host=True):
+        """Enqueue the exchange of one snapshot's events and return a handle for
+        ``finish_merge``.  Nothing here waits for the GPU: the send buffer is
+        packed by a kernel from the tracker's device arrays (event count and
+        per-halo offsets included), ONE all-gather moves every rank's buffer,
+        and a kernel merges the gathered (ascending) lists by order key and
+        derives the global ``region_offsets``.  The capacity of the send buffers
+        comes from the previous snapshot's sizes; a snapshot whose event list
+        outgrows it is detected in ``finish_merge`` and exchanged again."""
         gen = res.prev_gen
         if gen is None or gen.gpos is None:
             raise _lib.OrbitB200Error(
                 "sharded tracking needs the global block position of every "
                 "particle (pass gpos= to step_device)")
-        # The exchange runs on its own stream, after this snapshot's compaction
-        # only: it overlaps the kernels of the NEXT snapshot, which the caller
-        # has already submitted on the main stream.
+        if res.d_small is None:
+            raise _lib.OrbitB200Error(
+                "start_merge needs OrbitTracker.events_on_device = True")
         if self.stream is None:
             self.stream = torch.cuda.Stream(self.device)
+        if self._cap is None:
+            # first exchange: agree on a capacity (the only blocking collective)
+            t = torch.tensor([res.n_events], dtype=torch.int64,
+                             device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self._cap = self._round_cap(int(t.item()))
+        return self._launch_merge(tracker, res, self._cap, to_host)
+
+    def _round_cap(self, largest):
+        return -(-int(self.HEADROOM * max(largest, 1024)) // 4096) * 4096
+
+    def _launch_merge(self, tracker, res, cap, to_host):
+        gen = res.prev_gen
+        n_seg = len(res.apsis_offsets) - 1
+        h = _Exchange()
+        h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
         self.stream.wait_event(res.compacted)
         with torch.cuda.stream(self.stream):
             st = C.c_void_p(self.stream.cuda_stream)
-            E = res.n_events
-            if res.d_ids is None:
-                res.d_ids = torch.from_numpy(
-                    res.apsis_ids.astype(np.int64, copy=False)).to(self.device)
-                res.d_ang = torch.from_numpy(
-                    res.apsis_angles.view(np.int16)).to(self.device)
-            keys = torch.empty(max(E, 1), dtype=torch.int64,
+            nbytes = lib.oa_exchange_bytes(n_seg, cap)
+            send = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(lib.oa_pack_events(
+                ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+                ptr(res.d_ang_buf), ptr(res.d_small), n_seg, cap, ptr(send),
+                st))
+            recv = torch.empty(self.world * nbytes, dtype=torch.uint8,
                                device=self.device)
-            check(lib.oa_gather_i64(ptr(gen.gpos), ptr(res.apsis_prev_index),
-                                    E, None, ptr(keys), st))
-            local_counts = torch.from_numpy(
-                np.diff(res.apsis_offsets)).to(self.device, non_blocking=True)
-            k_all, i_all, a_all, counts, sizes = self.exchange_events(
-                keys[:E], res.d_ids[:E], res.d_ang[:E], local_counts,
-                return_sizes=True)
-            total = int(k_all.numel())
-            ids_o = torch.empty(max(total, 1), dtype=torch.int64,
+            dist.all_gather_into_tensor(recv, send)
+            h.ids = torch.empty(self.world * cap, dtype=torch.int64,
                                 device=self.device)
-            ang_o = torch.empty(max(total, 1), dtype=torch.int16,
+            h.ang = torch.empty(self.world * cap, dtype=torch.int16,
                                 device=self.device)
-            list_off = torch.from_numpy(np.concatenate(
-                ([0], np.cumsum(sizes))).astype(np.int64)).to(
-                    self.device, non_blocking=True)
-            check(lib.oa_merge_event_lists(
-                ptr(k_all), ptr(i_all), ptr(a_all), total, ptr(list_off),
-                self.world, ptr(ids_o), ptr(ang_o), st))
-            tracker.launches += 2
-            res.d_ids, res.d_ang = ids_o[:total], ang_o[:total]
-            res.n_events = total
-            res.apsis_offsets = np.concatenate(
-                ([0], np.cumsum(counts))).astype(np.int64)
-            # the ring buffers read above may be rewritten only after this
+            info = torch.empty(n_seg + 3 + self.world, dtype=torch.int64,
+                               device=self.device)
+            check(lib.oa_merge_gathered(ptr(recv), self.world, n_seg, cap,
+                                        ptr(h.ids), ptr(h.ang), ptr(info), st))
+            tracker.launches += 3
+            # the tracker's ring buffers read above may be rewritten after this
             done = torch.cuda.Event()
             done.record(self.stream)
             tracker.wait_before_submit = done
-        if to_host:
-            # asynchronous: res.wait_host() before reading apsis_ids / angles
-            h_ids, h_ang, ready = tracker.to_host_async(
-                res.d_ids, res.d_ang, stream=self.stream)
-            res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
-            res.apsis_angles = h_ang.numpy().view(np.float16)
-            res.host_ready = ready
+            h.keep = (send, recv, info)
+        # small read-back (sizes, offsets) and, on the writing rank, a
+        # speculative copy of the merged lists -- all asynchronous
+        spec = min(self.world * cap,
+                   int(1.25 * self._last_total) + 4096) if to_host else 0
+        h.spec = spec
+        outs = tracker.to_host_async(
+            info, h.ids[:spec], h.ang[:spec], stream=self.stream,
+            names=('x_info', 'x_ids', 'x_ang'),
+            reserve=self.world * cap if to_host else 0)
+        h.h_info, h.h_ids, h.h_ang, h.ready = outs
+        return h
+
+    def finish_merge(self, h):
+        """Wait for an exchange and fill the global event lists into its
+        ``StepResult`` (host arrays on the writing rank)."""
+        h.ready.synchronize()
+        info = h.h_info.numpy()
+        total = int(info[0])
+        sizes = info[2 + h.n_seg:2 + h.n_seg + self.world]
+        if int(info[2 + h.n_seg + self.world]):
+            # some rank had more events than the send buffers hold: repeat this
+            # snapshot's exchange with room for the largest list (all ranks see
+            # the same sizes and take the same branch)
+            self._cap = self._round_cap(int(sizes.max()))
+            return self.finish_merge(self._launch_merge(
+                h.tracker, h.res, self._cap, h.to_host))
+        self._cap = max(self._cap, self._round_cap(int(sizes.max())))
+        self._last_total = total
+        res = h.res
+        res.n_events = total
+        res.apsis_offsets = info[1:2 + h.n_seg].copy()
+        res.d_ids, res.d_ang = h.ids[:total], h.ang[:total]
+        if h.to_host:
+            if total > h.spec:                  # the speculative copy fell short
+                h.h_ids, h.h_ang = h.tracker.to_host(res.d_ids, res.d_ang,
+                                                     stream=self.stream)
+            gen = res.prev_gen
+            res.apsis_ids = h.h_ids.numpy()[:total].astype(gen.ids_dtype,
+                                                           copy=False)
+            res.apsis_angles = h.h_ang.numpy()[:total].view(np.float16)
+        h.keep = None
         return res
+
+    def merge_events(self, tracker, res, to_host=True):
+        """``start_merge`` + ``finish_merge``."""
+        return self.finish_merge(self.start_merge(tracker, res, to_host))
 
     def merge(self, keys, ids, angles, local_counts, order, take):
         """Exchange + ordering step shared by the GPU path and the gloo tests.

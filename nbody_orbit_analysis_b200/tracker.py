@@ -43,7 +43,8 @@ class StepResult:
     event after which ``apsis_ids`` / ``apsis_angles`` are valid on the host."""
     __slots__ = ('host_ready', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
-                 'apsis_prev_index', 'prev_gen', 'd_ids', 'd_ang', 'compacted')
+                 'apsis_prev_index', 'prev_gen', 'd_ids', 'd_ang', 'compacted',
+                 'd_sel', 'd_ids_buf', 'd_ang_buf', 'd_small')
 
 
 class Pending:
@@ -212,13 +213,16 @@ class OrbitTracker:
         self.copy_stream.synchronize()
         return out
 
-    def to_host_async(self, *tensors, stream=None):
+    def to_host_async(self, *tensors, stream=None, names=None, reserve=0):
         """Like ``to_host`` without the synchronisation: returns the pinned
-        tensors and the event that marks their completion."""
+        tensors and the event that marks their completion.  With ``names`` the
+        destinations are the tracker's pinned ring buffers of those names."""
         done = torch.cuda.Event()
         done.record(stream if stream is not None else self._main())
         self.copy_stream.wait_event(done)
-        out = [self._to_host_async(t) for t in tensors]
+        names = names or [None] * len(tensors)
+        out = [self._to_host_async(t, name=nm, reserve=reserve)
+               for t, nm in zip(tensors, names)]
         ready = torch.cuda.Event()
         ready.record(self.copy_stream)
         return out + [ready]
@@ -495,6 +499,7 @@ class OrbitTracker:
             p.keep += (ws, d_small)
         else:
             d_small = None
+        p.d_small = d_small
 
         # ---- small device->host copies on the copy stream ----------------------
         done = torch.cuda.Event()
@@ -544,6 +549,7 @@ class OrbitTracker:
         res.n_events = 0
         res.angles = None
         res.d_ids = res.d_ang = None
+        res.d_sel = res.d_ids_buf = res.d_ang_buf = res.d_small = None
         res.host_ready = None
         res.compacted = p.compacted
         res.prev_gen = p.prev
@@ -563,6 +569,9 @@ class OrbitTracker:
             res.n_events = total
             res.apsis_prev_index = p.sel[:total]
             res.d_ids, res.d_ang = p.d_ids[:total], p.d_ang[:total]
+            # whole device buffers + [offsets | total] for the multi-GPU pack
+            res.d_sel, res.d_ids_buf, res.d_ang_buf = p.sel, p.d_ids, p.d_ang
+            res.d_small = p.d_small
             if self.events_on_device:
                 if release:
                     p.keep = None

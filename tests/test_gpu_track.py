@@ -278,4 +278,34 @@ def test_id_sharding_emulated_on_one_gpu(world, tmp_path):
         u = f16_ulps(ang_o.cpu().numpy().view(np.float16), exp['apsis_angles'])
         assert u.size == 0 or u.max() <= 2
         n_events += total
+
+        # the same through the sync-free path: packed send buffers (the
+        # all-gather is emulated by concatenation) + oa_merge_gathered
+        n_seg = len(results[0].apsis_offsets) - 1
+        for cap, overflow in ((max(sizes) + 5, 0), (max(max(sizes) // 2, 1), 1)):
+            nbytes = lib.oa_exchange_bytes(n_seg, cap)
+            sends = []
+            for res in results:
+                send = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+                check(lib.oa_pack_events(
+                    ptr(res.prev_gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+                    ptr(res.d_ang_buf), ptr(res.d_small), n_seg, cap, ptr(send),
+                    st))
+                sends.append(send)
+            recv = torch.cat(sends)
+            ids2 = torch.empty(world * cap, dtype=torch.int64, device=dev)
+            ang2 = torch.empty(world * cap, dtype=torch.int16, device=dev)
+            info = torch.empty(n_seg + 3 + world, dtype=torch.int64, device=dev)
+            check(lib.oa_merge_gathered(ptr(recv), world, n_seg, cap, ptr(ids2),
+                                        ptr(ang2), ptr(info), st))
+            info = info.cpu().numpy()
+            assert int(info[2 + n_seg + world]) == overflow
+            assert list(info[2 + n_seg:2 + n_seg + world]) == sizes
+            assert np.array_equal(info[1:2 + n_seg], exp['apsis_offsets'])
+            if not overflow:
+                assert int(info[0]) == total
+                assert np.array_equal(ids2[:total].cpu().numpy(),
+                                      exp['apsis_ids'])
+                assert np.array_equal(ang2[:total].cpu().numpy(),
+                                      ang_o.cpu().numpy())
     assert n_events > 0
