@@ -201,6 +201,14 @@ int oa_select_count(const uint16_t* marks, int64_t n, int op, uint16_t value,
                     int64_t* total_dev, void* stream);
 int oa_select_gather(const uint16_t* marks, int64_t n, int op, uint16_t value,
                      const void* workspace, int64_t* sel_out, void* stream);
+/* Event lists in one pass (after oa_select_count with OA_SEL_NE, OA_NO_EVENT):
+ * positions, IDs (from the previous records) and float16 angles (the marks
+ * themselves) of all events, in previous-block order: apsis_inds / apsis_ids /
+ * apsis_angles of track_orbits.py:315-316, 347. */
+int oa_select_gather_events(const uint16_t* marks, int64_t n,
+                            const void* workspace, const void* rec,
+                            int frame_dtype, int64_t* sel_out, int64_t* ids_out,
+                            uint16_t* angles_out, void* stream);
 /* Consumers of a selection.  `n_sel` is the number of selected positions; when
  * `n_dev` is not NULL it points to the exact count ON THE DEVICE (as written by
  * oa_select_count) and `n_sel` is only an upper bound used to size the launch,

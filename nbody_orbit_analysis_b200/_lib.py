@@ -120,6 +120,8 @@ if lib.oa_track_args_size() != C.sizeof(TrackArgs):
 _sig('oa_select_workspace_bytes', _sz, _i64)
 _sig('oa_select_count', C.c_int, _vp, _i64, C.c_int, _u16, _vp, _sz, _vp, _vp)
 _sig('oa_select_gather', C.c_int, _vp, _i64, C.c_int, _u16, _vp, _vp, _vp)
+_sig('oa_select_gather_events', C.c_int, _vp, _i64, _vp, _vp, C.c_int, _vp, _vp,
+     _vp, _vp)
 _sig('oa_segment_offsets', C.c_int, _vp, _i64, _vp, _vp, C.c_int, _vp, _vp)
 _sig('oa_gather_record_ids', C.c_int, _vp, C.c_int, _vp, _i64, _vp, _vp, _vp)
 _sig('oa_gather_u16', C.c_int, _vp, _vp, _i64, _vp, _vp, _vp)
@@ -173,7 +175,7 @@ EXPORTS = [
     'oa_run_lengths', 'oa_merge_event_lists', 'oa_central_radii',
     'oa_segment_heads', 'oa_scatter_flags', 'oa_lookup_sorted', 'oa_vote_keys',
     'oa_vote_reduce', 'oa_angle_cut', 'oa_expand_segments', 'oa_exchange_bytes',
-    'oa_pack_events', 'oa_merge_gathered',
+    'oa_pack_events', 'oa_merge_gathered', 'oa_select_gather_events',
 ]
 
 

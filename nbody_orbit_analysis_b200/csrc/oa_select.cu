@@ -106,6 +106,33 @@ sel_gather_kernel(const uint16_t* __restrict__ marks, int64_t n, int op,
     }
 }
 
+// Event variant: the selected marks ARE the float16 event angles, and the event
+// ID is in the previous record at the same position -- one kernel writes the
+// three event arrays (positions, IDs, angles).
+template <typename TF>
+__global__ void __launch_bounds__(SEL_THREADS)
+sel_gather_events_kernel(const uint16_t* __restrict__ marks, int64_t n,
+                         const int64_t* __restrict__ tile_offsets,
+                         const OaRec<TF>* __restrict__ rec, int64_t* __restrict__ sel_out,
+                         int64_t* __restrict__ ids_out, uint16_t* __restrict__ angles_out) {
+    const int64_t tile = blockIdx.x;
+    const int64_t first = tile * SEL_TILE + (int64_t)threadIdx.x * SEL_ITEMS;
+    const uint32_t bits = first < n ? load_flags(marks, n, first, OA_SEL_NE, OA_NO_EVENT) : 0u;
+    uint32_t total;
+    const uint32_t excl = oa_block_exclusive_scan<SEL_THREADS>(__popc(bits), &total);
+    if (bits) {
+        int64_t o = tile_offsets[tile] + excl;
+#pragma unroll
+        for (int i = 0; i < SEL_ITEMS; ++i)
+            if (bits & (1u << i)) {
+                sel_out[o] = first + i;
+                ids_out[o] = rec[first + i].id;
+                angles_out[o] = marks[first + i];
+                ++o;
+            }
+    }
+}
+
 // Every consumer of a selection takes `n_sel` (a host-side upper bound) and an
 // optional device pointer `n_dev` to the exact count, so that a whole snapshot
 // can be enqueued without a host synchronisation in the middle.
@@ -219,6 +246,26 @@ extern "C" int oa_select_gather(const uint16_t* marks, int64_t n, int op,
     const int64_t tiles = sel_tiles(n);
     sel_gather_kernel<<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
         marks, n, op, value, ws_offsets(const_cast<void*>(workspace)), sel_out);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_select_gather_events(const uint16_t* marks, int64_t n,
+                                       const void* workspace, const void* rec,
+                                       int frame_dtype, int64_t* sel_out, int64_t* ids_out,
+                                       uint16_t* angles_out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0) return OA_OK;
+    OA_REQUIRE(marks && workspace && rec && sel_out && ids_out && angles_out,
+               "oa_select_gather_events: NULL pointer");
+    const int64_t tiles = sel_tiles(n);
+    const int64_t* offs = ws_offsets(const_cast<void*>(workspace));
+    if (frame_dtype == OA_F64)
+        sel_gather_events_kernel<double><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
+            marks, n, offs, static_cast<const OaRec<double>*>(rec), sel_out, ids_out, angles_out);
+    else
+        sel_gather_events_kernel<float><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
+            marks, n, offs, static_cast<const OaRec<float>*>(rec), sel_out, ids_out, angles_out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

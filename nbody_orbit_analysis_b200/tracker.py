@@ -21,6 +21,8 @@ from . import _lib
 from ._lib import lib, check, ptr
 
 _F = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+_ITEMSIZE = {torch.uint8: 1, torch.int8: 1, torch.int16: 2, torch.float16: 2,
+             torch.int32: 4, torch.float32: 4, torch.int64: 8, torch.float64: 8}
 
 
 def require_cuda():
@@ -117,7 +119,7 @@ class OrbitTracker:
         copy stream only reads per-step outputs, which ``collect`` has
         synchronised on long before their slot comes round again."""
         slot = self._step % self.RING if slot is None else slot
-        item = torch.empty(0, dtype=dtype).element_size()
+        item = _ITEMSIZE[dtype]
         nbytes = max(int(n), 1) * item
         key = (name, slot)
         raw = self._pool.get(key)
@@ -175,7 +177,7 @@ class OrbitTracker:
         arrays handed to the caller are views into these buffers: they stay
         valid until ``HOST_RING - 2`` further snapshots have been submitted."""
         step = self._step if step is None else step
-        item = torch.empty(0, dtype=dtype).element_size()
+        item = _ITEMSIZE[dtype]
         nbytes = max(int(n), 1) * item
         key = (name, step % self.HOST_RING)
         raw = self._hpool.get(key)
@@ -484,18 +486,14 @@ class OrbitTracker:
             p.sel = self._buf('sel', cap, torch.int64)
             p.d_ids = self._buf('ev_ids', cap, torch.int64)
             p.d_ang = self._buf('ev_ang', cap, torch.int16)
-            check(lib.oa_select_gather(
-                ptr(prev.mark), prev.n, _lib.OA_SEL_NE, _lib.OA_NO_EVENT,
-                ptr(ws), ptr(p.sel), st))
+            check(lib.oa_select_gather_events(
+                ptr(prev.mark), prev.n, ptr(ws), ptr(prev.rec),
+                int(prev.frame_f64), ptr(p.sel), ptr(p.d_ids), ptr(p.d_ang),
+                st))
             check(lib.oa_segment_offsets(
                 ptr(p.sel), cap, ptr(d_total), ptr(d_seg), n_m, ptr(d_small),
                 st))
-            check(lib.oa_gather_record_ids(
-                ptr(prev.rec), int(prev.frame_f64), ptr(p.sel), cap,
-                ptr(d_total), ptr(p.d_ids), st))
-            check(lib.oa_gather_u16(ptr(prev.mark), ptr(p.sel), cap,
-                                    ptr(d_total), ptr(p.d_ang), st))
-            self.launches += 6
+            self.launches += 4
             p.keep += (ws, d_small)
         else:
             d_small = None
