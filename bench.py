@@ -352,8 +352,9 @@ def run_b200(args):
         res = trk.collect(pending)
         done = None
         if comm is not None and res.apsis_offsets is not None:
-            # the merged lists are needed on the host by the writing rank only
-            h = comm.start_merge(trk, res, to_host=(rank == 0))
+            # every rank hands its 1/world share of the merged lists to the
+            # host (parallel write of the result datasets)
+            h = comm.start_merge(trk, res, to_host='slice')
             prev, exchange['inflight'] = exchange['inflight'], h
             if prev is not None:
                 done = comm.finish_merge(prev)
@@ -372,6 +373,8 @@ def run_b200(args):
         kernels of the following snapshots)."""
         trk = OrbitTracker(mode=args.mode)
         trk.events_on_device = comm is not None
+        if comm is not None:       # room for the NCCL kernels of the exchange
+            trk.sm_reserve = int(os.environ.get('OA_SM_RESERVE', '12'))
         # nvidia-smi is started before the warm-up: its NVML initialisation
         # stalls CUDA calls for tens of ms and must not fall in the timed region
         sampler = ClockSampler(local)

@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 10
+#define OA_ABI_VERSION 11
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -165,6 +165,11 @@ typedef struct oa_track_args {
     uint16_t* mark_cur;     /* (n_cur,) written: "no event"                   */
     void* workspace;        /* oa_track_workspace_bytes(n_cur) bytes          */
     size_t workspace_bytes;
+    /* The kernel is persistent, one CTA per SM.  sm_reserve > 0 leaves that many
+     * SMs free so that kernels of other streams (the NCCL event exchange of the
+     * previous snapshot) run concurrently instead of after it. */
+    int32_t sm_reserve;
+    int32_t reserved0;
     /* optional per-particle outputs, NULL to skip */
     void* out_rhat;         /* (n_cur,3) frame_dtype                          */
     void* out_vr;           /* (n_cur,) float64 (float32 if onthefly && F32)  */

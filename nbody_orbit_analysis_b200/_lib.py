@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 10
+ABI_VERSION = 11
 BUCKET_LOAD = 3          # OA_BUCKET_LOAD
 
 
@@ -76,6 +76,7 @@ class TrackArgs(C.Structure):
         ('mark_prev', _vp),
         ('rec_cur', _vp), ('tab_cur', _vp), ('tab_cur_buckets', _i64),
         ('mark_cur', _vp), ('workspace', _vp), ('workspace_bytes', _sz),
+        ('sm_reserve', _i32), ('reserved0', _i32),
         ('out_rhat', _vp), ('out_vr', _vp), ('out_r', _vp),
         ('out_angle', _vp), ('out_match', _vp), ('dangle_prev', _vp),
     ]

@@ -756,6 +756,7 @@ int launch_track_impl(const oa_track_args& a, cudaStream_t st) {
         a.cur_off, a.n_regions, a.n_cur, k.n_chunks, chunks);
     OA_LAUNCH_CHECK();
     int64_t grid = sms;                         // persistent: one CTA per SM
+    if (a.sm_reserve > 0 && a.sm_reserve < sms) grid = sms - a.sm_reserve;
     const int64_t ctas_needed = (k.n_chunks + TRACK_WARPS - 1) / TRACK_WARPS;
     if (grid > ctas_needed) grid = ctas_needed;
     kern<<<(unsigned)grid, TRACK_THREADS, smem_bytes, st>>>(a, k);

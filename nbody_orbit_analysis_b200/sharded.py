@@ -230,16 +230,9 @@ class Comm:
             done.record(self.stream)
             tracker.wait_before_submit = done
             h.keep = (send, recv, info)
-        # small read-back (sizes, offsets) and, on the writing rank, a
-        # speculative copy of the merged lists -- all asynchronous
-        spec = min(self.world * cap,
-                   int(1.25 * self._last_total) + 4096) if to_host else 0
-        h.spec = spec
-        outs = tracker.to_host_async(
-            info, h.ids[:spec], h.ang[:spec], stream=self.stream,
-            names=('x_info', 'x_ids', 'x_ang'),
-            reserve=self.world * cap if to_host else 0)
-        h.h_info, h.h_ids, h.h_ang, h.ready = outs
+        # small read-back (total, global offsets, sizes, overflow flag)
+        h.h_info, h.ready = tracker.to_host_async(
+            info, stream=self.stream, names=('x_info',))
         return h
 
     def finish_merge(self, h):
@@ -263,19 +256,30 @@ class Comm:
         res.apsis_offsets = info[1:2 + h.n_seg].copy()
         res.d_ids, res.d_ang = h.ids[:total], h.ang[:total]
         if h.to_host:
-            if total > h.spec:                  # the speculative copy fell short
-                h.h_ids, h.h_ang = h.tracker.to_host(res.d_ids, res.d_ang,
-                                                     stream=self.stream)
+            # the merged lists live on every rank; hand the host either all of
+            # them (single writer) or this rank's 1/world share (parallel write:
+            # the per-rank copy stays constant under weak scaling).  The copy is
+            # asynchronous: wait for res.host_ready before reading.
+            lo, hi = 0, total
+            if h.to_host == 'slice':
+                lo = total * self.rank // self.world
+                hi = total * (self.rank + 1) // self.world
             gen = res.prev_gen
-            res.apsis_ids = h.h_ids.numpy()[:total].astype(gen.ids_dtype,
-                                                           copy=False)
-            res.apsis_angles = h.h_ang.numpy()[:total].view(np.float16)
+            h_ids, h_ang, ready = h.tracker.to_host_async(
+                res.d_ids[lo:hi], res.d_ang[lo:hi], stream=self.stream,
+                names=('x_ids', 'x_ang'), reserve=hi - lo)
+            res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
+            res.apsis_angles = h_ang.numpy().view(np.float16)
+            res.host_slice, res.host_ready = (lo, hi), ready
         h.keep = None
         return res
 
     def merge_events(self, tracker, res, to_host=True):
-        """``start_merge`` + ``finish_merge``."""
-        return self.finish_merge(self.start_merge(tracker, res, to_host))
+        """``start_merge`` + ``finish_merge`` + wait for the host copy."""
+        res = self.finish_merge(self.start_merge(tracker, res, to_host))
+        if res.host_ready is not None:
+            res.host_ready.synchronize()
+        return res
 
     def merge(self, keys, ids, angles, local_counts, order, take):
         """Exchange + ordering step shared by the GPU path and the gloo tests.

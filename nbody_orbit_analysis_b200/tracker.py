@@ -43,7 +43,7 @@ class Generation:
 class StepResult:
     """Results of one snapshot.  ``host_ready`` (multi-GPU merge only) is the
     event after which ``apsis_ids`` / ``apsis_angles`` are valid on the host."""
-    __slots__ = ('host_ready', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
+    __slots__ = ('host_ready', 'host_slice', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
                  'apsis_prev_index', 'prev_gen', 'd_ids', 'd_ang', 'compacted',
                  'd_sel', 'd_ids_buf', 'd_ang_buf', 'd_small')
@@ -100,6 +100,7 @@ class OrbitTracker:
         # the NCCL exchange instead of being copied to the host per rank
         self.events_on_device = False
         self.wait_before_submit = None   # event the next submit must wait for
+        self.sm_reserve = 0        # SMs the fused kernel leaves to other streams
 
     # -- buffers -------------------------------------------------------------
     RING = 3      # generations / in-flight steps a buffer name cycles through
@@ -444,6 +445,7 @@ class OrbitTracker:
             a.out_match = ptr(diag['match'])
         a.dangle_prev = ptr(dangle)
         a.tab_cur_buckets = gen.n_buckets
+        a.sm_reserve = self.sm_reserve
         a.workspace_bytes = lib.oa_track_workspace_bytes(n)
         tile_ws = self._buf('chunk_ws', a.workspace_bytes, torch.uint8)
         a.workspace = ptr(tile_ws)
@@ -548,7 +550,7 @@ class OrbitTracker:
         res.angles = None
         res.d_ids = res.d_ang = None
         res.d_sel = res.d_ids_buf = res.d_ang_buf = res.d_small = None
-        res.host_ready = None
+        res.host_ready = res.host_slice = None
         res.compacted = p.compacted
         res.prev_gen = p.prev
         p.small_done.synchronize()
