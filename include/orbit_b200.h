@@ -298,6 +298,27 @@ int oa_pack_events(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
 int oa_merge_gathered(const void* gathered, int world, int n_seg, int64_t cap,
                       int64_t* ids_out, uint16_t* angles_out, int64_t* info,
                       void* stream);
+/* Scalable exchange (volume per rank independent of the number of GPUs): the
+ * key space is cut into `world` ranges at quantiles of the order key; rank q
+ * receives range q from everyone (all-to-all), merges and owns that contiguous
+ * slice of the global lists.
+ *   oa_split_quantiles : q_out[world-1] = this rank's quantile keys (every
+ *                        rank's events are a uniform sample of all events);
+ *   (all-gather of the proposals)
+ *   oa_pack_split      : splitters = per-quantile median of the proposals;
+ *                        send buffer = `world` blocks of oa_exchange_bytes(0, cap)
+ *                        bytes; counts[n_seg] = this rank's per-halo counts;
+ *                        bnd_ws: world+1 int64;
+ *   (all-to-all of the blocks, all-reduce of counts)
+ *   oa_merge_blocks    : this rank's slice in key order, info = [size | overflow]. */
+int oa_split_quantiles(const int64_t* gpos, const int64_t* sel, const int64_t* small,
+                       int n_seg, int world, int64_t* q_out, void* stream);
+int oa_pack_split(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
+                  const uint16_t* angles, const int64_t* small, int n_seg,
+                  const int64_t* proposals, int world, int64_t cap,
+                  int64_t* bnd_ws, void* out, int64_t* counts, void* stream);
+int oa_merge_blocks(const void* recv, int world, int64_t cap, int64_t* ids_out,
+                    uint16_t* angles_out, int64_t* info, void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
 

@@ -142,6 +142,10 @@ _sig('oa_merge_event_lists', C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, _vp,
 _sig('oa_exchange_bytes', _sz, C.c_int, _i64)
 _sig('oa_pack_events', C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp)
 _sig('oa_merge_gathered', C.c_int, _vp, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp)
+_sig('oa_split_quantiles', C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp)
+_sig('oa_pack_split', C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int,
+     _i64, _vp, _vp, _vp, _vp)
+_sig('oa_merge_blocks', C.c_int, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp)
 _sig('oa_run_heads', C.c_int, _vp, _vp, _i64, _vp, _vp)
 _sig('oa_run_lengths', C.c_int, _vp, _i64, _i64, _vp, _vp)
 _sig('oa_central_radii', C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
@@ -177,6 +181,7 @@ EXPORTS = [
     'oa_segment_heads', 'oa_scatter_flags', 'oa_lookup_sorted', 'oa_vote_keys',
     'oa_vote_reduce', 'oa_angle_cut', 'oa_expand_segments', 'oa_exchange_bytes',
     'oa_pack_events', 'oa_merge_gathered', 'oa_select_gather_events',
+    'oa_split_quantiles', 'oa_pack_split', 'oa_merge_blocks',
 ]
 
 

@@ -203,6 +203,127 @@ __global__ void merge_gathered_kernel(const unsigned char* __restrict__ gathered
     angles_out[pos] = reinterpret_cast<const uint16_t*>(mine + L.angles)[i];
 }
 
+// ---- scalable variant: key-range partitioned merge (all-to-all) ---------------------------
+// Every rank's events are a uniform sample of all events (particles are sharded
+// by ID), so local quantiles of the order key are global quantiles: they split
+// the key space into `world` ranges of (nearly) equal event counts.  Rank q
+// receives from every rank the events of range q, merges the `world` ascending
+// lists and owns that contiguous part of the global lists.  Volume per rank:
+// its own share, whatever the number of GPUs.
+//
+// local quantile keys: q_out[j] = key of local event floor(total * (j+1) / world)
+__global__ void quantile_keys_kernel(const int64_t* __restrict__ gpos,
+                                     const int64_t* __restrict__ sel,
+                                     const int64_t* __restrict__ small, int n_seg, int world,
+                                     int64_t* __restrict__ q_out) {
+    const int j = threadIdx.x;
+    if (j >= world - 1) return;
+    const int64_t total = small[n_seg];
+    // a rank without events proposes +inf (it is out-voted by the median below)
+    q_out[j] = total > 0 ? gpos[sel[total * (j + 1) / world]] : INT64_MAX;
+}
+
+// splitters = per-quantile median over the ranks' proposals; bounds of the local
+// (ascending) event list: bnd[q] = first local event with key >= splitter[q-1]
+__global__ void split_bounds_kernel(const int64_t* __restrict__ proposals, int world,
+                                    const int64_t* __restrict__ gpos,
+                                    const int64_t* __restrict__ sel,
+                                    const int64_t* __restrict__ small, int n_seg,
+                                    int64_t* __restrict__ bnd) {
+    const int q = threadIdx.x;                      // 0 .. world
+    if (q > world) return;
+    const int64_t total = small[n_seg];
+    if (q == 0) { bnd[0] = 0; return; }
+    if (q == world) { bnd[world] = total; return; }
+    // median of proposals[r][q-1] over ranks r (world <= 64: insertion into registers)
+    int64_t v[64];
+    for (int r = 0; r < world; ++r) {
+        int64_t x = proposals[r * (world - 1) + (q - 1)];
+        int k = r;
+        while (k > 0 && v[k - 1] > x) { v[k] = v[k - 1]; --k; }
+        v[k] = x;
+    }
+    const int64_t split = v[(world - 1) / 2];
+    int64_t lo = 0, hi = total;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (gpos[sel[mid]] < split) lo = mid + 1; else hi = mid;
+    }
+    bnd[q] = lo;
+}
+
+// send buffer: `world` blocks of exchange_layout(0, cap) bytes, block q = events
+// bnd[q] .. bnd[q+1]; counts[] = per-segment event counts of this rank
+__global__ void pack_split_kernel(const int64_t* __restrict__ gpos,
+                                  const int64_t* __restrict__ sel,
+                                  const int64_t* __restrict__ ids,
+                                  const uint16_t* __restrict__ angles,
+                                  const int64_t* __restrict__ small, int n_seg,
+                                  const int64_t* __restrict__ bnd, int world, int64_t cap,
+                                  unsigned char* __restrict__ out,
+                                  int64_t* __restrict__ counts) {
+    const ExchangeLayout L = exchange_layout(0, cap);
+    const int64_t total = small[n_seg];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t s = t0; s < n_seg; s += stride)
+        counts[s] = (s + 1 < n_seg ? small[s + 1] : total) - small[s];
+    if (t0 < world)
+        reinterpret_cast<int64_t*>(out + (size_t)t0 * L.bytes)[0] = bnd[t0 + 1] - bnd[t0];
+    for (int64_t i = t0; i < total; i += stride) {
+        int q = 0;
+        while (q + 1 < world && i >= bnd[q + 1]) ++q;
+        const int64_t k = i - bnd[q];
+        if (k >= cap) continue;                       // overflow: flagged by the receiver
+        unsigned char* blk = out + (size_t)q * L.bytes;
+        reinterpret_cast<int64_t*>(blk + L.keys)[k] = gpos[sel[i]];
+        reinterpret_cast<int64_t*>(blk + L.ids)[k] = ids[i];
+        reinterpret_cast<uint16_t*>(blk + L.angles)[k] = angles[i];
+    }
+}
+
+// merge of the `world` received blocks (same layout, block r from rank r) into
+// this rank's slice; info = [slice size | overflow flag]
+__global__ void merge_blocks_kernel(const unsigned char* __restrict__ recv, int world,
+                                    int64_t cap, int64_t* __restrict__ ids_out,
+                                    uint16_t* __restrict__ angles_out,
+                                    int64_t* __restrict__ info) {
+    const ExchangeLayout L = exchange_layout(0, cap);
+    const int r = blockIdx.y;
+    const unsigned char* mine = recv + (size_t)r * L.bytes;
+    const int64_t true_size = reinterpret_cast<const int64_t*>(mine)[0];
+    const int64_t size = true_size < cap ? true_size : cap;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && r == 0) {
+        int64_t tot = 0, over = 0;
+        for (int q = 0; q < world; ++q) {
+            const int64_t sz = reinterpret_cast<const int64_t*>(recv + (size_t)q * L.bytes)[0];
+            if (sz > cap) over = 1;
+            tot += sz < cap ? sz : cap;
+        }
+        info[0] = tot;
+        info[1] = over;
+    }
+    if (i >= size) return;
+    const int64_t key = reinterpret_cast<const int64_t*>(mine + L.keys)[i];
+    int64_t pos = i;
+    for (int q = 0; q < world; ++q) {
+        if (q == r) continue;
+        const unsigned char* other = recv + (size_t)q * L.bytes;
+        int64_t hi = reinterpret_cast<const int64_t*>(other)[0];
+        if (hi > cap) hi = cap;
+        const int64_t* keys = reinterpret_cast<const int64_t*>(other + L.keys);
+        int64_t lo = 0;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        pos += lo;
+    }
+    ids_out[pos] = reinterpret_cast<const int64_t*>(mine + L.ids)[i];
+    angles_out[pos] = reinterpret_cast<const uint16_t*>(mine + L.angles)[i];
+}
+
 inline unsigned blocks_for(int64_t n, int threads) {
     return (unsigned)((n + threads - 1) / threads);
 }
@@ -267,6 +388,49 @@ extern "C" int oa_merge_gathered(const void* gathered, int world, int n_seg, int
     dim3 grid(blocks_for(cap, 256), (unsigned)world);
     merge_gathered_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(gathered),
                                                 world, n_seg, cap, ids_out, angles_out);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_split_quantiles(const int64_t* gpos, const int64_t* sel,
+                                  const int64_t* small, int n_seg, int world,
+                                  int64_t* q_out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(gpos && sel && small && q_out && world >= 1 && world <= 64,
+               "oa_split_quantiles: bad arguments");
+    if (world == 1) return OA_OK;
+    quantile_keys_kernel<<<1, 64, 0, st>>>(gpos, sel, small, n_seg, world, q_out);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_pack_split(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
+                             const uint16_t* angles, const int64_t* small, int n_seg,
+                             const int64_t* proposals, int world, int64_t cap,
+                             int64_t* bnd_ws, void* out, int64_t* counts, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(gpos && sel && ids && angles && small && bnd_ws && out && counts &&
+               world >= 1 && world <= 64 && cap >= 1 && (world == 1 || proposals),
+               "oa_pack_split: bad arguments");
+    split_bounds_kernel<<<1, 96, 0, st>>>(proposals, world, gpos, sel, small, n_seg, bnd_ws);
+    OA_LAUNCH_CHECK();
+    int64_t blocks = (cap * world + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    pack_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        gpos, sel, ids, angles, small, n_seg, bnd_ws, world, cap,
+        static_cast<unsigned char*>(out), counts);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_merge_blocks(const void* recv, int world, int64_t cap, int64_t* ids_out,
+                               uint16_t* angles_out, int64_t* info, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(recv && ids_out && angles_out && info && world >= 1 && cap >= 1,
+               "oa_merge_blocks: bad arguments");
+    dim3 grid(blocks_for(cap, 256), (unsigned)world);
+    merge_blocks_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(recv), world,
+                                              cap, ids_out, angles_out, info);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

@@ -194,7 +194,60 @@ class Comm:
                              device=self.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             self._cap = self._round_cap(int(t.item()))
-        return self._launch_merge(tracker, res, self._cap, to_host)
+        if to_host is True:
+            # a single writer needs the whole merged list: all-gather path
+            return self._launch_merge(tracker, res, self._cap, to_host)
+        # every rank keeps (and writes) its own key range: all-to-all path, the
+        # volume per rank does not grow with the number of GPUs
+        return self._launch_split(tracker, res, self._block_cap(), to_host)
+
+    def _block_cap(self):
+        return -(-self._cap // self.world // 1024 + 1) * 1024
+
+    def _launch_split(self, tracker, res, cap, to_host):
+        gen = res.prev_gen
+        W = self.world
+        n_seg = len(res.apsis_offsets) - 1
+        h = _Exchange()
+        h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
+        h.split = True
+        self.stream.wait_event(res.compacted)
+        with torch.cuda.stream(self.stream):
+            st = C.c_void_p(self.stream.cuda_stream)
+            i64 = dict(dtype=torch.int64, device=self.device)
+            u8 = dict(dtype=torch.uint8, device=self.device)
+            prop = torch.empty(max(W - 1, 1), **i64)
+            check(lib.oa_split_quantiles(ptr(gen.gpos), ptr(res.d_sel),
+                                         ptr(res.d_small), n_seg, W, ptr(prop),
+                                         st))
+            prop_all = torch.empty(W * max(W - 1, 1), **i64)
+            dist.all_gather_into_tensor(prop_all, prop)
+            blk = lib.oa_exchange_bytes(0, cap)
+            send = torch.empty(W * blk, **u8)
+            recv = torch.empty(W * blk, **u8)
+            counts = torch.empty(max(n_seg, 1), **i64)
+            bnd = torch.empty(W + 1, **i64)
+            check(lib.oa_pack_split(
+                ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+                ptr(res.d_ang_buf), ptr(res.d_small), n_seg, ptr(prop_all), W,
+                cap, ptr(bnd), ptr(send), ptr(counts), st))
+            dist.all_to_all_single(recv, send)
+            h.ids = torch.empty(W * cap, **i64)
+            h.ang = torch.empty(W * cap, dtype=torch.int16, device=self.device)
+            info = torch.empty(2, **i64)
+            check(lib.oa_merge_blocks(ptr(recv), W, cap, ptr(h.ids), ptr(h.ang),
+                                      ptr(info), st))
+            info_all = torch.empty(2 * W, **i64)
+            dist.all_gather_into_tensor(info_all, info)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+            tracker.launches += 5
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            tracker.wait_before_submit = done
+            h.keep = (send, recv, prop, prop_all, bnd, info)
+        h.h_info, h.h_counts, h.ready = tracker.to_host_async(
+            info_all, counts, stream=self.stream, names=('x_info', 'x_counts'))
+        return h
 
     def _round_cap(self, largest):
         return -(-int(self.HEADROOM * max(largest, 1024)) // 4096) * 4096
@@ -237,8 +290,14 @@ class Comm:
 
     def finish_merge(self, h):
         """Wait for an exchange and fill the global event lists into its
-        ``StepResult`` (host arrays on the writing rank)."""
+        ``StepResult``: ``n_events`` and ``apsis_offsets`` are global;
+        ``d_ids`` / ``d_ang`` (and, after ``host_ready``, ``apsis_ids`` /
+        ``apsis_angles``) hold the records ``host_slice`` of the global lists --
+        everything on the all-gather path, this rank's key range on the
+        all-to-all path."""
         h.ready.synchronize()
+        if getattr(h, 'split', False):
+            return self._finish_split(h)
         info = h.h_info.numpy()
         total = int(info[0])
         sizes = info[2 + h.n_seg:2 + h.n_seg + self.world]
@@ -267,10 +326,40 @@ class Comm:
             gen = res.prev_gen
             h_ids, h_ang, ready = h.tracker.to_host_async(
                 res.d_ids[lo:hi], res.d_ang[lo:hi], stream=self.stream,
-                names=('x_ids', 'x_ang'), reserve=hi - lo)
+                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap))
             res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
             res.apsis_angles = h_ang.numpy().view(np.float16)
             res.host_slice, res.host_ready = (lo, hi), ready
+        h.keep = None
+        return res
+
+    def _finish_split(self, h):
+        W = self.world
+        info = h.h_info.numpy().reshape(W, 2)
+        sizes = info[:, 0]
+        if info[:, 1].any():
+            # a block outgrew the send buffers: repeat with generous room
+            self._cap = self._round_cap(int(sizes.max()) * W * 2)
+            return self.finish_merge(self._launch_split(
+                h.tracker, h.res, self._block_cap(), h.to_host))
+        self._cap = max(self._cap, self._round_cap(int(sizes.max())))
+        res = h.res
+        total = int(sizes.sum())
+        lo = int(sizes[:self.rank].sum())
+        hi = lo + int(sizes[self.rank])
+        res.n_events = total
+        res.apsis_offsets = np.concatenate(
+            ([0], np.cumsum(h.h_counts.numpy()[:h.n_seg]))).astype(np.int64)
+        res.d_ids, res.d_ang = h.ids[:hi - lo], h.ang[:hi - lo]
+        res.host_slice = (lo, hi)
+        if h.to_host:
+            gen = res.prev_gen
+            h_ids, h_ang, ready = h.tracker.to_host_async(
+                res.d_ids, res.d_ang, stream=self.stream,
+                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap))
+            res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
+            res.apsis_angles = h_ang.numpy().view(np.float16)
+            res.host_ready = ready
         h.keep = None
         return res
 

@@ -308,4 +308,52 @@ def test_id_sharding_emulated_on_one_gpu(world, tmp_path):
                                       exp['apsis_ids'])
                 assert np.array_equal(ang2[:total].cpu().numpy(),
                                       ang_o.cpu().numpy())
+
+        # key-range partitioned path: quantile proposals (all-gather emulated by
+        # concatenation), per-rank send blocks, all-to-all emulated by a block
+        # transpose, per-rank merge; the rank slices concatenated in rank order
+        # are the global lists
+        cap = max(sizes) // world + 64
+        blk = lib.oa_exchange_bytes(0, cap)
+        props, sends, cnts = [], [], []
+        for res in results:
+            prop = torch.zeros(max(world - 1, 1), dtype=torch.int64, device=dev)
+            check(lib.oa_split_quantiles(ptr(res.prev_gen.gpos), ptr(res.d_sel),
+                                         ptr(res.d_small), n_seg, world,
+                                         ptr(prop), st))
+            props.append(prop)
+        prop_all = torch.cat(props)
+        for res in results:
+            send = torch.zeros(world * blk, dtype=torch.uint8, device=dev)
+            cnt = torch.zeros(n_seg, dtype=torch.int64, device=dev)
+            bnd = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+            check(lib.oa_pack_split(
+                ptr(res.prev_gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+                ptr(res.d_ang_buf), ptr(res.d_small), n_seg, ptr(prop_all),
+                world, cap, ptr(bnd), ptr(send), ptr(cnt), st))
+            sends.append(send)
+            cnts.append(cnt)
+            assert int(bnd[-1]) == res.n_events
+        got_ids, got_ang, slice_sizes = [], [], []
+        for q in range(world):
+            recv = torch.cat([sd[q * blk:(q + 1) * blk] for sd in sends])
+            ids3 = torch.empty(world * cap, dtype=torch.int64, device=dev)
+            ang3 = torch.empty(world * cap, dtype=torch.int16, device=dev)
+            info3 = torch.empty(2, dtype=torch.int64, device=dev)
+            check(lib.oa_merge_blocks(ptr(recv), world, cap, ptr(ids3),
+                                      ptr(ang3), ptr(info3), st))
+            sz, over = (int(v) for v in info3.cpu().tolist())
+            assert over == 0
+            slice_sizes.append(sz)
+            got_ids.append(ids3[:sz])
+            got_ang.append(ang3[:sz])
+        assert sum(slice_sizes) == total
+        # the key ranges are balanced (local quantiles are global quantiles)
+        assert max(slice_sizes) <= 1.5 * total / world + 64
+        assert np.array_equal(torch.cat(got_ids).cpu().numpy(), exp['apsis_ids'])
+        assert np.array_equal(torch.cat(got_ang).cpu().numpy(),
+                              ang_o.cpu().numpy())
+        assert np.array_equal(
+            np.concatenate(([0], np.cumsum(sum(c.cpu().numpy() for c in cnts)))),
+            exp['apsis_offsets'])
     assert n_events > 0

@@ -32,7 +32,7 @@ for t in range(K):
         res = trk.collect(pend)
         t3 = time.perf_counter()
         if res.apsis_offsets is not None:
-            h = comm.start_merge(trk, res, to_host=(rank == 0))
+            h = comm.start_merge(trk, res, to_host='slice')
             t4 = time.perf_counter()
             if hprev is not None:
                 comm.finish_merge(hprev)
