@@ -303,7 +303,11 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        # a short collective timeout: a rank that dies must not leave the others
+        # (and the box) hanging for the default ten minutes
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+                                timeout=datetime.timedelta(seconds=120))
     K, W = args.steps, args.warmup
     n_snap = W + K + 1
 
@@ -382,6 +386,10 @@ def run_b200(args):
             sampler.start()
         from collections import deque
         depth = max(1, args.depth)     # snapshots in flight (tracker ring = 3)
+        if comm is not None:
+            # the exchange of snapshot k is finished one snapshot later and may
+            # have to be repeated from k's device buffers: keep them un-recycled
+            depth = 1
         queue = deque()
         for t in range(0, W + 1):      # same pipelined pattern as the timed loop
             queue.append(submit_step(trk, t, host))

@@ -167,7 +167,7 @@ class Comm:
         return out + (sizes,) if return_sizes else out
 
     # -- events: asynchronous exchange (NCCL path) ---------------------------------
-    HEADROOM = 1.5       # send-buffer capacity / largest event list last snapshot
+    HEADROOM = 2.0       # send-buffer capacity / largest event list last snapshot
 
     def start_merge(self, tracker, res, to_host=True):
         """Enqueue the exchange of one snapshot's events and return a handle for
@@ -187,7 +187,13 @@ class Comm:
             raise _lib.OrbitB200Error(
                 "start_merge needs OrbitTracker.events_on_device = True")
         if self.stream is None:
-            self.stream = torch.cuda.Stream(self.device)
+            # OA_EXCHANGE_STREAM=main: enqueue the exchange behind the kernels
+            # already submitted instead of beside them (no SM sharing between
+            # NCCL and the persistent tracking kernel)
+            import os
+            self.stream = torch.cuda.current_stream(self.device) \
+                if os.environ.get('OA_EXCHANGE_STREAM') == 'main' \
+                else torch.cuda.Stream(self.device)
         if self._cap is None:
             # first exchange: agree on a capacity (the only blocking collective)
             t = torch.tensor([res.n_events], dtype=torch.int64,
@@ -202,7 +208,22 @@ class Comm:
         return self._launch_split(tracker, res, self._block_cap(), to_host)
 
     def _block_cap(self):
-        return -(-self._cap // self.world // 1024 + 1) * 1024
+        """Records per (source, destination) block of the all-to-all path."""
+        per_block = -(-self._cap // self.world)             # ceil
+        return (per_block // 1024 + 1) * 1024
+
+    def _check_inputs_alive(self, h):
+        """An exchange is repeated from the tracker's ring buffers of its
+        snapshot; they are recycled RING submits later.  (Every rank takes the
+        same branch: the sizes that trigger a repeat are all-gathered.)"""
+        # buffers of snapshot k are rewritten while snapshot k + RING is being
+        # submitted, i.e. once tracker._step (snapshots submitted) > k + RING
+        if h.tracker._step - h.step0 > h.tracker.RING:
+            raise _lib.OrbitB200Error(
+                "the event exchange of a snapshot overflowed its send buffers "
+                "after the snapshot's device buffers had been recycled; call "
+                "finish_merge() no later than one snapshot after start_merge() "
+                "or raise Comm.HEADROOM")
 
     def _launch_split(self, tracker, res, cap, to_host):
         gen = res.prev_gen
@@ -211,6 +232,7 @@ class Comm:
         h = _Exchange()
         h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
         h.split = True
+        h.step0 = getattr(res, 'step', tracker._step)
         self.stream.wait_event(res.compacted)
         with torch.cuda.stream(self.stream):
             st = C.c_void_p(self.stream.cuda_stream)
@@ -257,6 +279,7 @@ class Comm:
         n_seg = len(res.apsis_offsets) - 1
         h = _Exchange()
         h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
+        h.step0 = getattr(res, 'step', tracker._step)
         self.stream.wait_event(res.compacted)
         with torch.cuda.stream(self.stream):
             st = C.c_void_p(self.stream.cuda_stream)
@@ -305,6 +328,7 @@ class Comm:
             # some rank had more events than the send buffers hold: repeat this
             # snapshot's exchange with room for the largest list (all ranks see
             # the same sizes and take the same branch)
+            self._check_inputs_alive(h)
             self._cap = self._round_cap(int(sizes.max()))
             return self.finish_merge(self._launch_merge(
                 h.tracker, h.res, self._cap, h.to_host))
@@ -338,8 +362,9 @@ class Comm:
         info = h.h_info.numpy().reshape(W, 2)
         sizes = info[:, 0]
         if info[:, 1].any():
-            # a block outgrew the send buffers: repeat with generous room
-            self._cap = self._round_cap(int(sizes.max()) * W * 2)
+            # a block outgrew the send buffers: repeat with twice the room
+            self._check_inputs_alive(h)
+            self._cap *= 2
             return self.finish_merge(self._launch_split(
                 h.tracker, h.res, self._block_cap(), h.to_host))
         self._cap = max(self._cap, self._round_cap(int(sizes.max())))

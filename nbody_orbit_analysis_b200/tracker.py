@@ -43,7 +43,7 @@ class Generation:
 class StepResult:
     """Results of one snapshot.  ``host_ready`` (multi-GPU merge only) is the
     event after which ``apsis_ids`` / ``apsis_angles`` are valid on the host."""
-    __slots__ = ('host_ready', 'host_slice', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
+    __slots__ = ('host_ready', 'host_slice', 'step', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
                  'apsis_prev_index', 'prev_gen', 'd_ids', 'd_ang', 'compacted',
                  'd_sel', 'd_ids_buf', 'd_ang_buf', 'd_small')
@@ -541,6 +541,7 @@ class OrbitTracker:
     def collect(self, p, release=True):
         """Wait for a submitted snapshot and return its ``StepResult``."""
         res = StepResult()
+        res.step = p.step
         res.n = p.n
         res.diag = p.diag
         res.hinds = np.flatnonzero(p.matched)
