@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 11
+#define OA_ABI_VERSION 12
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -310,7 +310,8 @@ int oa_merge_gathered(const void* gathered, int world, int n_seg, int64_t cap,
  *                        bytes; counts[n_seg] = this rank's per-halo counts;
  *                        bnd_ws: world+1 int64;
  *   (all-to-all of the blocks, all-reduce of counts)
- *   oa_merge_blocks    : this rank's slice in key order, info = [size | overflow]. */
+ *   oa_merge_blocks    : this rank's slice in key order, info = [size | largest
+ *                        received block before truncation (> cap: repeat)]. */
 int oa_split_quantiles(const int64_t* gpos, const int64_t* sel, const int64_t* small,
                        int n_seg, int world, int64_t* q_out, void* stream);
 int oa_pack_split(const int64_t* gpos, const int64_t* sel, const int64_t* ids,

@@ -283,7 +283,8 @@ __global__ void pack_split_kernel(const int64_t* __restrict__ gpos,
 }
 
 // merge of the `world` received blocks (same layout, block r from rank r) into
-// this rank's slice; info = [slice size | overflow flag]
+// this rank's slice; info = [slice size | largest received block before
+// truncation to cap (> cap: overflow, the exchange must be repeated)]
 __global__ void merge_blocks_kernel(const unsigned char* __restrict__ recv, int world,
                                     int64_t cap, int64_t* __restrict__ ids_out,
                                     uint16_t* __restrict__ angles_out,
@@ -295,14 +296,14 @@ __global__ void merge_blocks_kernel(const unsigned char* __restrict__ recv, int 
     const int64_t size = true_size < cap ? true_size : cap;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && r == 0) {
-        int64_t tot = 0, over = 0;
+        int64_t tot = 0, largest = 0;
         for (int q = 0; q < world; ++q) {
             const int64_t sz = reinterpret_cast<const int64_t*>(recv + (size_t)q * L.bytes)[0];
-            if (sz > cap) over = 1;
+            if (sz > largest) largest = sz;
             tot += sz < cap ? sz : cap;
         }
         info[0] = tot;
-        info[1] = over;
+        info[1] = largest;
     }
     if (i >= size) return;
     const int64_t key = reinterpret_cast<const int64_t*>(mine + L.keys)[i];

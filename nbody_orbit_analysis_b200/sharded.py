@@ -47,6 +47,28 @@ class _Exchange:
     pass
 
 
+class _HostStream:
+    """Stand-in for a CUDA stream / event when the communicator lives on the CPU
+    (gloo): the CPU tests drive the very same exchange code with host tensors
+    and numpy stand-ins for the kernels."""
+    cuda_stream = 0
+
+    def wait_event(self, event):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class Comm:
     """Collectives of one tracking step."""
 
@@ -63,6 +85,8 @@ class Comm:
         self._cat_pinned, self._cat_turn = {}, 0
         self._cap = None             # records per rank in the send buffers
         self._last_total = 0
+        self._results = 0            # finished exchanges: pinned slot of their lists
+        self._repeats = 0            # consecutive repeats after an overflow
 
     # -- catalogue ---------------------------------------------------------------
     def start_broadcast(self, pos, rad, bulk):
@@ -191,9 +215,12 @@ class Comm:
             # already submitted instead of beside them (no SM sharing between
             # NCCL and the persistent tracking kernel)
             import os
-            self.stream = torch.cuda.current_stream(self.device) \
-                if os.environ.get('OA_EXCHANGE_STREAM') == 'main' \
-                else torch.cuda.Stream(self.device)
+            if self.device.type != 'cuda':
+                self.stream = _HostStream()
+            elif os.environ.get('OA_EXCHANGE_STREAM') == 'main':
+                self.stream = torch.cuda.current_stream(self.device)
+            else:
+                self.stream = torch.cuda.Stream(self.device)
         if self._cap is None:
             # first exchange: agree on a capacity (the only blocking collective)
             t = torch.tensor([res.n_events], dtype=torch.int64,
@@ -207,10 +234,20 @@ class Comm:
         # volume per rank does not grow with the number of GPUs
         return self._launch_split(tracker, res, self._block_cap(), to_host)
 
+    def _on_stream(self):
+        return torch.cuda.stream(self.stream) if self.device.type == 'cuda' \
+            else self.stream
+
+    def _event(self):
+        return torch.cuda.Event() if self.device.type == 'cuda' \
+            else _HostStream()
+
     def _block_cap(self):
         """Records per (source, destination) block of the all-to-all path."""
         per_block = -(-self._cap // self.world)             # ceil
         return (per_block // 1024 + 1) * 1024
+
+    MAX_REPEATS = 4
 
     def _check_inputs_alive(self, h):
         """An exchange is repeated from the tracker's ring buffers of its
@@ -218,6 +255,13 @@ class Comm:
         same branch: the sizes that trigger a repeat are all-gathered.)"""
         # buffers of snapshot k are rewritten while snapshot k + RING is being
         # submitted, i.e. once tracker._step (snapshots submitted) > k + RING
+        # (consecutive repeats: a finished exchange resets the count)
+        self._repeats += 1
+        if self._repeats > self.MAX_REPEATS:
+            raise _lib.OrbitB200Error(
+                "the event exchange overflowed its send buffers %d times; the "
+                "event lists are not a uniform sample per rank (is the sharding "
+                "by particle ID?)" % self._repeats)
         if h.tracker._step - h.step0 > h.tracker.RING:
             raise _lib.OrbitB200Error(
                 "the event exchange of a snapshot overflowed its send buffers "
@@ -234,7 +278,7 @@ class Comm:
         h.split = True
         h.step0 = getattr(res, 'step', tracker._step)
         self.stream.wait_event(res.compacted)
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             st = C.c_void_p(self.stream.cuda_stream)
             i64 = dict(dtype=torch.int64, device=self.device)
             u8 = dict(dtype=torch.uint8, device=self.device)
@@ -263,12 +307,15 @@ class Comm:
             dist.all_gather_into_tensor(info_all, info)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM)
             tracker.launches += 5
-            done = torch.cuda.Event()
+            done = self._event()
             done.record(self.stream)
             tracker.wait_before_submit = done
             h.keep = (send, recv, prop, prop_all, bnd, info)
+        # small read-back into pinned buffers OWNED by the handle (torch's host
+        # allocator caches them): any number of exchanges -- repeats included --
+        # may be launched before this one is finished
         h.h_info, h.h_counts, h.ready = tracker.to_host_async(
-            info_all, counts, stream=self.stream, names=('x_info', 'x_counts'))
+            info_all, counts, stream=self.stream)
         return h
 
     def _round_cap(self, largest):
@@ -281,7 +328,7 @@ class Comm:
         h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
         h.step0 = getattr(res, 'step', tracker._step)
         self.stream.wait_event(res.compacted)
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             st = C.c_void_p(self.stream.cuda_stream)
             nbytes = lib.oa_exchange_bytes(n_seg, cap)
             send = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -302,13 +349,13 @@ class Comm:
                                         ptr(h.ids), ptr(h.ang), ptr(info), st))
             tracker.launches += 3
             # the tracker's ring buffers read above may be rewritten after this
-            done = torch.cuda.Event()
+            done = self._event()
             done.record(self.stream)
             tracker.wait_before_submit = done
             h.keep = (send, recv, info)
-        # small read-back (total, global offsets, sizes, overflow flag)
-        h.h_info, h.ready = tracker.to_host_async(
-            info, stream=self.stream, names=('x_info',))
+        # small read-back (total, global offsets, sizes, overflow flag) into a
+        # pinned buffer owned by the handle (see _launch_split)
+        h.h_info, h.ready = tracker.to_host_async(info, stream=self.stream)
         return h
 
     def finish_merge(self, h):
@@ -329,9 +376,10 @@ class Comm:
             # snapshot's exchange with room for the largest list (all ranks see
             # the same sizes and take the same branch)
             self._check_inputs_alive(h)
-            self._cap = self._round_cap(int(sizes.max()))
+            self._cap = max(self._cap, self._round_cap(int(sizes.max())))
             return self.finish_merge(self._launch_merge(
                 h.tracker, h.res, self._cap, h.to_host))
+        self._repeats = 0
         self._cap = max(self._cap, self._round_cap(int(sizes.max())))
         self._last_total = total
         res = h.res
@@ -348,9 +396,11 @@ class Comm:
                 lo = total * self.rank // self.world
                 hi = total * (self.rank + 1) // self.world
             gen = res.prev_gen
+            self._results += 1
             h_ids, h_ang, ready = h.tracker.to_host_async(
                 res.d_ids[lo:hi], res.d_ang[lo:hi], stream=self.stream,
-                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap))
+                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap),
+                step=self._results)
             res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
             res.apsis_angles = h_ang.numpy().view(np.float16)
             res.host_slice, res.host_ready = (lo, hi), ready
@@ -361,12 +411,17 @@ class Comm:
         W = self.world
         info = h.h_info.numpy().reshape(W, 2)
         sizes = info[:, 0]
-        if info[:, 1].any():
-            # a block outgrew the send buffers: repeat with twice the room
+        # info[:, 1] = largest (source, destination) block, in records, that
+        # each rank was sent; every rank reads the same all-gathered numbers
+        largest = int(info[:, 1].max())
+        if largest > h.cap:
+            # a block outgrew the send buffers: repeat with room for it (the
+            # key ranges of the repeat are the same, so once is enough)
             self._check_inputs_alive(h)
-            self._cap *= 2
+            self._cap = max(self._cap, self._round_cap(largest * W))
             return self.finish_merge(self._launch_split(
                 h.tracker, h.res, self._block_cap(), h.to_host))
+        self._repeats = 0
         self._cap = max(self._cap, self._round_cap(int(sizes.max())))
         res = h.res
         total = int(sizes.sum())
@@ -379,9 +434,11 @@ class Comm:
         res.host_slice = (lo, hi)
         if h.to_host:
             gen = res.prev_gen
+            self._results += 1
             h_ids, h_ang, ready = h.tracker.to_host_async(
                 res.d_ids, res.d_ang, stream=self.stream,
-                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap))
+                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap),
+                step=self._results)
             res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
             res.apsis_angles = h_ang.numpy().view(np.float16)
             res.host_ready = ready

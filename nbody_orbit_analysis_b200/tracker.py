@@ -216,15 +216,17 @@ class OrbitTracker:
         self.copy_stream.synchronize()
         return out
 
-    def to_host_async(self, *tensors, stream=None, names=None, reserve=0):
+    def to_host_async(self, *tensors, stream=None, names=None, reserve=0,
+                      step=None):
         """Like ``to_host`` without the synchronisation: returns the pinned
         tensors and the event that marks their completion.  With ``names`` the
-        destinations are the tracker's pinned ring buffers of those names."""
+        destinations are the tracker's pinned ring buffers of those names, slot
+        ``step`` mod HOST_RING (default: the number of submitted snapshots)."""
         done = torch.cuda.Event()
         done.record(stream if stream is not None else self._main())
         self.copy_stream.wait_event(done)
         names = names or [None] * len(tensors)
-        out = [self._to_host_async(t, name=nm, reserve=reserve)
+        out = [self._to_host_async(t, name=nm, reserve=reserve, step=step)
                for t, nm in zip(tensors, names)]
         ready = torch.cuda.Event()
         ready.record(self.copy_stream)

@@ -131,3 +131,98 @@ def test_shard_snapshot_keeps_block_structure():
             assert np.all((blk >= full[h]) & (blk < full[h + 1]))
         seen.append(gpos)
     assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(1000))
+
+
+# ---------------------------------------------------------------------------
+# asynchronous exchange (Comm.start_merge / finish_merge), host side
+# ---------------------------------------------------------------------------
+def _async_worker(rank, world, port, mode, out_dir):
+    """The bench's pipeline (exchange of snapshot k started after the submit of
+    k+1 and finished one snapshot later) with the kernels replaced by their
+    numpy restatements (tests/exchange_emul.py) and NCCL by gloo.  Event counts
+    jump by orders of magnitude between snapshots, so the send buffers overflow
+    and exchanges are repeated, also two in a row."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nbody_orbit_analysis_b200 import sharded
+        import exchange_emul as emul
+        emul.install(sharded)
+        comm = sharded.Comm(world, rank, device=torch.device('cpu'))
+        trk = emul.EmulTracker()
+        n_prev, n_halos = 120000, 7
+        counts = [0, 50, 3000, 2900, 40000, 90000, 100, 0, 39000, 95000, 5]
+        rng = np.random.default_rng(11)
+        expected, pending, finished = {}, None, []
+        caps = []
+
+        def finish(h):
+            res = comm.finish_merge(h)
+            if res.host_ready is not None:
+                res.host_ready.synchronize()
+            exp_ids, exp_ang, exp_off = expected.pop(res.step)
+            assert res.n_events == len(exp_ids), (res.step, res.n_events, len(exp_ids), comm._cap)
+            assert np.array_equal(res.apsis_offsets, exp_off)
+            lo, hi = res.host_slice if res.host_slice is not None \
+                else (0, res.n_events)
+            if mode is True:
+                assert (lo, hi) == (0, len(exp_ids))
+            assert np.array_equal(res.apsis_ids, exp_ids[lo:hi])
+            assert np.array_equal(res.apsis_angles.view(np.int16),
+                                  exp_ang[lo:hi].view(np.int16))
+            assert np.array_equal(res.d_ids.numpy(), exp_ids[lo:hi])
+            finished.append((res.step, lo, hi, res.n_events))
+            caps.append(comm._cap)
+
+        for k, m in enumerate(counts):
+            # unsharded previous snapshot: blocks of the halos, one owner per row
+            starts = np.sort(rng.choice(n_prev, n_halos - 1, replace=False))
+            starts = np.concatenate(([0], starts))
+            pid = rng.permutation(n_prev).astype(np.int64) + 10 ** 12
+            ev_pos = np.sort(rng.choice(n_prev, m, replace=False))
+            ev_ang = rng.standard_normal(n_prev).astype(np.float16)
+            expected[k] = (pid[ev_pos], ev_ang[ev_pos], np.append(
+                np.searchsorted(ev_pos, starts), m).astype(np.int64))
+            # this rank's share
+            mine = np.flatnonzero(pid % world == rank)
+            ev_local = np.flatnonzero(np.isin(mine, ev_pos))
+            res = emul.EmulResult(
+                k, mine.astype(np.int64), ev_local.astype(np.int64),
+                pid[mine][ev_local], ev_ang[mine][ev_local],
+                np.searchsorted(mine, starts))
+            trk._step = k + 2                       # snapshot k+1 submitted
+            h = comm.start_merge(trk, res, to_host=mode)
+            if pending is not None:
+                finish(pending)
+            pending = h
+        finish(pending)
+        assert [f[0] for f in finished] == list(range(len(counts)))
+        # every rank went through the same capacities ...
+        all_caps = [None] * world
+        dist.all_gather_object(all_caps, caps)
+        assert all(c == all_caps[0] for c in all_caps)
+        # ... and the slices of the ranks tile the global lists
+        all_fin = [None] * world
+        dist.all_gather_object(all_fin, finished)
+        if mode is not True:
+            for k in range(len(counts)):
+                edges = sorted((f[k][1], f[k][2]) for f in all_fin)
+                assert edges[0][0] == 0 and edges[-1][1] == counts[k]
+                assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        # capacity follows the data instead of doubling without bound
+        assert caps[-1] <= 8 * comm.HEADROOM * max(counts) / world + 8192
+        open(os.path.join(out_dir, 'ok_%d' % rank), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,mode', [(2, 'slice'), (4, 'slice'), (3, 'slice'),
+                                        (2, True), (4, True)])
+def test_async_exchange_host_logic(world, mode, tmp_path):
+    mp.spawn(_async_worker, args=(world, _free_port(), mode, str(tmp_path)),
+             nprocs=world, join=True)
+    assert all(os.path.exists(str(tmp_path / ('ok_%d' % r)))
+               for r in range(world))
