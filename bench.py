@@ -460,7 +460,27 @@ def run_b200(args):
 
     # ---- end to end: host (pinned) snapshots ---------------------------------
     e2e = None
-    if not args.no_e2e:
+    run_e2e = not args.no_e2e
+    if run_e2e:
+        # every snapshot of the run sits in pinned host memory (distinct inputs
+        # every step): make sure the node has room for all ranks' copies
+        need = n_snap * args.particles * 40 * world
+        try:
+            import psutil
+            if psutil.virtual_memory().available < 1.5 * need:
+                run_e2e = False
+                e2e_skipped = ('host memory: %d GB of pinned snapshots needed, '
+                               '%d GB available' % (
+                                   need >> 30,
+                                   psutil.virtual_memory().available >> 30))
+        except ImportError:
+            pass
+        if world > 1:       # all ranks take the same branch
+            flag = torch.tensor([int(run_e2e)], device='cuda')
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if run_e2e and not int(flag.item()):
+                run_e2e, e2e_skipped = False, 'host memory on another rank'
+    if run_e2e:
         host = []
         for t in range(n_snap):
             dev, n, offsets = snaps[t]
@@ -486,7 +506,9 @@ def run_b200(args):
         ev_per_step = e2e_run['events'] / K
         e2e = {'value': e2e_run['particles'] / (e2e_run['ms'] * 1e-3),
                'unit': 'particle-snapshots/s',
-               'h2d_bytes_per_step': int(n_per_step * 32 + args.halos * 72),
+               # ids + pos + vel (+ global block positions when sharded)
+               'h2d_bytes_per_step': int(n_per_step * (40 if world > 1 else 32)
+                                         + args.halos * 72),
                'd2h_bytes_per_step': int(ev_per_step * 10 + args.halos * 8 + 8),
                'ms_per_step': e2e_run['ms'] / K,
                'events_per_step': ev_per_step}
@@ -520,7 +542,7 @@ def run_b200(args):
 
     # ---- CPU baseline on a bounded sample + parity of that sample -------------
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args, snaps, cats, gen, torch)
 
     if rank == 0:
@@ -537,6 +559,8 @@ def run_b200(args):
         }
         if e2e is not None:
             line['e2e'] = e2e
+        elif not args.no_e2e:
+            line['e2e_skipped'] = e2e_skipped
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))

@@ -82,7 +82,7 @@ class Comm:
         self.stream = None           # CUDA stream of the exchange (NCCL path)
         self.cat_stream = None       # stream / communicator of the catalogue
         self.cat_group = None
-        self._cat_pinned, self._cat_turn = {}, 0
+        self._cat_pinned, self._cat_turn = {}, {}
         self._cap = None             # records per rank in the send buffers
         self._last_total = 0
         self._results = 0            # finished exchanges: pinned slot of their lists
@@ -104,13 +104,7 @@ class Comm:
             if self.cat_stream is None:
                 self.cat_stream = torch.cuda.Stream(self.device)
                 self.cat_group = dist.new_group(backend='nccl')
-            # a small ring of pinned staging buffers (pinning costs ~0.1 ms)
-            ring = self._cat_pinned.setdefault(n_h, [])
-            if len(ring) < 4:
-                ring.append(torch.zeros(7 * n_h, dtype=torch.float64,
-                                        pin_memory=True))
-            self._cat_turn = (self._cat_turn + 1) % 4
-            host = ring[self._cat_turn % len(ring)]
+            host = self._cat_buffer(n_h)
             buf = host.numpy()
             buf[:] = 0
         else:
@@ -134,6 +128,22 @@ class Comm:
             dist.broadcast(t, src=0)
             h.host, h.ready = t, None
         return h
+
+    CAT_RING = 4
+
+    def _cat_buffer(self, n_h, make=None):
+        """Pinned staging buffer of the next catalogue broadcast: a ring of
+        CAT_RING buffers per catalogue length, used strictly in turn (pinning
+        costs ~0.1 ms, so nothing is pinned in steady state).  A buffer comes
+        round again CAT_RING broadcasts later; at most two are ever in flight."""
+        ring = self._cat_pinned.setdefault(n_h, [])
+        turn = self._cat_turn.get(n_h, 0)
+        self._cat_turn[n_h] = turn + 1
+        if len(ring) < self.CAT_RING:
+            make = make or (lambda: torch.zeros(
+                7 * n_h, dtype=torch.float64, pin_memory=True))
+            ring.append(make())
+        return ring[turn % self.CAT_RING]
 
     def finish_broadcast(self, h):
         if h.ready is not None:

@@ -226,3 +226,17 @@ def test_async_exchange_host_logic(world, mode, tmp_path):
              nprocs=world, join=True)
     assert all(os.path.exists(str(tmp_path / ('ok_%d' % r)))
                for r in range(world))
+
+
+def test_catalogue_staging_ring_is_round_robin():
+    """A staging buffer of the catalogue broadcast comes round again only
+    CAT_RING broadcasts later (two broadcasts are in flight at a time)."""
+    sys.path.insert(0, REPO)
+    from nbody_orbit_analysis_b200 import sharded
+    comm = sharded.Comm(2, 0, device=torch.device('cpu'))
+    seq = [comm._cat_buffer(5, lambda: torch.zeros(35, dtype=torch.float64))
+           .data_ptr() for _ in range(3 * comm.CAT_RING)]
+    other = comm._cat_buffer(9, lambda: torch.zeros(63, dtype=torch.float64))
+    assert other.data_ptr() not in seq
+    for i in range(len(seq) - comm.CAT_RING + 1):
+        assert len(set(seq[i:i + comm.CAT_RING])) == comm.CAT_RING
