@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 12
+#define OA_ABI_VERSION 13
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -189,6 +189,92 @@ int oa_table_clear(uint32_t* tab, int64_t n, int64_t n_regions, void* stream);
 size_t oa_track_args_size(void);
 
 /* ---------------------------------------------------------------------------
+ * (a)+(b), second implementation: region-at-a-time PARTITIONED HASH JOIN.
+ *
+ * Same reference code as oa_track_fused (track(j), track_orbits.py:147-185:
+ * region_frame :247-290, compare_radial_velocities :293-327, calc_angles
+ * :330-351), for the float32-data / float32-frame / float64-v_r tracking mode
+ * (not on-the-fly, no per-particle diagnostic outputs).  The carried records of
+ * a region are stored partitioned by ID hash (2^bits partitions of at most
+ * ~OA_PJOIN_TARGET particles), so that the previous partition fits a
+ * shared-memory hash table and every global access is a stream; one persistent
+ * kernel runs COUNT / SCAN / SCATTER / JOIN items in ticket order with
+ * per-region dependency counters (csrc/oa_pjoin_core.cuh).
+ *
+ * Host-built plan (one row per region, plus a sentinel row with the totals):
+ *   bits_cur   = max(bits of the halo's previous block, smallest b with
+ *                cur_count <= OA_PJOIN_TARGET << b), at most OA_PJOIN_MAX_BITS;
+ *   pb_cur     = exclusive prefix over regions of (1 << bits_cur) + 1: the
+ *                region's entries in part_off_cur (partition starts + end);
+ *   tile_first = exclusive prefix of COUNT/SCATTER tiles
+ *                (bits_cur > 0 ? ceil(cur_count / OA_PJOIN_TILE) : 0);
+ *   scan_first = exclusive prefix of (bits_cur > 0);
+ *   join_first = exclusive prefix of JOIN items (bits_cur == 0: 1;
+ *                else bits_prev >= 0 ? 1 << bits_prev : 0).
+ * Regions are grouped (group_first: first region of each group + n_regions);
+ * range_start[4 * s + stage] = first ticket of stage `stage` (0 JOIN, 1
+ * SCATTER, 2 SCAN, 3 COUNT) in superstep s, which holds the items of group
+ * s - 3 / s - 2 / s - 1 / s respectively (n_ranges = 4 * (n_groups + 3),
+ * plus one end entry).
+ * ------------------------------------------------------------------------- */
+#define OA_PJOIN_THREADS 512
+#define OA_PJOIN_TILE 1024
+#define OA_PJOIN_REC_CAP 2944
+#define OA_PJOIN_TARGET 2304
+#define OA_PJOIN_MAX_BITS 12
+
+typedef struct oa_pjoin_region {
+    uint32_t pb_cur;
+    uint32_t pb_prev;     /* the halo's entries in part_off_prev               */
+    int32_t bits_cur;
+    int32_t bits_prev;    /* -1: the halo has no previous block                */
+    uint32_t tile_first;
+    uint32_t join_first;
+    uint32_t scan_first;
+    uint32_t reserved;
+} oa_pjoin_region;        /* 32 bytes */
+
+typedef struct oa_pjoin_args {
+    const float* pos;       /* (n_cur,3)                                      */
+    const float* vel;       /* (n_cur,3)                                      */
+    const int64_t* ids;     /* (n_cur,)                                       */
+    int64_t n_cur;
+    const oa_region* regions;      /* (n_regions,) centre, bulk, block ranges  */
+    const oa_pjoin_region* plan;   /* (n_regions + 1,)                         */
+    const uint32_t* group_first;   /* (n_groups + 1,)                          */
+    const uint32_t* range_start;   /* (n_ranges + 1,)                          */
+    int32_t n_regions;
+    int32_t n_groups;
+    int32_t n_ranges;
+    int32_t centre_f32;
+    int32_t bulk_f32;
+    int32_t periodic;
+    int32_t mode;           /* OA_MODE_*                                      */
+    int32_t hubble_on;
+    double box[3];
+    double hubble;
+    double one_plus_z;
+    /* previous generation */
+    const void* rec_prev;          /* (n_prev,) 32-byte records, partitioned   */
+    const uint32_t* part_off_prev; /* partition offsets written by that call   */
+    uint16_t* mark_prev;           /* (n_prev,) event marks in BLOCK order     */
+    int64_t n_prev;
+    /* current generation (written) */
+    void* rec_cur;
+    uint32_t* part_off_cur;        /* (n_part_entries,)                        */
+    uint16_t* mark_cur;            /* (n_cur,) written: "no event"             */
+    void* workspace;               /* oa_pjoin_workspace_bytes(), any content  */
+    size_t workspace_bytes;
+    int64_t n_part_entries;        /* plan[n_regions].pb_cur                   */
+    int32_t sm_reserve;
+    uint32_t total_tickets;        /* range_start[n_ranges] (host copy)        */
+} oa_pjoin_args;
+
+size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries);
+size_t oa_pjoin_args_size(void);
+int oa_pjoin_step(const oa_pjoin_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Ordered selection ("np.argwhere(cond).flatten()", track_orbits.py:315 and
  * the result assembly :199-217): positions i (ascending) of marks that satisfy
  * a predicate, plus per-segment offsets.
@@ -214,6 +300,13 @@ int oa_select_gather_events(const uint16_t* marks, int64_t n,
                             const void* workspace, const void* rec,
                             int frame_dtype, int64_t* sel_out, int64_t* ids_out,
                             uint16_t* angles_out, void* stream);
+/* Same, with the IDs taken from the previous snapshot's ID array (block order)
+ * instead of its records -- for generations whose records are not in block
+ * order (oa_pjoin_step). */
+int oa_select_gather_events_ids(const uint16_t* marks, int64_t n,
+                                const void* workspace, const int64_t* ids,
+                                int64_t* sel_out, int64_t* ids_out,
+                                uint16_t* angles_out, void* stream);
 /* Consumers of a selection.  `n_sel` is the number of selected positions; when
  * `n_dev` is not NULL it points to the exact count ON THE DEVICE (as written by
  * oa_select_count) and `n_sel` is only an upper bound used to size the launch,

@@ -1,0 +1,135 @@
+// Device build of the partitioned hash join (csrc/oa_pjoin_core.cuh): execution
+// context on a CUDA thread block, the persistent kernel and its C-ABI launcher
+// (include/orbit_b200.h: oa_pjoin_step).
+#include "oa_common.cuh"
+#include "oa_pjoin_core.cuh"
+
+namespace {
+
+struct DevCtx {
+    unsigned char* sm;
+    OA_D int tid() const { return (int)threadIdx.x; }
+    OA_D void sync() const { __syncthreads(); }
+    OA_D unsigned char* smem() const { return sm; }
+    OA_D uint32_t atomic_add(uint32_t* p, uint32_t v) const { return atomicAdd(p, v); }
+    OA_D uint32_t atomic_cas(uint32_t* p, uint32_t c, uint32_t v) const {
+        return atomicCAS(p, c, v);
+    }
+    OA_D uint32_t load_acquire(const uint32_t* p) const {
+        uint32_t v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
+    OA_D void release_add(uint32_t* p, uint32_t v) const {
+        __threadfence();
+        atomicAdd(p, v);
+    }
+    OA_D void backoff() const { __nanosleep(100); }
+    // a value another CTA of this launch may have written: L2, never L1
+    OA_D uint32_t ld_cg(const uint32_t* p) const { return __ldcg(p); }
+    OA_D pj::U4 ld_cg(const pj::U4* p) const {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+        pj::U4 r;
+        r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+        return r;
+    }
+    // read-only for this launch and touched once: streaming, no L1 allocation
+    OA_D pj::U4 ld_stream(const pj::U4* p) const {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+        pj::U4 r;
+        r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+        return r;
+    }
+};
+
+__global__ void __launch_bounds__(pj::THREADS, 2)
+oa_pjoin_kernel(const __grid_constant__ oa_pjoin_args a, const __grid_constant__ pj::Const k,
+                const __grid_constant__ pj::Work w) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    DevCtx cx;
+    cx.sm = smem;
+    pj::run(cx, a, k, w);
+}
+
+size_t work_words(int n_regions, int64_t n_part_entries) {
+    return 4 + 3 * (size_t)n_regions + (size_t)n_part_entries;
+}
+
+}  // namespace
+
+extern "C" size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries) {
+    return 4 * work_words(n_regions, n_part_entries);
+}
+
+extern "C" size_t oa_pjoin_args_size(void) { return sizeof(oa_pjoin_args); }
+
+extern "C" int oa_pjoin_step(const oa_pjoin_args* args, void* stream) {
+    OA_REQUIRE(args != nullptr, "oa_pjoin_step: args is NULL");
+    const oa_pjoin_args& a = *args;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(a.n_cur >= 0 && a.n_regions >= 0 && a.n_groups >= 0, "oa_pjoin_step: negative size");
+    OA_REQUIRE(a.n_cur < ((int64_t)1 << 32) && a.n_prev < ((int64_t)1 << 32),
+               "oa_pjoin_step: more than 2^32-1 region-particles on one GPU");
+    OA_REQUIRE(a.mode == OA_MODE_PERICENTRIC || a.mode == OA_MODE_APOCENTRIC,
+               "oa_pjoin_step: bad mode %d", a.mode);
+    if (a.n_regions == 0) return OA_OK;
+    OA_REQUIRE(a.regions && a.plan && a.group_first && a.range_start && a.rec_cur &&
+               a.part_off_cur && a.mark_cur && a.workspace,
+               "oa_pjoin_step: NULL required pointer");
+    OA_REQUIRE(a.n_cur == 0 || (a.pos && a.vel && a.ids), "oa_pjoin_step: NULL input array");
+    OA_REQUIRE(a.n_ranges == 4 * (a.n_groups + 3), "oa_pjoin_step: n_ranges != 4 (n_groups + 3)");
+    OA_REQUIRE(a.n_prev == 0 || !a.rec_prev || (a.part_off_prev && a.mark_prev),
+               "oa_pjoin_step: previous generation incomplete");
+    OA_REQUIRE(a.workspace_bytes >= oa_pjoin_workspace_bytes(a.n_regions, a.n_part_entries),
+               "oa_pjoin_step: workspace too small (need oa_pjoin_workspace_bytes)");
+    OA_REQUIRE((reinterpret_cast<uintptr_t>(a.rec_cur) & 31u) == 0 &&
+               (reinterpret_cast<uintptr_t>(a.rec_prev) & 31u) == 0,
+               "oa_pjoin_step: records must be 32-byte aligned");
+
+    static bool configured = false;
+    if (!configured) {
+        OA_CUDA_CHECK(cudaFuncSetAttribute(oa_pjoin_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           pj::SM_BYTES));
+        configured = true;
+    }
+    int dev = 0, sms = OA_NUM_SMS, per_sm = 0;
+    OA_CUDA_CHECK(cudaGetDevice(&dev));
+    OA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // every CTA of the grid must be resident: items wait for items with smaller
+    // tickets, which only resident CTAs can hold
+    OA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oa_pjoin_kernel,
+                                                                pj::THREADS, pj::SM_BYTES));
+    OA_REQUIRE(per_sm >= 1, "oa_pjoin_step: the kernel does not fit an SM");
+    if (a.sm_reserve > 0 && a.sm_reserve < sms) sms -= a.sm_reserve;
+
+    // (the ticket ranges live on the device; the host that built them passes
+    // their total, a read-back would cost a synchronisation)
+    const uint32_t total = a.total_tickets;
+    if (total == 0) return OA_OK;
+
+    pj::Const k;
+    for (int q = 0; q < 3; ++q) {
+        const double h = a.box[q] * 0.5;           // largest float <= L/2
+        float hf = (float)h;
+        if ((double)hf > h) hf = nextafterf(hf, -INFINITY);
+        k.half_box[q] = hf;
+    }
+    k.total_tickets = total;
+
+    uint32_t* ws = static_cast<uint32_t*>(a.workspace);
+    OA_CUDA_CHECK(cudaMemsetAsync(ws, 0, oa_pjoin_workspace_bytes(a.n_regions, a.n_part_entries),
+                                  st));
+    pj::Work w;
+    w.ticket = ws;
+    w.done_count = ws + 4;
+    w.done_scan = w.done_count + a.n_regions;
+    w.done_scatter = w.done_scan + a.n_regions;
+    w.cursor = w.done_scatter + a.n_regions;
+
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > (int64_t)total) grid = total;
+    oa_pjoin_kernel<<<(unsigned)grid, pj::THREADS, pj::SM_BYTES, st>>>(a, k, w);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}

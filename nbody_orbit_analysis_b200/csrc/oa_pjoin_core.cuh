@@ -1,0 +1,535 @@
+// Region-at-a-time partitioned hash join -- second implementation of the fused
+// tracking step (reference: track(j) = region_frame + compare_radial_velocities +
+// calc_angles, track_orbits.py:147-185, 247-351).  See DESIGN.md section 4.3.
+//
+// Why: oa_track_kernel does four random global accesses per particle and is
+// bound by the SM's L1TEX (one wavefront per lane per divergent access,
+// profiles/r01_ablation.md), not by HBM.  Here the carried records of a region
+// are kept PARTITIONED by ID hash into pieces that fit shared memory, so the
+// match of a particle against the previous snapshot is a shared-memory probe and
+// every global access is a stream:
+//
+//   COUNT   tile of 1024 IDs of region j  -> histogram over the 2^b partitions
+//   SCAN    region j                       -> partition offsets / cursors
+//   SCATTER tile of region j: halo frame of every particle, new 32 B record
+//           written to its partition (one full sector per particle)
+//   JOIN    previous partition q of region j -> shared-memory hash table; the
+//           records of the current partitions q*f .. (q+1)*f-1 stream through
+//           it: sign test, arccos, float16 accumulator, event mark.
+//
+// One persistent kernel runs all four stages: CTAs take tickets in order, the
+// ticket order interleaves the stages of neighbouring groups of regions
+// (JOIN of group g-3, SCATTER g-2, SCAN g-1, COUNT g), and per-region counters
+// carry the dependencies.  A region's new records are therefore re-read by its
+// JOIN while they are still in B200's 126 MB L2: HBM sees the inputs once
+// (32 B), the previous records once (32 B) and the new records once (32 B).
+//
+// This header is compiled twice: by nvcc into liborbit_b200.so (device code,
+// IEEE intrinsics), and by g++ with -DPJ_HOST_EMUL into the test-only
+// tests/pjoin_emul library, where a CTA is 512 real threads and a barrier --
+// the CPU tests run the very same stage code against the oracle.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/orbit_b200.h"
+
+#ifdef PJ_HOST_EMUL
+#define PJ_FN inline
+#else
+#include <cuda_fp16.h>
+#define PJ_FN __device__ __forceinline__
+#endif
+
+namespace pj {
+
+constexpr int THREADS = OA_PJOIN_THREADS;
+constexpr int TILE = OA_PJOIN_TILE;          // particles per COUNT / SCATTER item
+constexpr int REC_CAP = OA_PJOIN_REC_CAP;    // previous records per table build
+constexpr int SLOTS = 4096;                  // shared-memory hash slots (power of 2)
+constexpr int MAX_BITS = OA_PJOIN_MAX_BITS;  // at most 2^12 partitions per region
+constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr uint16_t NO_EVENT = 0x8000u;       // = OA_NO_EVENT of the legacy path
+
+enum Stage { JOIN = 0, SCATTER = 1, SCAN = 2, COUNT = 3 };
+
+// carried state of one region-particle: exactly one 32-byte sector
+struct alignas(16) Rec {
+    int64_t id;
+    float rx, ry, rz;    // unit vector to the particle in the halo frame
+    float vr;            // sign-faithful float copy of the float64 v_r
+    uint32_t pos;        // position of the particle in its snapshot (block order)
+    uint16_t angle;      // float16 bits of the swept-angle accumulator
+    uint16_t flags;      // bit 0: matched by an earlier table batch of this join
+};
+static_assert(sizeof(Rec) == 32, "record must be one sector");
+
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+
+// ---- shared-memory layout (bytes) ----------------------------------------------------
+// join    : records [REC_CAP] | slots [SLOTS]
+// scatter : ids | pos | vel | records [TILE] | partition [TILE] | rank [TILE] | hist
+// count   : hist            scan : values [4096] | partials [THREADS]
+constexpr int SM_JOIN_REC = 0;
+constexpr int SM_JOIN_SLOT = SM_JOIN_REC + REC_CAP * 32;
+constexpr int SM_JOIN_END = SM_JOIN_SLOT + SLOTS * 4;
+constexpr int SM_IDS = 0;
+constexpr int SM_POS = SM_IDS + TILE * 8;
+constexpr int SM_VEL = SM_POS + TILE * 12;
+constexpr int SM_REC = SM_VEL + TILE * 12;
+constexpr int SM_PART = SM_REC + TILE * 32;
+constexpr int SM_RANK = SM_PART + TILE * 2;
+constexpr int SM_HIST = SM_RANK + TILE * 2;
+constexpr int SM_SCATTER_END = SM_HIST + (1 << MAX_BITS) * 4;
+constexpr int SM_SCAN_VAL = 0;
+constexpr int SM_SCAN_PART = SM_SCAN_VAL + (1 << MAX_BITS) * 4;
+constexpr int SM_BODY = SM_JOIN_END > SM_SCATTER_END ? SM_JOIN_END : SM_SCATTER_END;
+constexpr int SM_BCAST = SM_BODY;            // 4 words of CTA-wide broadcast
+constexpr int SM_BYTES = SM_BCAST + 16;
+static_assert(SM_REC % 16 == 0 && SM_JOIN_SLOT % 16 == 0, "alignment");
+static_assert(SM_SCAN_PART + THREADS * 4 <= SM_BODY, "scan scratch");
+static_assert((1 << MAX_BITS) <= THREADS * 8, "scan: 8 values per thread");
+static_assert(REC_CAP < 4095, "record index must fit 12 bits, 4095 is reserved");
+
+// launch constants derived on the host
+struct Const {
+    float half_box[3];        // largest float <= L/2 (float-frame wrap test)
+    uint32_t total_tickets;
+};
+
+// views into the (zeroed) workspace
+struct Work {
+    uint32_t* ticket;
+    uint32_t* done_count;     // [n_regions] COUNT tiles finished
+    uint32_t* done_scan;      // [n_regions] 1 when the offsets are final
+    uint32_t* done_scatter;   // [n_regions] SCATTER tiles finished
+    uint32_t* cursor;         // [n_part_entries] counts, then write cursors
+};
+
+// ---- IEEE arithmetic without contraction (numpy's rounding points) ---------------------
+#ifdef PJ_HOST_EMUL
+PJ_FN float fadd(float a, float b) { return a + b; }
+PJ_FN float fsub(float a, float b) { return a - b; }
+PJ_FN float fmul(float a, float b) { return a * b; }
+PJ_FN float fdiv(float a, float b) { return a / b; }
+PJ_FN float fsqrt(float a) { return sqrtf(a); }
+PJ_FN double dadd(double a, double b) { return a + b; }
+PJ_FN double dsub(double a, double b) { return a - b; }
+PJ_FN double dmul(double a, double b) { return a * b; }
+PJ_FN double ddiv(double a, double b) { return a / b; }
+// float32 <-> float16 bits (GCC's _Float16 conversions round to nearest even)
+PJ_FN uint16_t half_bits(float f) {
+    const _Float16 h = (_Float16)f;
+    uint16_t b;
+    __builtin_memcpy(&b, &h, 2);
+    return b;
+}
+PJ_FN float half_value(uint16_t b) {
+    _Float16 h;
+    __builtin_memcpy(&h, &b, 2);
+    return (float)h;
+}
+#else
+PJ_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
+PJ_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
+PJ_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
+PJ_FN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+PJ_FN float fsqrt(float a) { return __fsqrt_rn(a); }
+PJ_FN double dadd(double a, double b) { return __dadd_rn(a, b); }
+PJ_FN double dsub(double a, double b) { return __dsub_rn(a, b); }
+PJ_FN double dmul(double a, double b) { return __dmul_rn(a, b); }
+PJ_FN double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+PJ_FN uint16_t half_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+PJ_FN float half_value(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+#endif
+
+// numpy einsum('...i,...i') over 3 terms: float32 (p0+p1)+p2, float64 (p0+p2)+p1
+PJ_FN float dot3f(const float* a, const float* b) {
+    return fadd(fadd(fmul(a[0], b[0]), fmul(a[1], b[1])), fmul(a[2], b[2]));
+}
+PJ_FN double dot3d(const double* a, const double* b) {
+    return dadd(dadd(dmul(a[0], b[0]), dmul(a[2], b[2])), dmul(a[1], b[1]));
+}
+// float copy of v_r whose `< 0` / `> 0` tests agree with the float64 value
+PJ_FN float sign_faithful(double v) {
+    float f = (float)v;
+    if (f == 0.0f && v != 0.0) f = (v > 0.0) ? 1.401298464e-45f : -1.401298464e-45f;
+    return f;
+}
+
+PJ_FN uint64_t mix64(uint64_t x) {             // = oa_mix64
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+// partition of an ID among the 2^bits partitions of its region: top hash bits, so
+// that doubling the partition count splits every partition in two
+PJ_FN uint32_t part_of(uint64_t hash, int bits) {
+    return bits > 0 ? (uint32_t)(hash >> 32) >> (32 - bits) : 0u;
+}
+
+// ---- halo frame of one particle (region_frame, track_orbits.py:247-290) ------------------
+// float32 data, float32 frame, float64 v_r (numpy >= 2 promotion);
+// same rounding points as stage_frame<float, float, double> in oa_track.cu
+PJ_FN void frame(const oa_pjoin_args& a, const Const& k, const oa_region& R, const float* x,
+                 const float* v, float* rh, double* vr) {
+    float d[3];
+    for (int q = 0; q < 3; ++q) {
+        if (!a.centre_f32) {
+            double dd = dsub((double)x[q], R.centre[q]);
+            if (a.periodic) {
+                const double Lq = a.box[q], h = Lq * 0.5;
+                if (dd > h) dd = dsub(dd, Lq);
+                if (dd < -h) dd = dadd(dd, Lq);
+            }
+            d[q] = (float)dd;
+        } else {
+            d[q] = fsub(x[q], R.centre_f[q]);
+        }
+    }
+    if (a.centre_f32 && a.periodic) {
+        for (int q = 0; q < 3; ++q) {
+            float df = d[q];
+            const float hf = k.half_box[q];
+            if (df > hf) df = (float)dsub((double)df, a.box[q]);
+            if (df < -hf) df = (float)dadd((double)df, a.box[q]);
+            d[q] = df;
+        }
+    }
+    const float r = fsqrt(dot3f(d, d));
+    for (int q = 0; q < 3; ++q) rh[q] = fdiv(d[q], r);
+    double w[3], rd[3];
+    for (int q = 0; q < 3; ++q) {
+        double wk;
+        if (!a.bulk_f32) wk = dsub((double)v[q], R.bulk[q]);
+        else wk = (double)fsub(v[q], R.bulk_f[q]);
+        if (a.hubble_on) wk = dadd(wk, ddiv(dmul(a.hubble, (double)d[q]), a.one_plus_z));
+        w[q] = wk;
+        rd[q] = (double)rh[q];
+    }
+    *vr = dot3d(w, rd);
+}
+
+// ---- CTA-wide helpers --------------------------------------------------------------------------
+// CX (execution context) provides: tid(), sync(), smem(), atomic_add / atomic_cas
+// on uint32 (shared or global), load_acquire / release_add (gpu scope), backoff(),
+// ld_cg (a global value another CTA of this launch may have written).
+template <class CX>
+PJ_FN void wait_ge(CX& cx, const uint32_t* p, uint32_t need) {
+    if (cx.tid() == 0)
+        while (cx.load_acquire(p) < need) cx.backoff();
+    cx.sync();
+}
+template <class CX>
+PJ_FN void signal(CX& cx, uint32_t* p) {
+    cx.sync();                         // all global writes of the item are issued
+    if (cx.tid() == 0) cx.release_add(p, 1u);
+}
+
+struct Item {
+    int stage;
+    int region;
+    uint32_t idx;
+};
+
+PJ_FN uint32_t stage_prefix(const oa_pjoin_region* plan, int stage, int j) {
+    return stage == JOIN ? plan[j].join_first
+         : stage == SCAN ? plan[j].scan_first : plan[j].tile_first;
+}
+
+// ticket -> (stage, region, index).  range r = 4 * superstep + stage holds the
+// items of group (superstep - lag[stage]); zero-length ranges share their start
+// with the next one and are skipped by taking the LAST range that starts <= t.
+PJ_FN Item decode(const oa_pjoin_args& a, uint32_t t) {
+    int lo = 0, hi = a.n_ranges - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.range_start[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    Item it;
+    it.stage = lo & 3;
+    const int g = (lo >> 2) - (3 - it.stage);          // lags: JOIN 3, SCATTER 2, SCAN 1, COUNT 0
+    const uint32_t target = stage_prefix(a.plan, it.stage, (int)a.group_first[g]) +
+                            (t - a.range_start[lo]);
+    int jl = (int)a.group_first[g], jh = (int)a.group_first[g + 1] - 1;
+    while (jl < jh) {                                   // last region whose prefix <= target
+        const int mid = (jl + jh + 1) >> 1;
+        if (stage_prefix(a.plan, it.stage, mid) <= target) jl = mid; else jh = mid - 1;
+    }
+    it.region = jl;
+    it.idx = target - stage_prefix(a.plan, it.stage, jl);
+    return it;
+}
+
+PJ_FN uint32_t tiles_of(int64_t count) { return (uint32_t)((count + TILE - 1) / TILE); }
+
+// ---- COUNT ---------------------------------------------------------------------------------------
+template <class CX>
+PJ_FN void stage_count(CX& cx, const oa_pjoin_args& a, const Work& w, int j, uint32_t t) {
+    const oa_region& R = a.regions[j];
+    const oa_pjoin_region& P = a.plan[j];
+    const int bits = P.bits_cur, nP = 1 << bits;
+    const int64_t begin = R.cur_begin + (int64_t)t * TILE;
+    const int cnt = (int)(R.cur_count - (int64_t)t * TILE < TILE ? R.cur_count - (int64_t)t * TILE
+                                                                : TILE);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(cx.smem() + SM_HIST);
+    for (int p = cx.tid(); p < nP; p += THREADS) hist[p] = 0;
+    cx.sync();
+    for (int i = cx.tid(); i < cnt; i += THREADS)
+        cx.atomic_add(&hist[part_of(mix64((uint64_t)a.ids[begin + i]), bits)], 1u);
+    cx.sync();
+    for (int p = cx.tid(); p < nP; p += THREADS)
+        if (hist[p]) cx.atomic_add(&w.cursor[P.pb_cur + p], hist[p]);
+    signal(cx, &w.done_count[j]);
+}
+
+// ---- SCAN ----------------------------------------------------------------------------------------
+template <class CX>
+PJ_FN void stage_scan(CX& cx, const oa_pjoin_args& a, const Work& w, int j) {
+    const oa_region& R = a.regions[j];
+    const oa_pjoin_region& P = a.plan[j];
+    const int nP = 1 << P.bits_cur;
+    wait_ge(cx, &w.done_count[j], tiles_of(R.cur_count));
+    uint32_t* val = reinterpret_cast<uint32_t*>(cx.smem() + SM_SCAN_VAL);
+    uint32_t* part = reinterpret_cast<uint32_t*>(cx.smem() + SM_SCAN_PART);
+    const int tid = cx.tid();
+    // 8 consecutive values per thread, then a scan of the 512 partial sums
+    uint32_t own = 0;
+    for (int e = 0; e < 8; ++e) {
+        const int p = tid * 8 + e;
+        const uint32_t v = p < nP ? cx.ld_cg(&w.cursor[P.pb_cur + p]) : 0u;
+        val[p] = own;                  // exclusive within the thread
+        own += v;
+    }
+    part[tid] = own;
+    cx.sync();
+    for (int d = 1; d < THREADS; d <<= 1) {
+        const uint32_t add = tid >= d ? part[tid - d] : 0u;
+        cx.sync();
+        part[tid] += add;
+        cx.sync();
+    }
+    const uint32_t base = (uint32_t)R.cur_begin + part[tid] - own;
+    for (int e = 0; e < 8; ++e) {
+        const int p = tid * 8 + e;
+        if (p < nP) {
+            const uint32_t off = base + val[p];
+            a.part_off_cur[P.pb_cur + p] = off;
+            w.cursor[P.pb_cur + p] = off;
+        }
+    }
+    if (tid == 0) a.part_off_cur[P.pb_cur + nP] = (uint32_t)(R.cur_begin + R.cur_count);
+    signal(cx, &w.done_scan[j]);
+}
+
+// inputs of one tile -> shared memory (coalesced element loads)
+template <class CX>
+PJ_FN void load_tile(CX& cx, const oa_pjoin_args& a, int64_t begin, int cnt) {
+    int64_t* s_ids = reinterpret_cast<int64_t*>(cx.smem() + SM_IDS);
+    float* s_pos = reinterpret_cast<float*>(cx.smem() + SM_POS);
+    float* s_vel = reinterpret_cast<float*>(cx.smem() + SM_VEL);
+    for (int i = cx.tid(); i < cnt; i += THREADS) s_ids[i] = a.ids[begin + i];
+    for (int i = cx.tid(); i < 3 * cnt; i += THREADS) {
+        s_pos[i] = a.pos[3 * begin + i];
+        s_vel[i] = a.vel[3 * begin + i];
+    }
+}
+
+// new record of particle i of the staged tile (angle accumulator 0: a particle
+// without a match starts from zero, track_orbits.py:180-183, 344-346)
+template <class CX>
+PJ_FN Rec make_record(CX& cx, const oa_pjoin_args& a, const Const& k, const oa_region& R,
+                      int i, int64_t c) {
+    const int64_t* s_ids = reinterpret_cast<const int64_t*>(cx.smem() + SM_IDS);
+    const float* s_pos = reinterpret_cast<const float*>(cx.smem() + SM_POS);
+    const float* s_vel = reinterpret_cast<const float*>(cx.smem() + SM_VEL);
+    float rh[3];
+    double vr;
+    frame(a, k, R, s_pos + 3 * i, s_vel + 3 * i, rh, &vr);
+    Rec rec;
+    rec.id = s_ids[i];
+    rec.rx = rh[0]; rec.ry = rh[1]; rec.rz = rh[2];
+    rec.vr = sign_faithful(vr);
+    rec.pos = (uint32_t)c;
+    rec.angle = 0;
+    rec.flags = 0;
+    return rec;
+}
+
+PJ_FN void store_rec(Rec* dst, const Rec& r) {
+    const U4* s = reinterpret_cast<const U4*>(&r);
+    U4* d = reinterpret_cast<U4*>(dst);
+    d[0] = s[0];
+    d[1] = s[1];
+}
+
+// ---- SCATTER -------------------------------------------------------------------------------------
+template <class CX>
+PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w, int j,
+                         uint32_t t) {
+    const oa_region& R = a.regions[j];
+    const oa_pjoin_region& P = a.plan[j];
+    const int bits = P.bits_cur, nP = 1 << bits;
+    const int64_t begin = R.cur_begin + (int64_t)t * TILE;
+    const int cnt = (int)(R.cur_count - (int64_t)t * TILE < TILE ? R.cur_count - (int64_t)t * TILE
+                                                                : TILE);
+    Rec* s_rec = reinterpret_cast<Rec*>(cx.smem() + SM_REC);
+    uint16_t* s_part = reinterpret_cast<uint16_t*>(cx.smem() + SM_PART);
+    uint16_t* s_rank = reinterpret_cast<uint16_t*>(cx.smem() + SM_RANK);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(cx.smem() + SM_HIST);
+    Rec* rec_cur = static_cast<Rec*>(a.rec_cur);
+
+    load_tile(cx, a, begin, cnt);
+    for (int p = cx.tid(); p < nP; p += THREADS) hist[p] = 0;
+    cx.sync();
+    for (int i = cx.tid(); i < cnt; i += THREADS) {
+        const Rec rec = make_record(cx, a, k, R, i, begin + i);
+        const uint32_t p = part_of(mix64((uint64_t)rec.id), bits);
+        s_rec[i] = rec;
+        s_part[i] = (uint16_t)p;
+        s_rank[i] = (uint16_t)cx.atomic_add(&hist[p], 1u);
+        a.mark_cur[begin + i] = NO_EVENT;
+    }
+    cx.sync();
+    // the offsets of this region are final before any of its tiles reserves room
+    wait_ge(cx, &w.done_scan[j], 1u);
+    for (int p = cx.tid(); p < nP; p += THREADS)
+        if (hist[p]) hist[p] = cx.atomic_add(&w.cursor[P.pb_cur + p], hist[p]);
+    cx.sync();
+    for (int i = cx.tid(); i < cnt; i += THREADS)
+        store_rec(rec_cur + (hist[s_part[i]] + s_rank[i]), s_rec[i]);
+    signal(cx, &w.done_scatter[j]);
+}
+
+// ---- JOIN ----------------------------------------------------------------------------------------
+// previous records [pb, pe) against current records [cb, ce) (both of one halo,
+// the current range holds every particle whose hash falls in the previous one)
+template <class CX>
+PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe, uint32_t cb,
+                       uint32_t ce) {
+    Rec* s_rec = reinterpret_cast<Rec*>(cx.smem() + SM_JOIN_REC);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(cx.smem() + SM_JOIN_SLOT);
+    const Rec* rec_prev = static_cast<const Rec*>(a.rec_prev);
+    Rec* rec_cur = static_cast<Rec*>(a.rec_cur);
+    const bool multi = pe - pb > (uint32_t)REC_CAP;
+    const int ncur = (int)(ce - cb);
+    for (uint32_t bs = pb; bs < pe; bs += REC_CAP) {
+        const int nb = (int)(pe - bs < (uint32_t)REC_CAP ? pe - bs : (uint32_t)REC_CAP);
+        for (int s = cx.tid(); s < SLOTS; s += THREADS) slots[s] = EMPTY;
+        {   // previous records -> shared memory, 16 bytes per thread and step
+            const U4* src = reinterpret_cast<const U4*>(rec_prev + bs);
+            U4* dst = reinterpret_cast<U4*>(s_rec);
+            for (int q = cx.tid(); q < 2 * nb; q += THREADS) dst[q] = cx.ld_stream(src + q);
+        }
+        cx.sync();
+        for (int i = cx.tid(); i < nb; i += THREADS) {
+            const uint32_t h = (uint32_t)mix64((uint64_t)s_rec[i].id);
+            const uint32_t val = ((h >> 12) << 12) | (uint32_t)i;
+            uint32_t s = h & (SLOTS - 1);
+            while (cx.atomic_cas(&slots[s], EMPTY, val) != EMPTY) s = (s + 1) & (SLOTS - 1);
+        }
+        cx.sync();
+        for (int c = cx.tid(); c < ncur; c += THREADS) {
+            Rec cur;
+            {
+                const U4* src = reinterpret_cast<const U4*>(rec_cur + cb + c);
+                U4* dst = reinterpret_cast<U4*>(&cur);
+                dst[0] = cx.ld_cg(src);
+                dst[1] = cx.ld_cg(src + 1);
+            }
+            if (multi && (cur.flags & 1u)) continue;
+            const uint32_t h = (uint32_t)mix64((uint64_t)cur.id);
+            uint32_t s = h & (SLOTS - 1);
+            int hit = -1;
+            for (;;) {
+                const uint32_t v = slots[s];
+                if (v == EMPTY) break;
+                if ((v >> 12) == (h >> 12) && s_rec[v & 0xFFFu].id == cur.id) {
+                    hit = (int)(v & 0xFFFu);
+                    break;
+                }
+                s = (s + 1) & (SLOTS - 1);
+            }
+            if (hit < 0) continue;
+            const Rec prev = s_rec[hit];
+            // compare_radial_velocities + calc_angles (track_orbits.py:311-325, 330-351)
+            const float pr[3] = {prev.rx, prev.ry, prev.rz}, cr[3] = {cur.rx, cur.ry, cur.rz};
+            const float dang = acosf(dot3f(pr, cr));
+            bool ev;
+            if (a.mode == OA_MODE_PERICENTRIC) ev = (prev.vr < 0) && (cur.vr > 0);
+            else ev = (prev.vr > 0) && (cur.vr < 0);
+            float run = fadd(half_value(prev.angle), dang);
+            if (ev) {
+                a.mark_prev[prev.pos] = half_bits(run);
+                run = 0.0f;
+            }
+            // angle accumulator + "matched" flag: the last word of the record
+            reinterpret_cast<uint32_t*>(rec_cur + cb + c)[7] = (uint32_t)half_bits(run) | (1u << 16);
+        }
+        cx.sync();                     // the table is rebuilt by the next batch / item
+    }
+}
+
+template <class CX>
+PJ_FN void stage_join(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w, int j,
+                      uint32_t q) {
+    const oa_region& R = a.regions[j];
+    const oa_pjoin_region& P = a.plan[j];
+    if (P.bits_cur > 0) {
+        // partitioned region: previous partition q, current partitions q*f .. (q+1)*f - 1
+        wait_ge(cx, &w.done_scatter[j], tiles_of(R.cur_count));
+        const int db = P.bits_cur - P.bits_prev;
+        const uint32_t pb = a.part_off_prev[P.pb_prev + q], pe = a.part_off_prev[P.pb_prev + q + 1];
+        const uint32_t cb = cx.ld_cg(&a.part_off_cur[P.pb_cur + (q << db)]);
+        const uint32_t ce = cx.ld_cg(&a.part_off_cur[P.pb_cur + ((q + 1) << db)]);
+        join_ranges(cx, a, pb, pe, cb, ce);
+        return;
+    }
+    // small region (one partition = the block itself, in block order): frame and
+    // records tile by tile, then the join against the previous block
+    Rec* rec_cur = static_cast<Rec*>(a.rec_cur);
+    const uint32_t tiles = tiles_of(R.cur_count);
+    for (uint32_t t = 0; t < tiles; ++t) {
+        const int64_t begin = R.cur_begin + (int64_t)t * TILE;
+        const int cnt = (int)(R.cur_count - (int64_t)t * TILE < TILE
+                                  ? R.cur_count - (int64_t)t * TILE : TILE);
+        load_tile(cx, a, begin, cnt);
+        cx.sync();
+        for (int i = cx.tid(); i < cnt; i += THREADS) {
+            store_rec(rec_cur + begin + i, make_record(cx, a, k, R, i, begin + i));
+            a.mark_cur[begin + i] = NO_EVENT;
+        }
+        cx.sync();
+    }
+    if (cx.tid() == 0) {
+        a.part_off_cur[P.pb_cur] = (uint32_t)R.cur_begin;
+        a.part_off_cur[P.pb_cur + 1] = (uint32_t)(R.cur_begin + R.cur_count);
+    }
+    if (P.bits_prev >= 0 && R.prev_count > 0)
+        join_ranges(cx, a, (uint32_t)R.prev_begin, (uint32_t)(R.prev_begin + R.prev_count),
+                    (uint32_t)R.cur_begin, (uint32_t)(R.cur_begin + R.cur_count));
+}
+
+// ---- the persistent CTA loop --------------------------------------------------------------------
+template <class CX>
+PJ_FN void run(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w) {
+    uint32_t* bc = reinterpret_cast<uint32_t*>(cx.smem() + SM_BCAST);
+    for (;;) {
+        if (cx.tid() == 0) bc[0] = cx.atomic_add(w.ticket, 1u);
+        cx.sync();
+        const uint32_t t = bc[0];
+        cx.sync();
+        if (t >= k.total_tickets) break;
+        const Item it = decode(a, t);
+        if (it.stage == COUNT) stage_count(cx, a, w, it.region, it.idx);
+        else if (it.stage == SCAN) stage_scan(cx, a, w, it.region);
+        else if (it.stage == SCATTER) stage_scatter(cx, a, k, w, it.region, it.idx);
+        else stage_join(cx, a, k, w, it.region, it.idx);
+        cx.sync();                     // shared memory is reused by the next item
+    }
+}
+
+}  // namespace pj

@@ -109,11 +109,13 @@ sel_gather_kernel(const uint16_t* __restrict__ marks, int64_t n, int op,
 // Event variant: the selected marks ARE the float16 event angles, and the event
 // ID is in the previous record at the same position -- one kernel writes the
 // three event arrays (positions, IDs, angles).
-template <typename TF>
+// (REC: OaRec<float>, OaRec<double>, or IdOnly = the snapshot's plain ID array)
+struct IdOnly { int64_t id; };
+template <typename REC>
 __global__ void __launch_bounds__(SEL_THREADS)
 sel_gather_events_kernel(const uint16_t* __restrict__ marks, int64_t n,
                          const int64_t* __restrict__ tile_offsets,
-                         const OaRec<TF>* __restrict__ rec, int64_t* __restrict__ sel_out,
+                         const REC* __restrict__ rec, int64_t* __restrict__ sel_out,
                          int64_t* __restrict__ ids_out, uint16_t* __restrict__ angles_out) {
     const int64_t tile = blockIdx.x;
     const int64_t first = tile * SEL_TILE + (int64_t)threadIdx.x * SEL_ITEMS;
@@ -261,11 +263,27 @@ extern "C" int oa_select_gather_events(const uint16_t* marks, int64_t n,
     const int64_t tiles = sel_tiles(n);
     const int64_t* offs = ws_offsets(const_cast<void*>(workspace));
     if (frame_dtype == OA_F64)
-        sel_gather_events_kernel<double><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
+        sel_gather_events_kernel<OaRec<double>><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
             marks, n, offs, static_cast<const OaRec<double>*>(rec), sel_out, ids_out, angles_out);
     else
-        sel_gather_events_kernel<float><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
+        sel_gather_events_kernel<OaRec<float>><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
             marks, n, offs, static_cast<const OaRec<float>*>(rec), sel_out, ids_out, angles_out);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_select_gather_events_ids(const uint16_t* marks, int64_t n,
+                                           const void* workspace, const int64_t* ids,
+                                           int64_t* sel_out, int64_t* ids_out,
+                                           uint16_t* angles_out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0) return OA_OK;
+    OA_REQUIRE(marks && workspace && ids && sel_out && ids_out && angles_out,
+               "oa_select_gather_events_ids: NULL pointer");
+    const int64_t tiles = sel_tiles(n);
+    const int64_t* offs = ws_offsets(const_cast<void*>(workspace));
+    sel_gather_events_kernel<IdOnly><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(
+        marks, n, offs, reinterpret_cast<const IdOnly*>(ids), sel_out, ids_out, angles_out);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

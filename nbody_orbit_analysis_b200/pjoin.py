@@ -1,0 +1,142 @@
+"""Host side of the partitioned hash join (``oa_pjoin_step``,
+``csrc/oa_pjoin_core.cuh``): the per-snapshot plan -- partition bits of every
+region, the layout of the partition-offset array, the work items of the four
+stages and their ticket order -- built with vectorised numpy from the block
+offsets.  Nothing here touches particle data.
+
+Reference: the plan only reorganises how ``track(j)`` (``track_orbits.py:
+147-185``) is evaluated; results are independent of it (tested against the
+oracle for several partition sizes in ``tests/test_pjoin_emul.py``).
+"""
+import ctypes as C
+
+import numpy as np
+
+THREADS = 512
+TILE = 1024            # OA_PJOIN_TILE
+REC_CAP = 2944         # OA_PJOIN_REC_CAP
+TARGET = 2304          # OA_PJOIN_TARGET: particles per partition at most (mean)
+MAX_BITS = 12          # OA_PJOIN_MAX_BITS
+LAG_PARTICLES = 1 << 19   # particles per group of regions (pipeline granularity)
+
+JOIN, SCATTER, SCAN, COUNT = 0, 1, 2, 3
+_LAG = (3, 2, 1, 0)    # superstep s holds stage `st` of group s - _LAG[st]
+
+PLAN_DTYPE = np.dtype([
+    ('pb_cur', np.uint32), ('pb_prev', np.uint32), ('bits_cur', np.int32),
+    ('bits_prev', np.int32), ('tile_first', np.uint32),
+    ('join_first', np.uint32), ('scan_first', np.uint32),
+    ('reserved', np.uint32)])
+assert PLAN_DTYPE.itemsize == 32
+
+_vp, _i64, _i32, _u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32
+
+
+class PJoinArgs(C.Structure):
+    """``oa_pjoin_args`` -- keep in sync with include/orbit_b200.h."""
+    _fields_ = [
+        ('pos', _vp), ('vel', _vp), ('ids', _vp), ('n_cur', _i64),
+        ('regions', _vp), ('plan', _vp), ('group_first', _vp),
+        ('range_start', _vp),
+        ('n_regions', _i32), ('n_groups', _i32), ('n_ranges', _i32),
+        ('centre_f32', _i32), ('bulk_f32', _i32), ('periodic', _i32),
+        ('mode', _i32), ('hubble_on', _i32),
+        ('box', C.c_double * 3), ('hubble', C.c_double),
+        ('one_plus_z', C.c_double),
+        ('rec_prev', _vp), ('part_off_prev', _vp), ('mark_prev', _vp),
+        ('n_prev', _i64),
+        ('rec_cur', _vp), ('part_off_cur', _vp), ('mark_cur', _vp),
+        ('workspace', _vp), ('workspace_bytes', C.c_size_t),
+        ('n_part_entries', _i64), ('sm_reserve', _i32),
+        ('total_tickets', _u32),
+    ]
+
+
+class Plan:
+    """Plan of one snapshot.  ``rows`` / ``group_first`` / ``range_start`` go to
+    the device; ``bits`` / ``pb`` are kept on the host for the next snapshot."""
+    __slots__ = ('rows', 'group_first', 'range_start', 'bits', 'pb',
+                 'n_entries', 'n_groups', 'n_ranges', 'total')
+
+
+def need_bits(lens, target=TARGET):
+    """Smallest b with ``len <= target << b`` (at most MAX_BITS)."""
+    thr = np.int64(target) << np.arange(MAX_BITS + 1, dtype=np.int64)
+    return np.minimum(np.searchsorted(thr, lens, side='left'),
+                      MAX_BITS).astype(np.int32)
+
+
+def make_plan(offsets, prev_bits, prev_pb, target=TARGET,
+              lag_particles=LAG_PARTICLES):
+    """``offsets``: (n_regions + 1,) block starts + n.  ``prev_bits`` /
+    ``prev_pb``: per region of THIS snapshot, the partition bits and the first
+    partition-offset entry of the same halo's previous block (bits -1: none)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n_h = len(offsets) - 1
+    lens = np.diff(offsets)
+    prev_bits = np.asarray(prev_bits, dtype=np.int32)
+    has_prev = prev_bits >= 0
+    bits = np.maximum(need_bits(lens, target), np.where(has_prev, prev_bits, 0))
+    big = bits > 0
+    entries = (np.int64(1) << bits) + 1
+    tiles = np.where(big, -(-lens // TILE), 0)
+    joins = np.where(big, np.where(has_prev,
+                                   np.int64(1) << np.maximum(prev_bits, 0), 0), 1)
+
+    p = Plan()
+    rows = np.zeros(n_h + 1, dtype=PLAN_DTYPE)
+    for name, per_region in (('pb_cur', entries), ('tile_first', tiles),
+                             ('join_first', joins), ('scan_first', big)):
+        pref = np.zeros(n_h + 1, dtype=np.int64)
+        np.cumsum(per_region, out=pref[1:])
+        assert pref[-1] < 2 ** 32
+        rows[name] = pref
+    rows['bits_cur'][:n_h] = bits
+    rows['bits_prev'][:n_h] = prev_bits
+    rows['pb_prev'][:n_h] = np.where(has_prev, prev_pb, 0)
+    p.rows = rows
+    p.bits = bits
+    p.pb = rows['pb_cur'][:n_h].astype(np.int64)
+    p.n_entries = int(rows['pb_cur'][n_h])
+
+    # groups of consecutive regions (by the position of their first particle)
+    if n_h:
+        gid = offsets[:-1] // lag_particles
+        cut = np.flatnonzero(gid[1:] != gid[:-1]) + 1
+        group_first = np.concatenate(([0], cut, [n_h]))
+    else:
+        group_first = np.zeros(1, dtype=np.int64)
+    G = len(group_first) - 1
+    p.group_first = group_first.astype(np.uint32)
+    p.n_groups = G
+
+    # items per (superstep, stage): stage st of group s - lag[st]
+    per = np.zeros((G + 3, 4), dtype=np.int64)
+    for st, name in ((JOIN, 'join_first'), (SCATTER, 'tile_first'),
+                     (SCAN, 'scan_first'), (COUNT, 'tile_first')):
+        pref = rows[name].astype(np.int64)
+        per[_LAG[st]:_LAG[st] + G, st] = np.diff(pref[group_first])
+    rs = np.zeros(4 * (G + 3) + 1, dtype=np.int64)
+    np.cumsum(per.reshape(-1), out=rs[1:])
+    assert rs[-1] < 2 ** 32
+    p.range_start = rs.astype(np.uint32)
+    p.n_ranges = 4 * (G + 3)
+    p.total = int(rs[-1])
+    return p
+
+
+def decode(plan, ticket):
+    """Python restatement of ``pj::decode`` (tests): ticket ->
+    (stage, region, index)."""
+    rs = plan.range_start.astype(np.int64)
+    r = int(np.searchsorted(rs, ticket, side='right')) - 1
+    r = min(r, plan.n_ranges - 1)
+    stage = r & 3
+    g = (r >> 2) - _LAG[stage]
+    name = {JOIN: 'join_first', SCAN: 'scan_first'}.get(stage, 'tile_first')
+    pref = plan.rows[name].astype(np.int64)
+    gf = plan.group_first.astype(np.int64)
+    target = pref[gf[g]] + (ticket - rs[r])
+    j = int(np.searchsorted(pref[gf[g]:gf[g + 1]], target, side='right')) - 1
+    j += int(gf[g])
+    return stage, j, int(target - pref[j])
