@@ -164,6 +164,14 @@ _sig('oa_synth_fill', C.c_int, C.POINTER(SynthParams), _vp, _i64, C.c_int,
 _sig('oa_synth_params_size', _sz)
 if lib.oa_synth_params_size() != C.sizeof(SynthParams):
     raise ImportError("oa_synth_params layout mismatch")
+_sig('oa_select_gather_events_ids', C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
+     _vp)
+_sig('oa_pjoin_workspace_bytes', _sz, C.c_int, _i64)
+_sig('oa_pjoin_args_size', _sz)
+_sig('oa_pjoin_step', C.c_int, _vp, _vp)
+from . import pjoin as _pjoin        # noqa: E402  (struct mirror of oa_pjoin_args)
+if lib.oa_pjoin_args_size() != C.sizeof(_pjoin.PJoinArgs):
+    raise ImportError("oa_pjoin_args layout mismatch")
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
@@ -182,6 +190,8 @@ EXPORTS = [
     'oa_vote_reduce', 'oa_angle_cut', 'oa_expand_segments', 'oa_exchange_bytes',
     'oa_pack_events', 'oa_merge_gathered', 'oa_select_gather_events',
     'oa_split_quantiles', 'oa_pack_split', 'oa_merge_blocks',
+    'oa_select_gather_events_ids', 'oa_pjoin_workspace_bytes',
+    'oa_pjoin_args_size', 'oa_pjoin_step',
 ]
 
 

@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, pjoin
 from ._lib import lib, check, ptr
 
 _F = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
@@ -37,7 +37,10 @@ class Generation:
     ``track_orbits.py:234-240``), resident in HBM."""
     __slots__ = ('n', 'rec', 'tab', 'mark', 'index_bits', 'offsets',
                  'halo_exists', 'frame_f64', 'ids_dtype', 'gpos', 'buckets',
-                 'n_buckets')
+                 'n_buckets',
+                 # partitioned-join generations (impl='pjoin'): records are
+                 # stored partitioned, events take their IDs from `ids`
+                 'pjoin', 'ids', 'part_off', 'pj_bits', 'pj_pb')
 
 
 class StepResult:
@@ -76,8 +79,19 @@ class OrbitTracker:
         v_r in the data dtype, no Hubble flow) and produce per-match outputs.
     """
 
-    def __init__(self, mode='pericentric', device=None, onthefly=False):
+    def __init__(self, mode='pericentric', device=None, onthefly=False,
+                 impl=None):
         require_cuda()
+        # 'hash' : oa_track_fused (global hash table, every option)
+        # 'pjoin': oa_pjoin_step (partitioned shared-memory join; float32 data
+        #          and catalogue, plain tracking without per-particle outputs)
+        import os
+        impl = impl or os.environ.get('OA_TRACK_IMPL', 'hash')
+        if impl not in ('hash', 'pjoin'):
+            raise ValueError("impl must be 'hash' or 'pjoin'")
+        if impl == 'pjoin' and onthefly:
+            raise ValueError("impl='pjoin' does not cover the on-the-fly path")
+        self.impl = impl
         if mode not in _lib.OA_MODE:
             raise ValueError("mode must be 'pericentric' or 'apocentric'")
         self.mode = mode
@@ -379,7 +393,6 @@ class OrbitTracker:
                 ptr(d_bulk_out), ptr(ws), ws_bytes, st))
             self.launches += 2
 
-        # ---- new generation buffers ------------------------------------------
         lens = np.diff(offsets)
         gen = Generation()
         gen.n = n
@@ -387,80 +400,93 @@ class OrbitTracker:
         gen.ids_dtype = np.dtype(ids_dtype)
         gen.offsets = offsets
         gen.halo_exists = halo_exists
-        gen.index_bits = lib.oa_index_bits(int(lens.max()) if n_h else 0)
         gen.gpos = gpos
         gen.buckets = buckets
-        rec_bytes = lib.oa_record_bytes(int(frame_f64))
-        gen.rec = self._buf('rec', max(n, 1) * rec_bytes, torch.uint8)
-        gen.tab = self._buf('tab', lib.oa_table_slots(n, n_h), torch.int32)
-        gen.n_buckets = lib.oa_table_buckets(n, n_h)
-        gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16)
-
-        fdt = torch.float64 if frame_f64 else torch.float32
-        diag = None
-        out_angle = None
-        if want_angles:
-            out_angle = self._empty(max(n, 1), torch.int16)
-        if diagnostics:
-            vr_dt = fdt if self.onthefly else torch.float64
-            diag = {'rhat': self._empty(3 * n, fdt), 'vr': self._empty(n, vr_dt),
-                    'r': self._empty(n, fdt),
-                    'match': self._empty(n, torch.int64)}
-        dangle = None
-        if self.onthefly and prev is not None:
-            dangle = self._empty(max(prev.n, 1), fdt)
-
-        a = _lib.TrackArgs()
-        a.pos, a.vel, a.ids = ptr(dev['pos']), ptr(dev['vel']), ptr(dev['ids'])
-        a.n_cur = n
-        a.cur_off, a.regions = ptr(d_off), ptr(d_rows)
-        a.n_regions = n_h
-        a.data_dtype = int(x64)
-        a.frame_dtype = int(frame_f64)
-        a.centre_f32 = int(centre_f32)
-        a.bulk_f32 = int(bulk_f32)
-        a.periodic = int(box_size is not None)
-        a.onthefly = int(self.onthefly)
-        a.mode = _lib.OA_MODE[self.mode]
-        if box_size is not None:
-            box = np.broadcast_to(
-                np.asarray(box_size, dtype=np.float64), (3,))
-            a.box[0], a.box[1], a.box[2] = float(box[0]), float(box[1]), \
-                float(box[2])
-        a.hubble = float(H)
-        a.one_plus_z = 1 + float(redshift)
-        if prev is not None:
-            a.rec_prev, a.tab_prev = ptr(prev.rec), ptr(prev.tab)
-            a.tab_prev_buckets = prev.n_buckets
-            a.n_prev = prev.n
-            a.prev_index_bits = prev.index_bits
-            a.mark_prev = ptr(prev.mark)
+        gen.pjoin = self.impl == 'pjoin'
+        gen.ids = dev['ids']
+        diag = dangle = out_angle = None
+        if gen.pjoin:
+            if frame_f64 or x64 or not centre_f32 or want_angles or diagnostics:
+                raise _lib.OrbitB200Error(
+                    "impl='pjoin' needs float32 data and region centres and "
+                    "has no per-particle outputs (checkpoint angles, "
+                    "diagnostics); use impl='hash'")
+            if prev is not None and not prev.pjoin:
+                raise _lib.OrbitB200Error("generations of two implementations")
+            self._launch_pjoin(gen, prev, dev, d_rows, rows, matched, lens,
+                               bulk_f32, box_size, H, redshift, st)
+            tile_ws = a = None
         else:
-            a.prev_index_bits = 1
-        a.cur_index_bits = gen.index_bits
-        a.rec_cur, a.tab_cur, a.mark_cur = ptr(gen.rec), ptr(gen.tab), \
-            ptr(gen.mark)
-        a.out_angle = ptr(out_angle)
-        if diag is not None:
-            a.out_rhat, a.out_vr, a.out_r = ptr(diag['rhat']), \
-                ptr(diag['vr']), ptr(diag['r'])
-            a.out_match = ptr(diag['match'])
-        a.dangle_prev = ptr(dangle)
-        a.tab_cur_buckets = gen.n_buckets
-        a.sm_reserve = self.sm_reserve
-        a.workspace_bytes = lib.oa_track_workspace_bytes(n)
-        tile_ws = self._buf('chunk_ws', a.workspace_bytes, torch.uint8)
-        a.workspace = ptr(tile_ws)
-        check(lib.oa_table_clear(ptr(gen.tab), n, n_h, st))
-        if self.timing is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), \
-                torch.cuda.Event(enable_timing=True)
-            ev0.record(self._main())
-        check(lib.oa_track_fused(C.byref(a), st))
-        if self.timing is not None:
-            ev1.record(self._main())
-            self.timing.append((ev0, ev1, n))
-        self.launches += 3
+            # ---- new generation buffers ------------------------------------------
+            gen.index_bits = lib.oa_index_bits(int(lens.max()) if n_h else 0)
+            rec_bytes = lib.oa_record_bytes(int(frame_f64))
+            gen.rec = self._buf('rec', max(n, 1) * rec_bytes, torch.uint8)
+            gen.tab = self._buf('tab', lib.oa_table_slots(n, n_h), torch.int32)
+            gen.n_buckets = lib.oa_table_buckets(n, n_h)
+            gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16)
+
+            fdt = torch.float64 if frame_f64 else torch.float32
+            if want_angles:
+                out_angle = self._empty(max(n, 1), torch.int16)
+            if diagnostics:
+                vr_dt = fdt if self.onthefly else torch.float64
+                diag = {'rhat': self._empty(3 * n, fdt), 'vr': self._empty(n, vr_dt),
+                        'r': self._empty(n, fdt),
+                        'match': self._empty(n, torch.int64)}
+            if self.onthefly and prev is not None:
+                dangle = self._empty(max(prev.n, 1), fdt)
+
+            a = _lib.TrackArgs()
+            a.pos, a.vel, a.ids = ptr(dev['pos']), ptr(dev['vel']), ptr(dev['ids'])
+            a.n_cur = n
+            a.cur_off, a.regions = ptr(d_off), ptr(d_rows)
+            a.n_regions = n_h
+            a.data_dtype = int(x64)
+            a.frame_dtype = int(frame_f64)
+            a.centre_f32 = int(centre_f32)
+            a.bulk_f32 = int(bulk_f32)
+            a.periodic = int(box_size is not None)
+            a.onthefly = int(self.onthefly)
+            a.mode = _lib.OA_MODE[self.mode]
+            if box_size is not None:
+                box = np.broadcast_to(
+                    np.asarray(box_size, dtype=np.float64), (3,))
+                a.box[0], a.box[1], a.box[2] = float(box[0]), float(box[1]), \
+                    float(box[2])
+            a.hubble = float(H)
+            a.one_plus_z = 1 + float(redshift)
+            if prev is not None:
+                a.rec_prev, a.tab_prev = ptr(prev.rec), ptr(prev.tab)
+                a.tab_prev_buckets = prev.n_buckets
+                a.n_prev = prev.n
+                a.prev_index_bits = prev.index_bits
+                a.mark_prev = ptr(prev.mark)
+            else:
+                a.prev_index_bits = 1
+            a.cur_index_bits = gen.index_bits
+            a.rec_cur, a.tab_cur, a.mark_cur = ptr(gen.rec), ptr(gen.tab), \
+                ptr(gen.mark)
+            a.out_angle = ptr(out_angle)
+            if diag is not None:
+                a.out_rhat, a.out_vr, a.out_r = ptr(diag['rhat']), \
+                    ptr(diag['vr']), ptr(diag['r'])
+                a.out_match = ptr(diag['match'])
+            a.dangle_prev = ptr(dangle)
+            a.tab_cur_buckets = gen.n_buckets
+            a.sm_reserve = self.sm_reserve
+            a.workspace_bytes = lib.oa_track_workspace_bytes(n)
+            tile_ws = self._buf('chunk_ws', a.workspace_bytes, torch.uint8)
+            a.workspace = ptr(tile_ws)
+            check(lib.oa_table_clear(ptr(gen.tab), n, n_h, st))
+            if self.timing is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), \
+                    torch.cuda.Event(enable_timing=True)
+                ev0.record(self._main())
+            check(lib.oa_track_fused(C.byref(a), st))
+            if self.timing is not None:
+                ev1.record(self._main())
+                self.timing.append((ev0, ev1, n))
+            self.launches += 3
         consumed = torch.cuda.Event()
         consumed.record(self._main())
         self._consumed[self._step % self.RING] = consumed
@@ -490,10 +516,15 @@ class OrbitTracker:
             p.sel = self._buf('sel', cap, torch.int64)
             p.d_ids = self._buf('ev_ids', cap, torch.int64)
             p.d_ang = self._buf('ev_ang', cap, torch.int16)
-            check(lib.oa_select_gather_events(
-                ptr(prev.mark), prev.n, ptr(ws), ptr(prev.rec),
-                int(prev.frame_f64), ptr(p.sel), ptr(p.d_ids), ptr(p.d_ang),
-                st))
+            if prev.pjoin:
+                check(lib.oa_select_gather_events_ids(
+                    ptr(prev.mark), prev.n, ptr(ws), ptr(prev.ids), ptr(p.sel),
+                    ptr(p.d_ids), ptr(p.d_ang), st))
+            else:
+                check(lib.oa_select_gather_events(
+                    ptr(prev.mark), prev.n, ptr(ws), ptr(prev.rec),
+                    int(prev.frame_f64), ptr(p.sel), ptr(p.d_ids), ptr(p.d_ang),
+                    st))
             check(lib.oa_segment_offsets(
                 ptr(p.sel), cap, ptr(d_total), ptr(d_seg), n_m, ptr(d_small),
                 st))
@@ -534,6 +565,73 @@ class OrbitTracker:
         self.prev = gen
         self._step += 1
         return p
+
+    def _launch_pjoin(self, gen, prev, dev, d_rows, rows, matched, lens,
+                      bulk_f32, box_size, H, redshift, st):
+        """Enqueue ``oa_pjoin_step`` for the current snapshot (see pjoin.py)."""
+        n, n_h = gen.n, len(lens)
+        prev_bits = np.full(n_h, -1, dtype=np.int32)
+        prev_pb = np.zeros(n_h, dtype=np.int64)
+        if prev is not None and matched.any():
+            k = np.searchsorted(prev.halo_exists, gen.halo_exists[matched])
+            prev_bits[matched] = prev.pj_bits[k]
+            prev_pb[matched] = prev.pj_pb[k]
+        plan = pjoin.make_plan(gen.offsets, prev_bits, prev_pb)
+        gen.pj_bits, gen.pj_pb = plan.bits, plan.pb
+        # one packed host->device copy: [plan rows | group_first | range_start]
+        nb_rows = plan.rows.nbytes
+        nb_grp = -(-plan.group_first.nbytes // 16) * 16
+        nb_rng = -(-plan.range_start.nbytes // 16) * 16
+        pack = self._hbuf('pjpack', nb_rows + nb_grp + nb_rng, torch.uint8)
+        hp = pack.numpy()
+        hp[:nb_rows] = plan.rows.view(np.uint8)
+        hp[nb_rows:nb_rows + plan.group_first.nbytes] = \
+            plan.group_first.view(np.uint8)
+        hp[nb_rows + nb_grp:nb_rows + nb_grp + plan.range_start.nbytes] = \
+            plan.range_start.view(np.uint8)
+        d_pack = self._buf('pjpack', pack.numel(), torch.uint8)
+        d_pack.copy_(pack, non_blocking=True)
+        gen.rec = self._buf('rec', max(n, 1) * 32, torch.uint8)
+        gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16)
+        gen.part_off = self._buf('poff', max(plan.n_entries, 1), torch.int32)
+        ws_bytes = lib.oa_pjoin_workspace_bytes(n_h, plan.n_entries)
+        ws = self._buf('pj_ws', ws_bytes, torch.uint8)
+
+        a = pjoin.PJoinArgs()
+        a.pos, a.vel, a.ids = ptr(dev['pos']), ptr(dev['vel']), ptr(dev['ids'])
+        a.n_cur = n
+        a.regions = ptr(d_rows)
+        a.plan = ptr(d_pack)
+        a.group_first = ptr(d_pack[nb_rows:])
+        a.range_start = ptr(d_pack[nb_rows + nb_grp:])
+        a.n_regions, a.n_groups, a.n_ranges = n_h, plan.n_groups, plan.n_ranges
+        a.centre_f32, a.bulk_f32 = 1, int(bulk_f32)
+        a.periodic = int(box_size is not None)
+        if box_size is not None:
+            box = np.broadcast_to(np.asarray(box_size, dtype=np.float64), (3,))
+            a.box[0], a.box[1], a.box[2] = float(box[0]), float(box[1]), \
+                float(box[2])
+        a.mode = _lib.OA_MODE[self.mode]
+        a.hubble_on, a.hubble = int(float(H) != 0.0), float(H)
+        a.one_plus_z = 1 + float(redshift)
+        if prev is not None:
+            a.rec_prev, a.part_off_prev = ptr(prev.rec), ptr(prev.part_off)
+            a.mark_prev, a.n_prev = ptr(prev.mark), prev.n
+        a.rec_cur, a.part_off_cur = ptr(gen.rec), ptr(gen.part_off)
+        a.mark_cur = ptr(gen.mark)
+        a.workspace, a.workspace_bytes = ptr(ws), ws_bytes
+        a.n_part_entries, a.total_tickets = plan.n_entries, plan.total
+        a.sm_reserve = self.sm_reserve
+        if self.timing is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), \
+                torch.cuda.Event(enable_timing=True)
+            ev0.record(self._main())
+        check(lib.oa_pjoin_step(C.byref(a), st))
+        if self.timing is not None:
+            ev1.record(self._main())
+            self.timing.append((ev0, ev1, n))
+        self.launches += 2          # workspace memset + the persistent kernel
+        self._pj_keep = (a, d_pack, ws)
 
     def collect_keep(self, p):
         """``collect`` that leaves the snapshot's device inputs and per-particle
@@ -598,6 +696,8 @@ class OrbitTracker:
         host float16 array in block order (resume, reference
         ``track_orbits.py:229-232``)."""
         gen = self.prev
+        if gen is not None and gen.pjoin:
+            raise _lib.OrbitB200Error("impl='pjoin' cannot resume from a checkpoint")
         angles = np.ascontiguousarray(angles, dtype=np.float16)
         if gen is None or len(angles) != gen.n:
             raise ValueError("checkpoint does not match the resumed snapshot")

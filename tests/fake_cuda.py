@@ -1,0 +1,162 @@
+"""Run the HOST code of ``OrbitTracker`` in the CPU container.
+
+Test infrastructure only.  ``install`` makes ``torch.cuda``'s streams / events
+no-ops on CPU tensors and replaces the compute entry points of the C ABI inside
+``tracker`` by stand-ins that work on host pointers:
+
+* ``oa_pjoin_step``          -> the g++ build of the very same stage code
+  (tests/pjoin_emul), so ``OrbitTracker(impl='pjoin', device='cpu')`` produces
+  real results that the tests compare with the oracle;
+* ordered selection / offsets -> numpy restatements;
+* ``oa_track_fused`` & co     -> no-ops (the hash-table kernel has no host twin:
+  that branch is only checked to run through without Python errors).
+
+Size queries (``*_workspace_bytes``, ``oa_index_bits`` ...) go to the real
+library, which answers them without a device.
+"""
+import contextlib
+import ctypes as C
+
+import numpy as np
+import torch
+
+NO_EVENT = 0x8000
+
+
+class FakeStream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class FakeEvent:
+    def __init__(self, enable_timing=False, **k):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def query(self):
+        return True
+
+    def elapsed_time(self, other):
+        return 0.0
+
+
+def _arr(p, n, ctype):
+    addr = p.value if isinstance(p, C.c_void_p) else p
+    if n <= 0 or not addr:
+        return np.zeros(0, dtype=np.dtype(ctype))
+    return np.ctypeslib.as_array((ctype * int(n)).from_address(addr))
+
+
+class FakeLib:
+    """Real library for host-only queries, stand-ins for the kernels."""
+
+    def __init__(self, real, emul):
+        self._real, self._emul = real, emul
+        self.calls = []
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    # ---- no-op kernels of the hash-table branch --------------------------------
+    def oa_table_clear(self, *a):
+        self.calls.append('oa_table_clear')
+        return 0
+
+    def oa_track_fused(self, *a):
+        self.calls.append('oa_track_fused')
+        return 0
+
+    def oa_bulk_velocity(self, *a):
+        self.calls.append('oa_bulk_velocity')
+        return 0
+
+    # ---- partitioned join: the emulated kernel --------------------------------
+    def oa_pjoin_step(self, args, stream):
+        self.calls.append('oa_pjoin_step')
+        return self._emul.pj_emul_step(args, 3)
+
+    # ---- ordered selection (numpy) ---------------------------------------------
+    def _sel(self, marks, n):
+        m = _arr(marks, n, C.c_uint16)
+        return np.flatnonzero(m != NO_EVENT), m
+
+    def oa_select_count(self, marks, n, op, value, ws, ws_bytes, total_dev, st):
+        assert op == 0 and value == NO_EVENT
+        sel, _ = self._sel(marks, n)
+        _arr(total_dev, 1, C.c_int64)[0] = len(sel)
+        return 0
+
+    def oa_select_gather_events_ids(self, marks, n, ws, ids, sel_out, ids_out,
+                                    ang_out, st):
+        sel, m = self._sel(marks, n)
+        k = len(sel)
+        _arr(sel_out, k, C.c_int64)[:] = sel
+        _arr(ids_out, k, C.c_int64)[:] = _arr(ids, n, C.c_int64)[sel]
+        _arr(ang_out, k, C.c_uint16)[:] = m[sel]
+        return 0
+
+    def oa_select_gather_events(self, marks, n, ws, rec, frame, sel_out, ids_out,
+                                ang_out, st):
+        sel, m = self._sel(marks, n)
+        k = len(sel)
+        stride = 8 if frame else 4            # record size in int64 words
+        _arr(sel_out, k, C.c_int64)[:] = sel
+        _arr(ids_out, k, C.c_int64)[:] = _arr(rec, n * stride, C.c_int64)[sel * stride]
+        _arr(ang_out, k, C.c_uint16)[:] = m[sel]
+        return 0
+
+    def oa_segment_offsets(self, sel, n_sel, n_dev, seg_begin, n_seg, out, st):
+        total = int(_arr(n_dev, 1, C.c_int64)[0]) if n_dev else int(n_sel)
+        s = _arr(sel, min(total, int(n_sel)), C.c_int64)
+        _arr(out, n_seg, C.c_int64)[:] = np.searchsorted(
+            s, _arr(seg_begin, n_seg, C.c_int64))
+        return 0
+
+
+@contextlib.contextmanager
+def install(emul):
+    """Patch torch.cuda and the tracker's library handle; restore on exit."""
+    from nbody_orbit_analysis_b200 import tracker, _lib
+    saved = {}
+    cuda = torch.cuda
+    for name, val in (('is_available', lambda: True),
+                      ('current_device', lambda: 0),
+                      ('Stream', FakeStream), ('Event', FakeEvent),
+                      ('stream', lambda s: contextlib.nullcontext()),
+                      ('current_stream', lambda *a, **k: FakeStream()),
+                      ('synchronize', lambda *a, **k: None)):
+        saved[name] = getattr(cuda, name)
+        setattr(cuda, name, val)
+    real_empty, real_zeros = torch.empty, torch.zeros
+
+    def empty(*a, **k):
+        k.pop('pin_memory', None)
+        return real_empty(*a, **k)
+
+    def zeros(*a, **k):
+        k.pop('pin_memory', None)
+        return real_zeros(*a, **k)
+    torch.empty, torch.zeros = empty, zeros
+    fake = FakeLib(_lib.lib, emul)
+    real_lib = tracker.lib
+    tracker.lib = fake
+    try:
+        yield fake
+    finally:
+        tracker.lib = real_lib
+        torch.empty, torch.zeros = real_empty, real_zeros
+        for name, val in saved.items():
+            setattr(cuda, name, val)

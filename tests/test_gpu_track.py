@@ -342,8 +342,8 @@ def test_id_sharding_emulated_on_one_gpu(world, tmp_path):
             info3 = torch.empty(2, dtype=torch.int64, device=dev)
             check(lib.oa_merge_blocks(ptr(recv), world, cap, ptr(ids3),
                                       ptr(ang3), ptr(info3), st))
-            sz, over = (int(v) for v in info3.cpu().tolist())
-            assert over == 0
+            sz, largest = (int(v) for v in info3.cpu().tolist())
+            assert 0 <= largest <= cap          # no block was truncated
             slice_sizes.append(sz)
             got_ids.append(ids3[:sz])
             got_ang.append(ang3[:sz])
