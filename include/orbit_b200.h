@@ -206,8 +206,9 @@ size_t oa_track_args_size(void);
  *                cur_count <= OA_PJOIN_TARGET << b), at most OA_PJOIN_MAX_BITS;
  *   pb_cur     = exclusive prefix over regions of (1 << bits_cur) + 1: the
  *                region's entries in part_off_cur (partition starts + end);
- *   tile_first = exclusive prefix of COUNT/SCATTER tiles
+ *   tile_first = exclusive prefix of SCATTER tiles
  *                (bits_cur > 0 ? ceil(cur_count / OA_PJOIN_TILE) : 0);
+ *   count_first = the same for COUNT tiles of OA_PJOIN_CTILE particles;
  *   scan_first = exclusive prefix of (bits_cur > 0);
  *   join_first = exclusive prefix of JOIN items (bits_cur == 0: 1;
  *                else bits_prev >= 0 ? 1 << bits_prev : 0).
@@ -215,10 +216,12 @@ size_t oa_track_args_size(void);
  * range_start[4 * s + stage] = first ticket of stage `stage` (0 JOIN, 1
  * SCATTER, 2 SCAN, 3 COUNT) in superstep s, which holds the items of group
  * s - 3 / s - 2 / s - 1 / s respectively (n_ranges = 4 * (n_groups + 3),
- * plus one end entry).
+ * plus one end entry).  A small pre-kernel expands the plan into the explicit
+ * item list (8 bytes per ticket, in the workspace) that the CTAs index by ticket.
  * ------------------------------------------------------------------------- */
 #define OA_PJOIN_THREADS 512
-#define OA_PJOIN_TILE 1024
+#define OA_PJOIN_TILE 2048     /* particles per SCATTER item                  */
+#define OA_PJOIN_CTILE 8192    /* particles per COUNT item                    */
 #define OA_PJOIN_REC_CAP 2944
 #define OA_PJOIN_TARGET 2304
 #define OA_PJOIN_MAX_BITS 12
@@ -231,7 +234,7 @@ typedef struct oa_pjoin_region {
     uint32_t tile_first;
     uint32_t join_first;
     uint32_t scan_first;
-    uint32_t reserved;
+    uint32_t count_first;
 } oa_pjoin_region;        /* 32 bytes */
 
 typedef struct oa_pjoin_args {
@@ -270,7 +273,8 @@ typedef struct oa_pjoin_args {
     uint32_t total_tickets;        /* range_start[n_ranges] (host copy)        */
 } oa_pjoin_args;
 
-size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries);
+size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries,
+                                uint32_t total_tickets);
 size_t oa_pjoin_args_size(void);
 int oa_pjoin_step(const oa_pjoin_args* args, void* stream);
 

@@ -166,7 +166,7 @@ if lib.oa_synth_params_size() != C.sizeof(SynthParams):
     raise ImportError("oa_synth_params layout mismatch")
 _sig('oa_select_gather_events_ids', C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
      _vp)
-_sig('oa_pjoin_workspace_bytes', _sz, C.c_int, _i64)
+_sig('oa_pjoin_workspace_bytes', _sz, C.c_int, _i64, C.c_uint32)
 _sig('oa_pjoin_args_size', _sz)
 _sig('oa_pjoin_step', C.c_int, _vp, _vp)
 from . import pjoin as _pjoin        # noqa: E402  (struct mirror of oa_pjoin_args)

@@ -51,14 +51,22 @@ oa_pjoin_kernel(const __grid_constant__ oa_pjoin_args a, const __grid_constant__
     pj::run(cx, a, k, w);
 }
 
+// one block per region writes the region's work items (see pj::expand_region)
+__global__ void oa_pjoin_expand_kernel(const __grid_constant__ oa_pjoin_args a,
+                                       uint64_t* __restrict__ items) {
+    pj::expand_region(a, items, (int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// workspace: [ items (8 B each) | ticket (4 words) | done x 3 per region | cursors ]
 size_t work_words(int n_regions, int64_t n_part_entries) {
     return 4 + 3 * (size_t)n_regions + (size_t)n_part_entries;
 }
 
 }  // namespace
 
-extern "C" size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries) {
-    return 4 * work_words(n_regions, n_part_entries);
+extern "C" size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries,
+                                           uint32_t total_tickets) {
+    return 8 * (size_t)total_tickets + 4 * work_words(n_regions, n_part_entries);
 }
 
 extern "C" size_t oa_pjoin_args_size(void) { return sizeof(oa_pjoin_args); }
@@ -80,7 +88,8 @@ extern "C" int oa_pjoin_step(const oa_pjoin_args* args, void* stream) {
     OA_REQUIRE(a.n_ranges == 4 * (a.n_groups + 3), "oa_pjoin_step: n_ranges != 4 (n_groups + 3)");
     OA_REQUIRE(a.n_prev == 0 || !a.rec_prev || (a.part_off_prev && a.mark_prev),
                "oa_pjoin_step: previous generation incomplete");
-    OA_REQUIRE(a.workspace_bytes >= oa_pjoin_workspace_bytes(a.n_regions, a.n_part_entries),
+    OA_REQUIRE(a.workspace_bytes >=
+                   oa_pjoin_workspace_bytes(a.n_regions, a.n_part_entries, a.total_tickets),
                "oa_pjoin_step: workspace too small (need oa_pjoin_workspace_bytes)");
     OA_REQUIRE((reinterpret_cast<uintptr_t>(a.rec_cur) & 31u) == 0 &&
                (reinterpret_cast<uintptr_t>(a.rec_prev) & 31u) == 0,
@@ -117,15 +126,19 @@ extern "C" int oa_pjoin_step(const oa_pjoin_args* args, void* stream) {
     }
     k.total_tickets = total;
 
-    uint32_t* ws = static_cast<uint32_t*>(a.workspace);
-    OA_CUDA_CHECK(cudaMemsetAsync(ws, 0, oa_pjoin_workspace_bytes(a.n_regions, a.n_part_entries),
-                                  st));
+    OA_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 7u) == 0,
+               "oa_pjoin_step: workspace must be 8-byte aligned");
     pj::Work w;
+    w.items = static_cast<uint64_t*>(a.workspace);
+    uint32_t* ws = reinterpret_cast<uint32_t*>(w.items + total);
+    OA_CUDA_CHECK(cudaMemsetAsync(ws, 0, 4 * work_words(a.n_regions, a.n_part_entries), st));
     w.ticket = ws;
     w.done_count = ws + 4;
     w.done_scan = w.done_count + a.n_regions;
     w.done_scatter = w.done_scan + a.n_regions;
     w.cursor = w.done_scatter + a.n_regions;
+    oa_pjoin_expand_kernel<<<(unsigned)a.n_regions, 128, 0, st>>>(a, w.items);
+    OA_LAUNCH_CHECK();
 
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > (int64_t)total) grid = total;

@@ -44,7 +44,8 @@
 namespace pj {
 
 constexpr int THREADS = OA_PJOIN_THREADS;
-constexpr int TILE = OA_PJOIN_TILE;          // particles per COUNT / SCATTER item
+constexpr int TILE = OA_PJOIN_TILE;          // particles per SCATTER item
+constexpr int CTILE = OA_PJOIN_CTILE;        // particles per COUNT item
 constexpr int REC_CAP = OA_PJOIN_REC_CAP;    // previous records per table build
 constexpr int SLOTS = 4096;                  // shared-memory hash slots (power of 2)
 constexpr int MAX_BITS = OA_PJOIN_MAX_BITS;  // at most 2^12 partitions per region
@@ -68,7 +69,7 @@ struct alignas(16) U4 { uint32_t x, y, z, w; };
 
 // ---- shared-memory layout (bytes) ----------------------------------------------------
 // join    : records [REC_CAP] | slots [SLOTS]
-// scatter : ids | pos | vel | records [TILE] | partition [TILE] | rank [TILE] | hist
+// scatter : ids | pos | vel | partition [TILE] | rank [TILE] | hist
 // count   : hist            scan : values [4096] | partials [THREADS]
 constexpr int SM_JOIN_REC = 0;
 constexpr int SM_JOIN_SLOT = SM_JOIN_REC + REC_CAP * 32;
@@ -76,8 +77,7 @@ constexpr int SM_JOIN_END = SM_JOIN_SLOT + SLOTS * 4;
 constexpr int SM_IDS = 0;
 constexpr int SM_POS = SM_IDS + TILE * 8;
 constexpr int SM_VEL = SM_POS + TILE * 12;
-constexpr int SM_REC = SM_VEL + TILE * 12;
-constexpr int SM_PART = SM_REC + TILE * 32;
+constexpr int SM_PART = SM_VEL + TILE * 12;
 constexpr int SM_RANK = SM_PART + TILE * 2;
 constexpr int SM_HIST = SM_RANK + TILE * 2;
 constexpr int SM_SCATTER_END = SM_HIST + (1 << MAX_BITS) * 4;
@@ -86,7 +86,7 @@ constexpr int SM_SCAN_PART = SM_SCAN_VAL + (1 << MAX_BITS) * 4;
 constexpr int SM_BODY = SM_JOIN_END > SM_SCATTER_END ? SM_JOIN_END : SM_SCATTER_END;
 constexpr int SM_BCAST = SM_BODY;            // 4 words of CTA-wide broadcast
 constexpr int SM_BYTES = SM_BCAST + 16;
-static_assert(SM_REC % 16 == 0 && SM_JOIN_SLOT % 16 == 0, "alignment");
+static_assert(SM_JOIN_SLOT % 16 == 0 && SM_HIST % 4 == 0, "alignment");
 static_assert(SM_SCAN_PART + THREADS * 4 <= SM_BODY, "scan scratch");
 static_assert((1 << MAX_BITS) <= THREADS * 8, "scan: 8 values per thread");
 static_assert(REC_CAP < 4095, "record index must fit 12 bits, 4095 is reserved");
@@ -104,6 +104,7 @@ struct Work {
     uint32_t* done_scan;      // [n_regions] 1 when the offsets are final
     uint32_t* done_scatter;   // [n_regions] SCATTER tiles finished
     uint32_t* cursor;         // [n_part_entries] counts, then write cursors
+    uint64_t* items;          // [total_tickets] work items in ticket order
 };
 
 // ---- IEEE arithmetic without contraction (numpy's rounding points) ---------------------
@@ -237,34 +238,54 @@ struct Item {
 
 PJ_FN uint32_t stage_prefix(const oa_pjoin_region* plan, int stage, int j) {
     return stage == JOIN ? plan[j].join_first
-         : stage == SCAN ? plan[j].scan_first : plan[j].tile_first;
+         : stage == SCAN ? plan[j].scan_first
+         : stage == COUNT ? plan[j].count_first : plan[j].tile_first;
 }
 
-// ticket -> (stage, region, index).  range r = 4 * superstep + stage holds the
-// items of group (superstep - lag[stage]); zero-length ranges share their start
-// with the next one and are skipped by taking the LAST range that starts <= t.
-PJ_FN Item decode(const oa_pjoin_args& a, uint32_t t) {
-    int lo = 0, hi = a.n_ranges - 1;
+PJ_FN uint32_t stage_count_of(const oa_pjoin_region* plan, int stage, int j) {
+    return stage_prefix(plan, stage, j + 1) - stage_prefix(plan, stage, j);
+}
+
+// Work items in ticket order.  Range r = 4 * superstep + stage holds the items of
+// group (superstep - lag[stage]), lags: JOIN 3, SCATTER 2, SCAN 1, COUNT 0; inside
+// a range, regions in order and a region's items in order.  item = stage << 62 |
+// region << 32 | index.  (Every dependency of an item has a smaller ticket.)
+PJ_FN uint64_t encode_item(int stage, int region, uint32_t idx) {
+    return ((uint64_t)stage << 62) | ((uint64_t)(uint32_t)region << 32) | idx;
+}
+PJ_FN Item decode_item(uint64_t v) {
+    Item it;
+    it.stage = (int)(v >> 62);
+    it.region = (int)((v >> 32) & 0x3FFFFFFFu);
+    it.idx = (uint32_t)v;
+    return it;
+}
+// first ticket of region j's items of `stage`
+PJ_FN uint32_t item_base(const oa_pjoin_args& a, int stage, int j) {
+    int lo = 0, hi = a.n_groups - 1;                    // group of region j
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (a.range_start[mid] <= t) lo = mid; else hi = mid - 1;
+        if ((int)a.group_first[mid] <= j) lo = mid; else hi = mid - 1;
     }
-    Item it;
-    it.stage = lo & 3;
-    const int g = (lo >> 2) - (3 - it.stage);          // lags: JOIN 3, SCATTER 2, SCAN 1, COUNT 0
-    const uint32_t target = stage_prefix(a.plan, it.stage, (int)a.group_first[g]) +
-                            (t - a.range_start[lo]);
-    int jl = (int)a.group_first[g], jh = (int)a.group_first[g + 1] - 1;
-    while (jl < jh) {                                   // last region whose prefix <= target
-        const int mid = (jl + jh + 1) >> 1;
-        if (stage_prefix(a.plan, it.stage, mid) <= target) jl = mid; else jh = mid - 1;
+    const int r = 4 * (lo + (3 - stage)) + stage;
+    return a.range_start[r] + stage_prefix(a.plan, stage, j) -
+           stage_prefix(a.plan, stage, (int)a.group_first[lo]);
+}
+
+// items of region j, written by `nthreads` cooperating threads
+PJ_FN void expand_region(const oa_pjoin_args& a, uint64_t* items, int j, int tid,
+                         int nthreads) {
+    for (int stage = 0; stage < 4; ++stage) {
+        const uint32_t cnt = stage_count_of(a.plan, stage, j);
+        if (cnt == 0) continue;
+        const uint32_t base = item_base(a, stage, j);
+        for (uint32_t i = (uint32_t)tid; i < cnt; i += (uint32_t)nthreads)
+            items[base + i] = encode_item(stage, j, i);
     }
-    it.region = jl;
-    it.idx = target - stage_prefix(a.plan, it.stage, jl);
-    return it;
 }
 
 PJ_FN uint32_t tiles_of(int64_t count) { return (uint32_t)((count + TILE - 1) / TILE); }
+PJ_FN uint32_t ctiles_of(int64_t count) { return (uint32_t)((count + CTILE - 1) / CTILE); }
 
 // ---- COUNT ---------------------------------------------------------------------------------------
 template <class CX>
@@ -272,9 +293,9 @@ PJ_FN void stage_count(CX& cx, const oa_pjoin_args& a, const Work& w, int j, uin
     const oa_region& R = a.regions[j];
     const oa_pjoin_region& P = a.plan[j];
     const int bits = P.bits_cur, nP = 1 << bits;
-    const int64_t begin = R.cur_begin + (int64_t)t * TILE;
-    const int cnt = (int)(R.cur_count - (int64_t)t * TILE < TILE ? R.cur_count - (int64_t)t * TILE
-                                                                : TILE);
+    const int64_t begin = R.cur_begin + (int64_t)t * CTILE;
+    const int64_t left = R.cur_count - (int64_t)t * CTILE;
+    const int cnt = (int)(left < CTILE ? left : CTILE);
     uint32_t* hist = reinterpret_cast<uint32_t*>(cx.smem() + SM_HIST);
     for (int p = cx.tid(); p < nP; p += THREADS) hist[p] = 0;
     cx.sync();
@@ -292,7 +313,7 @@ PJ_FN void stage_scan(CX& cx, const oa_pjoin_args& a, const Work& w, int j) {
     const oa_region& R = a.regions[j];
     const oa_pjoin_region& P = a.plan[j];
     const int nP = 1 << P.bits_cur;
-    wait_ge(cx, &w.done_count[j], tiles_of(R.cur_count));
+    wait_ge(cx, &w.done_count[j], ctiles_of(R.cur_count));
     uint32_t* val = reinterpret_cast<uint32_t*>(cx.smem() + SM_SCAN_VAL);
     uint32_t* part = reinterpret_cast<uint32_t*>(cx.smem() + SM_SCAN_PART);
     const int tid = cx.tid();
@@ -374,9 +395,9 @@ PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const W
     const oa_pjoin_region& P = a.plan[j];
     const int bits = P.bits_cur, nP = 1 << bits;
     const int64_t begin = R.cur_begin + (int64_t)t * TILE;
-    const int cnt = (int)(R.cur_count - (int64_t)t * TILE < TILE ? R.cur_count - (int64_t)t * TILE
-                                                                : TILE);
-    Rec* s_rec = reinterpret_cast<Rec*>(cx.smem() + SM_REC);
+    const int64_t left = R.cur_count - (int64_t)t * TILE;
+    const int cnt = (int)(left < TILE ? left : TILE);
+    const int64_t* s_ids = reinterpret_cast<const int64_t*>(cx.smem() + SM_IDS);
     uint16_t* s_part = reinterpret_cast<uint16_t*>(cx.smem() + SM_PART);
     uint16_t* s_rank = reinterpret_cast<uint16_t*>(cx.smem() + SM_RANK);
     uint32_t* hist = reinterpret_cast<uint32_t*>(cx.smem() + SM_HIST);
@@ -385,13 +406,11 @@ PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const W
     load_tile(cx, a, begin, cnt);
     for (int p = cx.tid(); p < nP; p += THREADS) hist[p] = 0;
     cx.sync();
+    // pass 1: partition and rank (inside the tile) of every particle
     for (int i = cx.tid(); i < cnt; i += THREADS) {
-        const Rec rec = make_record(cx, a, k, R, i, begin + i);
-        const uint32_t p = part_of(mix64((uint64_t)rec.id), bits);
-        s_rec[i] = rec;
+        const uint32_t p = part_of(mix64((uint64_t)s_ids[i]), bits);
         s_part[i] = (uint16_t)p;
         s_rank[i] = (uint16_t)cx.atomic_add(&hist[p], 1u);
-        a.mark_cur[begin + i] = NO_EVENT;
     }
     cx.sync();
     // the offsets of this region are final before any of its tiles reserves room
@@ -399,8 +418,12 @@ PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const W
     for (int p = cx.tid(); p < nP; p += THREADS)
         if (hist[p]) hist[p] = cx.atomic_add(&w.cursor[P.pb_cur + p], hist[p]);
     cx.sync();
-    for (int i = cx.tid(); i < cnt; i += THREADS)
-        store_rec(rec_cur + (hist[s_part[i]] + s_rank[i]), s_rec[i]);
+    // pass 2: halo frame, record -> its place in the partition (one sector)
+    for (int i = cx.tid(); i < cnt; i += THREADS) {
+        store_rec(rec_cur + (hist[s_part[i]] + s_rank[i]),
+                  make_record(cx, a, k, R, i, begin + i));
+        a.mark_cur[begin + i] = NO_EVENT;
+    }
     signal(cx, &w.done_scatter[j]);
 }
 
@@ -523,7 +546,7 @@ PJ_FN void run(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w) {
         const uint32_t t = bc[0];
         cx.sync();
         if (t >= k.total_tickets) break;
-        const Item it = decode(a, t);
+        const Item it = decode_item(w.items[t]);
         if (it.stage == COUNT) stage_count(cx, a, w, it.region, it.idx);
         else if (it.stage == SCAN) stage_scan(cx, a, w, it.region);
         else if (it.stage == SCATTER) stage_scatter(cx, a, k, w, it.region, it.idx);

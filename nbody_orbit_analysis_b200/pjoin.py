@@ -13,7 +13,8 @@ import ctypes as C
 import numpy as np
 
 THREADS = 512
-TILE = 1024            # OA_PJOIN_TILE
+TILE = 2048            # OA_PJOIN_TILE  (particles per SCATTER item)
+CTILE = 8192           # OA_PJOIN_CTILE (particles per COUNT item)
 REC_CAP = 2944         # OA_PJOIN_REC_CAP
 TARGET = 2304          # OA_PJOIN_TARGET: particles per partition at most (mean)
 MAX_BITS = 12          # OA_PJOIN_MAX_BITS
@@ -26,7 +27,7 @@ PLAN_DTYPE = np.dtype([
     ('pb_cur', np.uint32), ('pb_prev', np.uint32), ('bits_cur', np.int32),
     ('bits_prev', np.int32), ('tile_first', np.uint32),
     ('join_first', np.uint32), ('scan_first', np.uint32),
-    ('reserved', np.uint32)])
+    ('count_first', np.uint32)])
 assert PLAN_DTYPE.itemsize == 32
 
 _vp, _i64, _i32, _u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32
@@ -80,12 +81,14 @@ def make_plan(offsets, prev_bits, prev_pb, target=TARGET,
     big = bits > 0
     entries = (np.int64(1) << bits) + 1
     tiles = np.where(big, -(-lens // TILE), 0)
+    ctiles = np.where(big, -(-lens // CTILE), 0)
     joins = np.where(big, np.where(has_prev,
                                    np.int64(1) << np.maximum(prev_bits, 0), 0), 1)
 
     p = Plan()
     rows = np.zeros(n_h + 1, dtype=PLAN_DTYPE)
     for name, per_region in (('pb_cur', entries), ('tile_first', tiles),
+                             ('count_first', ctiles),
                              ('join_first', joins), ('scan_first', big)):
         pref = np.zeros(n_h + 1, dtype=np.int64)
         np.cumsum(per_region, out=pref[1:])
@@ -113,7 +116,7 @@ def make_plan(offsets, prev_bits, prev_pb, target=TARGET,
     # items per (superstep, stage): stage st of group s - lag[st]
     per = np.zeros((G + 3, 4), dtype=np.int64)
     for st, name in ((JOIN, 'join_first'), (SCATTER, 'tile_first'),
-                     (SCAN, 'scan_first'), (COUNT, 'tile_first')):
+                     (SCAN, 'scan_first'), (COUNT, 'count_first')):
         pref = rows[name].astype(np.int64)
         per[_LAG[st]:_LAG[st] + G, st] = np.diff(pref[group_first])
     rs = np.zeros(4 * (G + 3) + 1, dtype=np.int64)
@@ -126,14 +129,15 @@ def make_plan(offsets, prev_bits, prev_pb, target=TARGET,
 
 
 def decode(plan, ticket):
-    """Python restatement of ``pj::decode`` (tests): ticket ->
-    (stage, region, index)."""
+    """ticket -> (stage, region, index): what the expand pre-kernel writes
+    into the item list (Python restatement for the tests)."""
     rs = plan.range_start.astype(np.int64)
     r = int(np.searchsorted(rs, ticket, side='right')) - 1
     r = min(r, plan.n_ranges - 1)
     stage = r & 3
     g = (r >> 2) - _LAG[stage]
-    name = {JOIN: 'join_first', SCAN: 'scan_first'}.get(stage, 'tile_first')
+    name = {JOIN: 'join_first', SCAN: 'scan_first',
+            COUNT: 'count_first'}.get(stage, 'tile_first')
     pref = plan.rows[name].astype(np.int64)
     gf = plan.group_first.astype(np.int64)
     target = pref[gf[g]] + (ticket - rs[r])

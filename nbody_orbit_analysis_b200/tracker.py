@@ -594,7 +594,7 @@ class OrbitTracker:
         gen.rec = self._buf('rec', max(n, 1) * 32, torch.uint8)
         gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16)
         gen.part_off = self._buf('poff', max(plan.n_entries, 1), torch.int32)
-        ws_bytes = lib.oa_pjoin_workspace_bytes(n_h, plan.n_entries)
+        ws_bytes = lib.oa_pjoin_workspace_bytes(n_h, plan.n_entries, plan.total)
         ws = self._buf('pj_ws', ws_bytes, torch.uint8)
 
         a = pjoin.PJoinArgs()
@@ -630,7 +630,7 @@ class OrbitTracker:
         if self.timing is not None:
             ev1.record(self._main())
             self.timing.append((ev0, ev1, n))
-        self.launches += 2          # workspace memset + the persistent kernel
+        self.launches += 3          # memset, item expansion, persistent kernel
         self._pj_keep = (a, d_pack, ws)
 
     def collect_keep(self, p):

@@ -58,7 +58,7 @@ void* thread_main(void* p) {
 
 extern "C" int pj_emul_sizes(int* threads, int* tile, int* rec_cap, int* smem_bytes) {
     *threads = pj::THREADS;
-    *tile = pj::TILE;
+    *tile = pj::TILE + (pj::CTILE << 16);
     *rec_cap = pj::REC_CAP;
     *smem_bytes = pj::SM_BYTES;
     return (int)sizeof(oa_pjoin_args);
@@ -80,14 +80,17 @@ extern "C" int pj_emul_step(const oa_pjoin_args* args, int n_ctas) {
         k.half_box[q] = hf;
     }
     k.total_tickets = a.total_tickets;
-    uint32_t* ws = static_cast<uint32_t*>(a.workspace);
-    memset(ws, 0, 4 * (4 + 3 * (size_t)a.n_regions + (size_t)a.n_part_entries));
     pj::Work w;
+    w.items = static_cast<uint64_t*>(a.workspace);
+    uint32_t* ws = reinterpret_cast<uint32_t*>(w.items + a.total_tickets);
+    memset(ws, 0, 4 * (4 + 3 * (size_t)a.n_regions + (size_t)a.n_part_entries));
     w.ticket = ws;
     w.done_count = ws + 4;
     w.done_scan = w.done_count + a.n_regions;
     w.done_scatter = w.done_scan + a.n_regions;
     w.cursor = w.done_scatter + a.n_regions;
+    for (int j = 0; j < a.n_regions; ++j)        // the expand pre-kernel
+        for (int t = 0; t < 128; ++t) pj::expand_region(a, w.items, j, t, 128);
 
     std::vector<Cta> ctas(n_ctas);
     std::vector<ThreadArg> targs((size_t)n_ctas * pj::THREADS);

@@ -60,8 +60,8 @@ def emul():
     sizes = [C.c_int() for _ in range(4)]
     assert lib.pj_emul_sizes(*[C.byref(s) for s in sizes]) == \
         C.sizeof(pjoin.PJoinArgs), 'PJoinArgs does not mirror oa_pjoin_args'
-    assert [s.value for s in sizes[:3]] == [pjoin.THREADS, pjoin.TILE,
-                                            pjoin.REC_CAP]
+    assert [s.value for s in sizes[:3]] == [
+        pjoin.THREADS, pjoin.TILE + (pjoin.CTILE << 16), pjoin.REC_CAP]
     return lib
 
 
@@ -115,7 +115,8 @@ class EmulTracker:
         g.rec = np.full(max(n, 1), 0x5A, dtype=np.uint8).repeat(32).view(REC_DTYPE)
         g.part_off = np.full(max(plan.n_entries, 1), 0xDEADBEEF, dtype=np.uint32)
         g.mark = np.full(max(n, 1), 0x1234, dtype=np.uint16)
-        ws = np.full(4 + 3 * n_h + plan.n_entries, 0x77, dtype=np.uint32)
+        ws = np.full(2 * plan.total + 4 + 3 * n_h + plan.n_entries, 0x77,
+                     dtype=np.uint32)
 
         a = pjoin.PJoinArgs()
         a.pos, a.vel, a.ids, a.n_cur = _ptr(pos), _ptr(vel), _ptr(ids), n
@@ -139,6 +140,11 @@ class EmulTracker:
         a.workspace, a.workspace_bytes = _ptr(ws), ws.nbytes
         a.n_part_entries, a.total_tickets = plan.n_entries, plan.total
         assert self.lib.pj_emul_step(C.byref(a), self.n_ctas) == 0
+        # the item list written by the expand pre-kernel is the plan's ticket order
+        items = ws[:2 * plan.total].view(np.uint64)
+        for tkt in range(0, plan.total, max(1, plan.total // 200)):
+            st_, j_, i_ = pjoin.decode(plan, tkt)
+            assert int(items[tkt]) == (st_ << 62) | (j_ << 32) | i_
 
         out = None
         if prev is not None:
@@ -240,9 +246,10 @@ def test_plan_decode_covers_every_item_once():
     bits = plan.bits
     for j in range(60):
         tiles = -(-int(lens[j]) // pjoin.TILE) if bits[j] > 0 else 0
+        ctiles = -(-int(lens[j]) // pjoin.CTILE) if bits[j] > 0 else 0
         joins = (1 << max(int(prev_bits[j]), 0) if prev_bits[j] >= 0 else 0) \
             if bits[j] > 0 else 1
-        assert all((pjoin.COUNT, j, i) in seen for i in range(tiles))
+        assert all((pjoin.COUNT, j, i) in seen for i in range(ctiles))
         assert all((pjoin.SCATTER, j, i) in seen for i in range(tiles))
         assert ((pjoin.SCAN, j, 0) in seen) == (bits[j] > 0)
         assert all((pjoin.JOIN, j, i) in seen for i in range(joins))
