@@ -520,9 +520,13 @@ def run_b200(args):
     k_ms = float(np.mean(dev_run['kern_ms']))
     k_n = float(np.mean(dev_run['kern_n']))
     achieved = k_n * B_ALG_F32 / (k_ms * 1e-3) / 1e9
+    impl = os.environ.get('OA_TRACK_IMPL', 'hash')
     roofline = {
         'kernel': 'oa_track_kernel<float,float,double> (fused frame + hash '
-                  'match + apsis + angle update + table insert)',
+                  'match + apsis + angle update + table insert)'
+                  if impl == 'hash' else
+                  'oa_pjoin_kernel (frame + partition scatter + shared-memory '
+                  'hash join + apsis + angle update)',
         'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
         'algorithmic_bytes_per_particle': B_ALG_F32,
@@ -536,7 +540,8 @@ def run_b200(args):
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:
-                roofline['traffic'] = json.load(fh).get('oa_track_kernel')
+                roofline['traffic'] = json.load(fh).get(
+                    'oa_track_kernel' if impl == 'hash' else 'oa_pjoin_kernel')
         except (OSError, ValueError):
             pass
 
@@ -555,6 +560,7 @@ def run_b200(args):
             'data': 'synthetic', 'config': workload_config(args),
             'clocks': dev_run['clocks'], 'gpu_launches': dev_run['launches'],
             'events_per_step': dev_run['events'] / K,
+            'track_impl': impl,
             'roofline': roofline,
         }
         if e2e is not None:

@@ -25,6 +25,7 @@ struct DevCtx {
         atomicAdd(p, v);
     }
     OA_D void backoff() const { __nanosleep(100); }
+    OA_D void fail() const { __trap(); }
     // a value another CTA of this launch may have written: L2, never L1
     OA_D uint32_t ld_cg(const uint32_t* p) const { return __ldcg(p); }
     OA_D pj::U4 ld_cg(const pj::U4* p) const {

@@ -217,11 +217,20 @@ PJ_FN void frame(const oa_pjoin_args& a, const Const& k, const oa_region& R, con
 // ---- CTA-wide helpers --------------------------------------------------------------------------
 // CX (execution context) provides: tid(), sync(), smem(), atomic_add / atomic_cas
 // on uint32 (shared or global), load_acquire / release_add (gpu scope), backoff(),
-// ld_cg (a global value another CTA of this launch may have written).
+// fail(), ld_cg (a global value another CTA of this launch may have written).
+// (a dependency always has a smaller ticket, i.e. a CTA that is running: the wait
+// is short.  A wait of seconds can only be a bug -- it ends the kernel with an
+// error instead of hanging the device.)
+constexpr uint32_t MAX_SPINS = 1u << 25;
 template <class CX>
 PJ_FN void wait_ge(CX& cx, const uint32_t* p, uint32_t need) {
-    if (cx.tid() == 0)
-        while (cx.load_acquire(p) < need) cx.backoff();
+    if (cx.tid() == 0) {
+        uint32_t spins = 0;
+        while (cx.load_acquire(p) < need) {
+            cx.backoff();
+            if (++spins > MAX_SPINS) cx.fail();
+        }
+    }
     cx.sync();
 }
 template <class CX>

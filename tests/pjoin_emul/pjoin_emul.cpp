@@ -36,6 +36,7 @@ struct HostCtx {
     uint32_t load_acquire(const uint32_t* p) const { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
     void release_add(uint32_t* p, uint32_t v) const { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
     void backoff() const { sched_yield(); }
+    void fail() const { abort(); }
     uint32_t ld_cg(const uint32_t* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
     pj::U4 ld_cg(const pj::U4* p) const { return *p; }
     pj::U4 ld_stream(const pj::U4* p) const { return *p; }

@@ -298,3 +298,31 @@ def test_many_ctas_and_one_cta(emul):
     sim = SynthSim(40000, 7, 4, dtype=np.float32, catalogue_dtype=np.float32)
     run_case(emul, sim, targets=[500], n_ctas=1)
     run_case(emul, sim, targets=[500], n_ctas=6, lag=1 << 10)
+
+
+def test_no_data_race_under_tsan(emul, tmp_path):
+    """The stage code under ThreadSanitizer (partitioned, growing partition
+    count, multi-batch join; 2-3 concurrent CTAs of 512 threads): no report."""
+    import sys
+    gcc = shutil.which('gcc')
+    tsan = subprocess.run([gcc, '-print-file-name=libtsan.so'],
+                          capture_output=True, text=True).stdout.strip() \
+        if gcc else ''
+    if not os.path.isabs(tsan) or not os.path.exists(tsan):
+        pytest.skip('libtsan not available')
+    lib = str(tmp_path / 'libpjoin_emul_tsan.so')
+    subprocess.run([shutil.which('g++'), '-O1', '-g', '-ffp-contract=off',
+                    '-pthread', '-shared', '-fPIC', '-std=c++17',
+                    '-DPJ_HOST_EMUL', '-fsanitize=thread', '-o', lib, SRC],
+                   check=True)
+    env = dict(os.environ, LD_PRELOAD=tsan,
+               TSAN_OPTIONS='report_signal_unsafe=0 exitcode=0 halt_on_error=0')
+    run = subprocess.run(
+        [sys.executable, os.path.join(HERE, 'pjoin_emul', 'tsan_run.py'), lib],
+        capture_output=True, text=True, env=env, timeout=1500)
+    out = run.stdout + run.stderr
+    if 'tsan-run-complete' not in out and 'ThreadSanitizer' not in out:
+        pytest.skip('the interpreter does not run under libtsan here: %s'
+                    % out[-300:])
+    assert 'WARNING: ThreadSanitizer' not in out, out[-3000:]
+    assert 'tsan-run-complete' in out, out[-3000:]
