@@ -36,9 +36,11 @@
 
 #ifdef PJ_HOST_EMUL
 #define PJ_FN inline
+#define PJ_UNROLL4
 #else
 #include <cuda_fp16.h>
 #define PJ_FN __device__ __forceinline__
+#define PJ_UNROLL4 _Pragma("unroll 4")
 #endif
 
 namespace pj {
@@ -217,7 +219,8 @@ PJ_FN void frame(const oa_pjoin_args& a, const Const& k, const oa_region& R, con
 // ---- CTA-wide helpers --------------------------------------------------------------------------
 // CX (execution context) provides: tid(), sync(), smem(), atomic_add / atomic_cas
 // on uint32 (shared or global), load_acquire / release_add (gpu scope), backoff(),
-// fail(), ld_cg (a global value another CTA of this launch may have written).
+// fail(), ld_cg / load_rec_cg (global data another CTA of this launch may have
+// written), ld_stream (read-only data touched once), store_rec.
 // (a dependency always has a smaller ticket, i.e. a CTA that is running: the wait
 // is short.  A wait of seconds can only be a bug -- it ends the kernel with an
 // error instead of hanging the device.)
@@ -308,6 +311,7 @@ PJ_FN void stage_count(CX& cx, const oa_pjoin_args& a, const Work& w, int j, uin
     uint32_t* hist = reinterpret_cast<uint32_t*>(cx.smem() + SM_HIST);
     for (int p = cx.tid(); p < nP; p += THREADS) hist[p] = 0;
     cx.sync();
+    PJ_UNROLL4
     for (int i = cx.tid(); i < cnt; i += THREADS)
         cx.atomic_add(&hist[part_of(mix64((uint64_t)a.ids[begin + i]), bits)], 1u);
     cx.sync();
@@ -361,7 +365,9 @@ PJ_FN void load_tile(CX& cx, const oa_pjoin_args& a, int64_t begin, int cnt) {
     int64_t* s_ids = reinterpret_cast<int64_t*>(cx.smem() + SM_IDS);
     float* s_pos = reinterpret_cast<float*>(cx.smem() + SM_POS);
     float* s_vel = reinterpret_cast<float*>(cx.smem() + SM_VEL);
+    PJ_UNROLL4
     for (int i = cx.tid(); i < cnt; i += THREADS) s_ids[i] = a.ids[begin + i];
+    PJ_UNROLL4
     for (int i = cx.tid(); i < 3 * cnt; i += THREADS) {
         s_pos[i] = a.pos[3 * begin + i];
         s_vel[i] = a.vel[3 * begin + i];
@@ -387,13 +393,6 @@ PJ_FN Rec make_record(CX& cx, const oa_pjoin_args& a, const Const& k, const oa_r
     rec.angle = 0;
     rec.flags = 0;
     return rec;
-}
-
-PJ_FN void store_rec(Rec* dst, const Rec& r) {
-    const U4* s = reinterpret_cast<const U4*>(&r);
-    U4* d = reinterpret_cast<U4*>(dst);
-    d[0] = s[0];
-    d[1] = s[1];
 }
 
 // ---- SCATTER -------------------------------------------------------------------------------------
@@ -429,8 +428,8 @@ PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const W
     cx.sync();
     // pass 2: halo frame, record -> its place in the partition (one sector)
     for (int i = cx.tid(); i < cnt; i += THREADS) {
-        store_rec(rec_cur + (hist[s_part[i]] + s_rank[i]),
-                  make_record(cx, a, k, R, i, begin + i));
+        cx.store_rec(rec_cur + (hist[s_part[i]] + s_rank[i]),
+                     make_record(cx, a, k, R, i, begin + i));
         a.mark_cur[begin + i] = NO_EVENT;
     }
     signal(cx, &w.done_scatter[j]);
@@ -454,6 +453,7 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
         {   // previous records -> shared memory, 16 bytes per thread and step
             const U4* src = reinterpret_cast<const U4*>(rec_prev + bs);
             U4* dst = reinterpret_cast<U4*>(s_rec);
+            PJ_UNROLL4
             for (int q = cx.tid(); q < 2 * nb; q += THREADS) dst[q] = cx.ld_stream(src + q);
         }
         cx.sync();
@@ -465,13 +465,7 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
         }
         cx.sync();
         for (int c = cx.tid(); c < ncur; c += THREADS) {
-            Rec cur;
-            {
-                const U4* src = reinterpret_cast<const U4*>(rec_cur + cb + c);
-                U4* dst = reinterpret_cast<U4*>(&cur);
-                dst[0] = cx.ld_cg(src);
-                dst[1] = cx.ld_cg(src + 1);
-            }
+            const Rec cur = cx.load_rec_cg(rec_cur + cb + c);    // one 32-byte sector
             if (multi && (cur.flags & 1u)) continue;
             const uint32_t h = (uint32_t)mix64((uint64_t)cur.id);
             uint32_t s = h & (SLOTS - 1);
@@ -531,7 +525,7 @@ PJ_FN void stage_join(CX& cx, const oa_pjoin_args& a, const Const& k, const Work
         load_tile(cx, a, begin, cnt);
         cx.sync();
         for (int i = cx.tid(); i < cnt; i += THREADS) {
-            store_rec(rec_cur + begin + i, make_record(cx, a, k, R, i, begin + i));
+            cx.store_rec(rec_cur + begin + i, make_record(cx, a, k, R, i, begin + i));
             a.mark_cur[begin + i] = NO_EVENT;
         }
         cx.sync();

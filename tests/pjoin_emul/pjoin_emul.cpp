@@ -38,8 +38,9 @@ struct HostCtx {
     void backoff() const { sched_yield(); }
     void fail() const { abort(); }
     uint32_t ld_cg(const uint32_t* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
-    pj::U4 ld_cg(const pj::U4* p) const { return *p; }
     pj::U4 ld_stream(const pj::U4* p) const { return *p; }
+    pj::Rec load_rec_cg(const pj::Rec* p) const { return *p; }
+    void store_rec(pj::Rec* p, const pj::Rec& r) const { *p = r; }
 };
 
 struct ThreadArg {
