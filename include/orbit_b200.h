@@ -273,6 +273,26 @@ typedef struct oa_pjoin_args {
     uint32_t total_tickets;        /* range_start[n_ranges] (host copy)        */
 } oa_pjoin_args;
 
+/* The plan on the HOST (all pointers are host pointers; no CUDA call): fills
+ * rows[n_regions + 1], bits_out / pb_out [n_regions] (kept by the caller for the
+ * next snapshot), group_first (capacity n_regions + 1) and range_start (capacity
+ * 4 * (n_regions + 3) + 1).  prev_bits[j] / prev_pb[j]: partition bits and first
+ * part_off entry of the same halo's previous block, bits -1 = none.  Groups are
+ * runs of regions whose first particle lies in the same window of
+ * `lag_particles` particles. */
+typedef struct oa_pjoin_plan_info {
+    int64_t n_part_entries;
+    uint32_t total_tickets;
+    int32_t n_groups;
+    int32_t n_ranges;
+    int32_t max_bits;
+} oa_pjoin_plan_info;
+int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
+                       const int32_t* prev_bits, const int64_t* prev_pb,
+                       int64_t target, int64_t lag_particles,
+                       oa_pjoin_region* rows, int32_t* bits_out, int64_t* pb_out,
+                       uint32_t* group_first, uint32_t* range_start,
+                       oa_pjoin_plan_info* info);
 size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries,
                                 uint32_t total_tickets);
 size_t oa_pjoin_args_size(void);

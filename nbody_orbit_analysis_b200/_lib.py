@@ -168,6 +168,8 @@ _sig('oa_select_gather_events_ids', C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
      _vp)
 _sig('oa_pjoin_workspace_bytes', _sz, C.c_int, _i64, C.c_uint32)
 _sig('oa_pjoin_args_size', _sz)
+_sig('oa_pjoin_plan_host', C.c_int, _vp, C.c_int, _vp, _vp, _i64, _i64, _vp, _vp,
+     _vp, _vp, _vp, _vp)
 _sig('oa_pjoin_step', C.c_int, _vp, _vp)
 from . import pjoin as _pjoin        # noqa: E402  (struct mirror of oa_pjoin_args)
 if lib.oa_pjoin_args_size() != C.sizeof(_pjoin.PJoinArgs):
@@ -191,7 +193,7 @@ EXPORTS = [
     'oa_pack_events', 'oa_merge_gathered', 'oa_select_gather_events',
     'oa_split_quantiles', 'oa_pack_split', 'oa_merge_blocks',
     'oa_select_gather_events_ids', 'oa_pjoin_workspace_bytes',
-    'oa_pjoin_args_size', 'oa_pjoin_step',
+    'oa_pjoin_args_size', 'oa_pjoin_step', 'oa_pjoin_plan_host',
 ]
 
 

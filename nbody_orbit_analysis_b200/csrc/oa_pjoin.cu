@@ -83,6 +83,88 @@ extern "C" size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries
 
 extern "C" size_t oa_pjoin_args_size(void) { return sizeof(oa_pjoin_args); }
 
+// host-side plan (restated in numpy in pjoin.py:make_plan, which the tests
+// compare with this function)
+extern "C" int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
+                                  const int32_t* prev_bits, const int64_t* prev_pb,
+                                  int64_t target, int64_t lag_particles,
+                                  oa_pjoin_region* rows, int32_t* bits_out, int64_t* pb_out,
+                                  uint32_t* group_first, uint32_t* range_start,
+                                  oa_pjoin_plan_info* info) {
+    OA_REQUIRE(n_regions >= 0 && target >= 1 && lag_particles >= 1 && rows && group_first &&
+               range_start && info && (n_regions == 0 || (offsets && prev_bits && prev_pb &&
+                                                          bits_out && pb_out)),
+               "oa_pjoin_plan_host: bad arguments");
+    uint64_t pb = 0, tiles = 0, ctiles = 0, joins = 0, scans = 0;
+    int n_groups = 0, max_bits = 0;
+    int64_t gid_prev = -1;
+    for (int j = 0; j < n_regions; ++j) {
+        const int64_t len = offsets[j + 1] - offsets[j];
+        OA_REQUIRE(len >= 0, "oa_pjoin_plan_host: offsets must not decrease");
+        int bits = 0;
+        while (bits < OA_PJOIN_MAX_BITS && len > (target << bits)) ++bits;
+        if (prev_bits[j] > bits) bits = prev_bits[j];
+        OA_REQUIRE(bits <= OA_PJOIN_MAX_BITS, "oa_pjoin_plan_host: bad prev_bits");
+        if (bits > max_bits) max_bits = bits;
+        oa_pjoin_region& r = rows[j];
+        r.pb_cur = (uint32_t)pb;
+        r.pb_prev = prev_bits[j] >= 0 ? (uint32_t)prev_pb[j] : 0u;
+        r.bits_cur = bits;
+        r.bits_prev = prev_bits[j];
+        r.tile_first = (uint32_t)tiles;
+        r.count_first = (uint32_t)ctiles;
+        r.join_first = (uint32_t)joins;
+        r.scan_first = (uint32_t)scans;
+        bits_out[j] = bits;
+        pb_out[j] = (int64_t)pb;
+        pb += ((uint64_t)1 << bits) + 1;
+        if (bits > 0) {
+            tiles += (uint64_t)((len + OA_PJOIN_TILE - 1) / OA_PJOIN_TILE);
+            ctiles += (uint64_t)((len + OA_PJOIN_CTILE - 1) / OA_PJOIN_CTILE);
+            scans += 1;
+            if (prev_bits[j] >= 0) joins += (uint64_t)1 << prev_bits[j];
+        } else {
+            joins += 1;
+        }
+        const int64_t gid = offsets[j] / lag_particles;
+        if (j == 0 || gid != gid_prev) group_first[n_groups++] = (uint32_t)j;
+        gid_prev = gid;
+    }
+    OA_REQUIRE(pb < ((uint64_t)1 << 32) && tiles + ctiles + joins + scans < ((uint64_t)1 << 32),
+               "oa_pjoin_plan_host: plan does not fit 32-bit counters");
+    oa_pjoin_region& e = rows[n_regions];
+    e.pb_cur = (uint32_t)pb;
+    e.pb_prev = 0;
+    e.bits_cur = e.bits_prev = 0;
+    e.tile_first = (uint32_t)tiles;
+    e.count_first = (uint32_t)ctiles;
+    e.join_first = (uint32_t)joins;
+    e.scan_first = (uint32_t)scans;
+    group_first[n_groups] = (uint32_t)n_regions;
+
+    // ticket ranges: superstep s holds JOIN of group s-3, SCATTER s-2, SCAN s-1, COUNT s
+    const int n_ranges = 4 * (n_groups + 3);
+    uint32_t t = 0;
+    for (int s = 0; s < n_groups + 3; ++s)
+        for (int st = 0; st < 4; ++st) {
+            range_start[4 * s + st] = t;
+            const int g = s - (3 - st);
+            if (g < 0 || g >= n_groups) continue;
+            const oa_pjoin_region &lo = rows[group_first[g]], &hi = rows[group_first[g + 1]];
+            t += st == pj::JOIN ? hi.join_first - lo.join_first
+               : st == pj::SCAN ? hi.scan_first - lo.scan_first
+               : st == pj::COUNT ? hi.count_first - lo.count_first
+                                 : hi.tile_first - lo.tile_first;
+        }
+    range_start[n_ranges] = t;
+    info->n_part_entries = (int64_t)pb;
+    info->total_tickets = t;
+    info->n_groups = n_groups;
+    info->n_ranges = n_ranges;
+    info->max_bits = max_bits;
+    return OA_OK;
+}
+
 extern "C" int oa_pjoin_step(const oa_pjoin_args* args, void* stream) {
     OA_REQUIRE(args != nullptr, "oa_pjoin_step: args is NULL");
     const oa_pjoin_args& a = *args;

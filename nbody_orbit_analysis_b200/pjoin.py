@@ -53,6 +53,12 @@ class PJoinArgs(C.Structure):
     ]
 
 
+class PlanInfo(C.Structure):
+    """``oa_pjoin_plan_info``."""
+    _fields_ = [('n_part_entries', _i64), ('total_tickets', _u32),
+                ('n_groups', _i32), ('n_ranges', _i32), ('max_bits', _i32)]
+
+
 class Plan:
     """Plan of one snapshot.  ``rows`` / ``group_first`` / ``range_start`` go to
     the device; ``bits`` / ``pb`` are kept on the host for the next snapshot."""
@@ -144,3 +150,53 @@ def decode(plan, ticket):
     j = int(np.searchsorted(pref[gf[g]:gf[g + 1]], target, side='right')) - 1
     j += int(gf[g])
     return stage, j, int(target - pref[j])
+
+
+class Planner:
+    """``make_plan`` through the C ABI (``oa_pjoin_plan_host``: one loop over the
+    regions instead of ~40 numpy calls; 0.2 ms -> a few microseconds per
+    snapshot at 1000 regions).  Scratch arrays are reused between snapshots."""
+
+    def __init__(self, lib):
+        self._fn = lib.oa_pjoin_plan_host
+        self._cap = -1
+
+    def _reserve(self, n_h):
+        if n_h > self._cap:
+            cap = int(n_h * 1.25) + 16
+            self._rows = np.zeros(cap + 1, dtype=PLAN_DTYPE)
+            self._group = np.zeros(cap + 1, dtype=np.uint32)
+            self._range = np.zeros(4 * (cap + 3) + 1, dtype=np.uint32)
+            self._cap = cap
+
+    def __call__(self, offsets, prev_bits, prev_pb, target=None,
+                 lag_particles=None):
+        target = TARGET if target is None else target
+        lag_particles = LAG_PARTICLES if lag_particles is None else lag_particles
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        prev_bits = np.ascontiguousarray(prev_bits, dtype=np.int32)
+        prev_pb = np.ascontiguousarray(prev_pb, dtype=np.int64)
+        n_h = len(offsets) - 1
+        self._reserve(n_h)
+        bits = np.empty(n_h, dtype=np.int32)
+        pb = np.empty(n_h, dtype=np.int64)
+        info = PlanInfo()
+        vp = C.c_void_p
+        rc = self._fn(offsets.ctypes.data_as(vp), n_h,
+                      prev_bits.ctypes.data_as(vp), prev_pb.ctypes.data_as(vp),
+                      int(target), int(lag_particles),
+                      self._rows.ctypes.data_as(vp), bits.ctypes.data_as(vp),
+                      pb.ctypes.data_as(vp), self._group.ctypes.data_as(vp),
+                      self._range.ctypes.data_as(vp), C.byref(info))
+        if rc != 0:
+            raise RuntimeError('oa_pjoin_plan_host failed (%d)' % rc)
+        p = Plan()
+        # (views into the scratch arrays: valid until the next call)
+        p.rows = self._rows[:n_h + 1]
+        p.group_first = self._group[:info.n_groups + 1]
+        p.range_start = self._range[:info.n_ranges + 1]
+        p.bits, p.pb = bits, pb
+        p.n_entries = int(info.n_part_entries)
+        p.n_groups, p.n_ranges = int(info.n_groups), int(info.n_ranges)
+        p.total = int(info.total_tickets)
+        return p

@@ -92,6 +92,7 @@ class OrbitTracker:
         if impl == 'pjoin' and onthefly:
             raise ValueError("impl='pjoin' does not cover the on-the-fly path")
         self.impl = impl
+        self._planner = None
         if mode not in _lib.OA_MODE:
             raise ValueError("mode must be 'pericentric' or 'apocentric'")
         self.mode = mode
@@ -576,7 +577,9 @@ class OrbitTracker:
             k = np.searchsorted(prev.halo_exists, gen.halo_exists[matched])
             prev_bits[matched] = prev.pj_bits[k]
             prev_pb[matched] = prev.pj_pb[k]
-        plan = pjoin.make_plan(gen.offsets, prev_bits, prev_pb)
+        if self._planner is None:
+            self._planner = pjoin.Planner(lib)
+        plan = self._planner(gen.offsets, prev_bits, prev_pb)
         gen.pj_bits, gen.pj_pb = plan.bits, plan.pb
         # one packed host->device copy: [plan rows | group_first | range_start]
         nb_rows = plan.rows.nbytes

@@ -40,7 +40,8 @@ def test_track_orbits_pjoin_matches_oracle(case, mode, target, tmp_path,
     from oracle import orbit_oracle as oracle
     monkeypatch.setenv('OA_TRACK_IMPL', 'pjoin')
     if target is not None:       # small partitions: every stage at these sizes
-        monkeypatch.setattr(pjoin.make_plan, '__defaults__', (target, 1 << 12))
+        monkeypatch.setattr(pjoin, 'TARGET', target)
+        monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
     n, nh, ns, kw = case
     sim = SynthSim(n, nh, ns, dtype=np.float32, catalogue_dtype=np.float32, **kw)
     f_gpu, f_cpu = str(tmp_path / 'gpu.h5'), str(tmp_path / 'cpu.h5')

@@ -263,6 +263,31 @@ def test_plan_decode_covers_every_item_once():
     assert n_items == plan.total
 
 
+def test_c_plan_equals_numpy_plan():
+    """``oa_pjoin_plan_host`` (what the tracker calls) against ``make_plan``."""
+    from nbody_orbit_analysis_b200 import _lib
+    rng = np.random.default_rng(5)
+    planner = pjoin.Planner(_lib.lib)
+    for trial in range(120):
+        nh = int(rng.integers(0, 300))
+        lens = rng.integers(0, 30000, nh)
+        if nh > 3:
+            lens[rng.integers(0, nh, 2)] = [0, 900000]
+        offsets = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        prev_bits = rng.integers(-1, 6, nh).astype(np.int32)
+        prev_pb = rng.integers(0, 10 ** 6, nh).astype(np.int64)
+        target = int(rng.choice([300, 2304, 5000]))
+        lag = int(rng.choice([1 << 12, 1 << 19]))
+        a = pjoin.make_plan(offsets, prev_bits, prev_pb, target, lag)
+        b = planner(offsets, prev_bits, prev_pb, target, lag)
+        assert np.array_equal(a.rows, b.rows)
+        assert np.array_equal(a.group_first, b.group_first)
+        assert np.array_equal(a.range_start, b.range_start)
+        assert np.array_equal(a.bits, b.bits) and np.array_equal(a.pb, b.pb)
+        assert (a.n_entries, a.n_groups, a.n_ranges, a.total) == \
+            (b.n_entries, b.n_groups, b.n_ranges, b.total)
+
+
 def test_small_regions_direct_join(emul):
     """Every region is one partition (bits 0): frame + join in one item."""
     sim = SynthSim(12000, 12, 5, dtype=np.float32, catalogue_dtype=np.float32)

@@ -41,8 +41,7 @@ def test_track_orbits_pjoin_matches_oracle(emul, pjoin_env, monkeypatch, case,
     derived = not kw.get('catalogue_bulk', True)
     # small partitions, so that the partitioned stages run at these sizes
     monkeypatch.setattr(pjoin, 'TARGET', 400)
-    monkeypatch.setattr(pjoin.make_plan, '__defaults__',
-                        (400, 1 << 12))
+    monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
     sim = SynthSim(n, nh, ns, dtype=np.float32, catalogue_dtype=np.float32, **kw)
     f_dev, f_cpu = str(tmp_path / 'dev.h5'), str(tmp_path / 'cpu.h5')
     args = (sim.snapshot_numbers, sim.main_branches, sim.regions,
