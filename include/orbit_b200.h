@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 13
+#define OA_ABI_VERSION 14
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -69,6 +69,26 @@ typedef struct oa_region {
     float bulk_f[3];     /* (float)bulk  (oa_bulk_velocity keeps it in sync)  */
     int64_t reserved;
 } oa_region;             /* 128 bytes; the table must be 16-byte aligned      */
+
+/* The region table on the HOST (host pointers, no CUDA call): what the Python
+ * driver otherwise assembles with ~20 numpy calls per snapshot.  For region j:
+ * centre / bulk from the catalogue arrays (float32 or float64, `bulk` may be NULL
+ * when the bulk velocity is derived on the device), the block range from
+ * `offsets`, and -- when `halo_ids[j]` is found in the ascending
+ * `prev_halo_ids` (track_orbits.py:162-165) -- the previous block and its
+ * bucket range.  Also written: buckets_out[j] (oa_table_bucket_begin of this
+ * block), matched_out[j] (0/1), prev_index_out[j] (position in prev_halo_ids or
+ * -1), seg_begin_out[m] = previous block start of the m-th matched region; the
+ * number of matched regions is returned in *n_matched. */
+int oa_region_rows_host(int n_regions, const int64_t* offsets,
+                        const void* centres, int centre_dtype,
+                        const void* bulk, int bulk_dtype,
+                        const int64_t* halo_ids, const int64_t* prev_halo_ids,
+                        int n_prev_regions, const int64_t* prev_offsets,
+                        const int64_t* prev_buckets, oa_region* rows,
+                        int64_t* buckets_out, uint8_t* matched_out,
+                        int32_t* prev_index_out, int64_t* seg_begin_out,
+                        int* n_matched);
 
 /* Bytes of one carried-state record (32 for an OA_F32 frame, 64 for OA_F64). */
 size_t oa_record_bytes(int frame_dtype);

@@ -31,3 +31,75 @@ extern "C" int oa_device_info(int* sm_count, int* cc_major, int* cc_minor,
 
 extern "C" size_t oa_track_args_size(void) { return sizeof(oa_track_args); }
 extern "C" size_t oa_synth_params_size(void) { return sizeof(oa_synth_params); }
+
+// ---- host-side assembly of the region table (see include/orbit_b200.h) -------------
+extern "C" int oa_region_rows_host(int n_regions, const int64_t* offsets,
+                                   const void* centres, int centre_dtype,
+                                   const void* bulk, int bulk_dtype,
+                                   const int64_t* halo_ids, const int64_t* prev_halo_ids,
+                                   int n_prev_regions, const int64_t* prev_offsets,
+                                   const int64_t* prev_buckets, oa_region* rows,
+                                   int64_t* buckets_out, uint8_t* matched_out,
+                                   int32_t* prev_index_out, int64_t* seg_begin_out,
+                                   int* n_matched) {
+    OA_REQUIRE(n_regions >= 0 && n_matched, "oa_region_rows_host: bad arguments");
+    *n_matched = 0;
+    if (n_regions == 0) return OA_OK;
+    OA_REQUIRE(offsets && centres && halo_ids && rows && buckets_out && matched_out &&
+               prev_index_out && seg_begin_out, "oa_region_rows_host: NULL pointer");
+    OA_REQUIRE((centre_dtype == OA_F32 || centre_dtype == OA_F64) &&
+               (!bulk || bulk_dtype == OA_F32 || bulk_dtype == OA_F64),
+               "oa_region_rows_host: bad dtype");
+    OA_REQUIRE(n_prev_regions == 0 || (prev_halo_ids && prev_offsets && prev_buckets),
+               "oa_region_rows_host: previous generation incomplete");
+    int m = 0;
+    for (int j = 0; j < n_regions; ++j) {
+        oa_region& r = rows[j];
+        memset(&r, 0, sizeof(r));
+        for (int q = 0; q < 3; ++q) {
+            if (centre_dtype == OA_F32) {
+                const float c = static_cast<const float*>(centres)[3 * j + q];
+                r.centre[q] = (double)c;
+                r.centre_f[q] = c;
+            } else {
+                const double c = static_cast<const double*>(centres)[3 * j + q];
+                r.centre[q] = c;
+                r.centre_f[q] = (float)c;
+            }
+            if (bulk) {
+                if (bulk_dtype == OA_F32) {
+                    const float b = static_cast<const float*>(bulk)[3 * j + q];
+                    r.bulk[q] = (double)b;
+                    r.bulk_f[q] = b;
+                } else {
+                    const double b = static_cast<const double*>(bulk)[3 * j + q];
+                    r.bulk[q] = b;
+                    r.bulk_f[q] = (float)b;
+                }
+            }
+        }
+        r.cur_begin = offsets[j];
+        r.cur_count = offsets[j + 1] - offsets[j];
+        r.cur_bucket = oa_table_bucket_begin(offsets[j], j);
+        buckets_out[j] = r.cur_bucket;
+        r.prev_begin = -1;
+        // position of this halo in the previous (ascending) list
+        int lo = 0, hi = n_prev_regions;
+        const int64_t id = halo_ids[j];
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (prev_halo_ids[mid] < id) lo = mid + 1; else hi = mid;
+        }
+        const bool hit = lo < n_prev_regions && prev_halo_ids[lo] == id;
+        matched_out[j] = hit ? 1 : 0;
+        prev_index_out[j] = hit ? lo : -1;
+        if (hit) {
+            r.prev_begin = prev_offsets[lo];
+            r.prev_count = prev_offsets[lo + 1] - prev_offsets[lo];
+            r.prev_bucket = prev_buckets[lo];
+            seg_begin_out[m++] = r.prev_begin;
+        }
+    }
+    *n_matched = m;
+    return OA_OK;
+}

@@ -45,6 +45,8 @@ struct DevCtx {
                         "r"(w[6]), "r"(w[7])
                      : "memory");
     }
+    OA_D int64_t ld_last(const int64_t* p) const { return __ldcs(p); }
+    OA_D float ld_last(const float* p) const { return __ldcs(p); }
     // read-only for this launch and touched once: streaming, no L1 allocation
     OA_D pj::U4 ld_stream(const pj::U4* p) const {
         const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));

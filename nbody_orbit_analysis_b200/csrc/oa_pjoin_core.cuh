@@ -220,7 +220,8 @@ PJ_FN void frame(const oa_pjoin_args& a, const Const& k, const oa_region& R, con
 // CX (execution context) provides: tid(), sync(), smem(), atomic_add / atomic_cas
 // on uint32 (shared or global), load_acquire / release_add (gpu scope), backoff(),
 // fail(), ld_cg / load_rec_cg (global data another CTA of this launch may have
-// written), ld_stream (read-only data touched once), store_rec.
+// written), ld_stream / ld_last (read-only data touched for the last time),
+// store_rec.
 // (a dependency always has a smaller ticket, i.e. a CTA that is running: the wait
 // is short.  A wait of seconds can only be a bug -- it ends the kernel with an
 // error instead of hanging the device.)
@@ -365,12 +366,14 @@ PJ_FN void load_tile(CX& cx, const oa_pjoin_args& a, int64_t begin, int cnt) {
     int64_t* s_ids = reinterpret_cast<int64_t*>(cx.smem() + SM_IDS);
     float* s_pos = reinterpret_cast<float*>(cx.smem() + SM_POS);
     float* s_vel = reinterpret_cast<float*>(cx.smem() + SM_VEL);
+    // last use of the inputs: streaming loads, they must not displace the records
+    // that wait in L2 for their JOIN
     PJ_UNROLL4
-    for (int i = cx.tid(); i < cnt; i += THREADS) s_ids[i] = a.ids[begin + i];
+    for (int i = cx.tid(); i < cnt; i += THREADS) s_ids[i] = cx.ld_last(a.ids + begin + i);
     PJ_UNROLL4
     for (int i = cx.tid(); i < 3 * cnt; i += THREADS) {
-        s_pos[i] = a.pos[3 * begin + i];
-        s_vel[i] = a.vel[3 * begin + i];
+        s_pos[i] = cx.ld_last(a.pos + 3 * begin + i);
+        s_vel[i] = cx.ld_last(a.vel + 3 * begin + i);
     }
 }
 

@@ -38,6 +38,7 @@ class Generation:
     __slots__ = ('n', 'rec', 'tab', 'mark', 'index_bits', 'offsets',
                  'halo_exists', 'frame_f64', 'ids_dtype', 'gpos', 'buckets',
                  'n_buckets',
+                 'halo_ids64',
                  # partitioned-join generations (impl='pjoin'): records are
                  # stored partitioned, events take their IDs from `ids`
                  'pjoin', 'ids', 'part_off', 'pj_bits', 'pj_pb')
@@ -333,51 +334,51 @@ class OrbitTracker:
                 % (64 if prev.frame_f64 else 32, 64 if frame_f64 else 32))
 
         # ---- region table (oa_region rows) ---------------------------------
-        rows = np.zeros(n_h, dtype=_lib.REGION_DTYPE)
-        rows['centre'] = region_positions.astype(np.float64).reshape(n_h, 3)
-        rows['centre_f'] = rows['centre']
-        rows['cur_begin'] = offsets[:-1]
-        rows['cur_count'] = np.diff(offsets)
-        rows['prev_begin'] = -1
-        matched = np.zeros(n_h, dtype=bool)
-        if prev is not None and n_h and len(prev.halo_exists):
-            pos_in_prev = np.searchsorted(prev.halo_exists, halo_exists)
-            pos_c = np.minimum(pos_in_prev, len(prev.halo_exists) - 1)
-            matched = prev.halo_exists[pos_c] == halo_exists
-            k = pos_c[matched]
-            rows['prev_begin'][matched] = prev.offsets[k]
-            rows['prev_count'][matched] = prev.offsets[k + 1] - prev.offsets[k]
-            rows['prev_bucket'][matched] = prev.buckets[k]
-        # closed-form bucket ranges of this snapshot's table (see
-        # oa_table_bucket_begin in include/orbit_b200.h)
-        buckets = offsets[:-1] // _lib.BUCKET_LOAD + np.arange(
-            n_h, dtype=np.int64)
-        rows['cur_bucket'] = buckets
+        # assembled by oa_region_rows_host straight into the pinned staging
+        # buffer of the packed host->device copy [rows | offsets | seg_begin]
+        # (numpy restatement: tests/test_abi_and_host.py)
         derive_bulk = region_bulk_vels is None
+        cen = region_positions if region_positions.dtype in _F else \
+            region_positions.astype(np.float64)
+        cen = np.ascontiguousarray(cen).reshape(-1)
         if not derive_bulk:
             bulk = np.asarray(region_bulk_vels)
-            rows['bulk'] = bulk.astype(np.float64).reshape(n_h, 3)
-            rows['bulk_f'] = rows['bulk']
             bulk_dtype = bulk.dtype if bulk.dtype in _F else np.dtype(
                 np.float64)
+            bulk = np.ascontiguousarray(bulk, dtype=bulk_dtype).reshape(-1)
         else:
+            bulk = None
             bulk_dtype = data_dtype if mass_dtype is None else np.result_type(
                 data_dtype, mass_dtype)
         bulk_f32 = bulk_dtype == np.float32
-        seg_begin = np.ascontiguousarray(rows['prev_begin'][matched])
-        n_m = len(seg_begin)
-
-        # one packed host->device copy: [rows | offsets | seg_begin]
+        hx = np.ascontiguousarray(halo_exists, dtype=np.int64)
         nb_rows, nb_off = 128 * n_h, 8 * (n_h + 1)
-        pack = self._hbuf('pack', nb_rows + nb_off + 8 * max(n_m, 1),
+        pack = self._hbuf('pack', nb_rows + nb_off + 8 * max(n_h, 1),
                           torch.uint8)
         hp = pack.numpy()
-        hp[:nb_rows] = rows.view(np.uint8)
+        buckets = np.empty(n_h, dtype=np.int64)
+        matched = np.empty(n_h, dtype=np.bool_)
+        prev_index = np.empty(n_h, dtype=np.int32)
+        n_m_c = C.c_int(0)
+        have_prev = prev is not None and len(prev.halo_exists) > 0
+        if have_prev:
+            phx = prev.halo_ids64
+            p_args = (phx.ctypes.data, len(phx), prev.offsets.ctypes.data,
+                      prev.buckets.ctypes.data)
+        else:
+            p_args = (None, 0, None, None)
+        check(lib.oa_region_rows_host(
+            n_h, offsets.ctypes.data, cen.ctypes.data,
+            _lib.dtype_code(cen.dtype), bulk.ctypes.data if bulk is not None
+            else None, _lib.dtype_code(bulk.dtype) if bulk is not None else 0,
+            hx.ctypes.data, *p_args, pack.data_ptr(), buckets.ctypes.data,
+            matched.ctypes.data, prev_index.ctypes.data,
+            pack.data_ptr() + nb_rows + nb_off, C.byref(n_m_c)))
+        n_m = n_m_c.value
         hp[nb_rows:nb_rows + nb_off] = offsets.view(np.uint8)
-        hp[nb_rows + nb_off:nb_rows + nb_off + 8 * n_m] = \
-            seg_begin.view(np.uint8)
-        d_pack = self._buf('pack', pack.numel(), torch.uint8)
-        d_pack.copy_(pack, non_blocking=True)
+        used = nb_rows + nb_off + 8 * max(n_m, 1)
+        d_pack = self._buf('pack', used, torch.uint8)
+        d_pack.copy_(pack[:used], non_blocking=True)
         d_rows = d_pack[:nb_rows]
         d_off = d_pack[nb_rows:nb_rows + nb_off]
         d_seg = d_pack[nb_rows + nb_off:]
@@ -401,6 +402,7 @@ class OrbitTracker:
         gen.ids_dtype = np.dtype(ids_dtype)
         gen.offsets = offsets
         gen.halo_exists = halo_exists
+        gen.halo_ids64 = hx
         gen.gpos = gpos
         gen.buckets = buckets
         gen.pjoin = self.impl == 'pjoin'
@@ -414,8 +416,8 @@ class OrbitTracker:
                     "diagnostics); use impl='hash'")
             if prev is not None and not prev.pjoin:
                 raise _lib.OrbitB200Error("generations of two implementations")
-            self._launch_pjoin(gen, prev, dev, d_rows, rows, matched, lens,
-                               bulk_f32, box_size, H, redshift, st)
+            self._launch_pjoin(gen, prev, dev, d_rows, prev_index, matched,
+                               lens, bulk_f32, box_size, H, redshift, st)
             tile_ws = a = None
         else:
             # ---- new generation buffers ------------------------------------------
@@ -567,14 +569,14 @@ class OrbitTracker:
         self._step += 1
         return p
 
-    def _launch_pjoin(self, gen, prev, dev, d_rows, rows, matched, lens,
+    def _launch_pjoin(self, gen, prev, dev, d_rows, prev_index, matched, lens,
                       bulk_f32, box_size, H, redshift, st):
         """Enqueue ``oa_pjoin_step`` for the current snapshot (see pjoin.py)."""
         n, n_h = gen.n, len(lens)
         prev_bits = np.full(n_h, -1, dtype=np.int32)
         prev_pb = np.zeros(n_h, dtype=np.int64)
         if prev is not None and matched.any():
-            k = np.searchsorted(prev.halo_exists, gen.halo_exists[matched])
+            k = prev_index[matched]
             prev_bits[matched] = prev.pj_bits[k]
             prev_pb[matched] = prev.pj_pb[k]
         if self._planner is None:

@@ -39,6 +39,8 @@ struct HostCtx {
     void fail() const { abort(); }
     uint32_t ld_cg(const uint32_t* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
     pj::U4 ld_stream(const pj::U4* p) const { return *p; }
+    int64_t ld_last(const int64_t* p) const { return *p; }
+    float ld_last(const float* p) const { return *p; }
     pj::Rec load_rec_cg(const pj::Rec* p) const { return *p; }
     void store_rec(pj::Rec* p, const pj::Rec& r) const { *p = r; }
 };

@@ -132,3 +132,74 @@ def test_synthetic_workload_is_reproducible_and_has_apsides():
     assert not np.array_equal(
         sa['ids'][np.isin(sa['ids'], common)],
         sc['ids'][np.isin(sc['ids'], common)])
+
+
+def test_region_rows_host_equals_numpy_assembly():
+    """``oa_region_rows_host`` (what ``OrbitTracker.submit_device`` calls)
+    against the numpy assembly of the region table it replaced: centres and
+    bulk velocities in both float dtypes, matched / new / vanished halos
+    (reference ``track_orbits.py:155-165``)."""
+    from nbody_orbit_analysis_b200 import _lib
+    rng = np.random.default_rng(9)
+    lib = _lib.lib
+    for trial in range(60):
+        n_h = int(rng.integers(0, 50))
+        n_p = int(rng.integers(0, 50))
+        ids_cur = np.sort(rng.choice(200, n_h, replace=False)).astype(np.int64)
+        ids_prev = np.sort(rng.choice(200, n_p, replace=False)).astype(np.int64)
+        offsets = np.concatenate(([0], np.cumsum(rng.integers(0, 5000, n_h)))
+                                 ).astype(np.int64)
+        p_off = np.concatenate(([0], np.cumsum(rng.integers(0, 5000, n_p)))
+                               ).astype(np.int64)
+        p_buckets = (p_off[:-1] // _lib.BUCKET_LOAD + np.arange(n_p)).astype(np.int64)
+        cdt = rng.choice([np.float32, np.float64])
+        bdt = rng.choice([np.float32, np.float64])
+        cen = rng.standard_normal((n_h, 3)).astype(cdt) * 50
+        bulk = rng.standard_normal((n_h, 3)).astype(bdt) if trial % 3 else None
+
+        # numpy assembly (the code this function replaced)
+        rows = np.zeros(n_h, dtype=_lib.REGION_DTYPE)
+        rows['centre'] = cen.astype(np.float64)
+        rows['centre_f'] = rows['centre']
+        rows['cur_begin'] = offsets[:-1]
+        rows['cur_count'] = np.diff(offsets)
+        rows['prev_begin'] = -1
+        matched = np.zeros(n_h, dtype=bool)
+        if n_h and n_p:
+            pos_c = np.minimum(np.searchsorted(ids_prev, ids_cur), n_p - 1)
+            matched = ids_prev[pos_c] == ids_cur
+            k = pos_c[matched]
+            rows['prev_begin'][matched] = p_off[k]
+            rows['prev_count'][matched] = p_off[k + 1] - p_off[k]
+            rows['prev_bucket'][matched] = p_buckets[k]
+        buckets = offsets[:-1] // _lib.BUCKET_LOAD + np.arange(n_h)
+        rows['cur_bucket'] = buckets
+        if bulk is not None:
+            rows['bulk'] = bulk.astype(np.float64)
+            rows['bulk_f'] = rows['bulk']
+
+        got = np.full(n_h, 0x33, dtype=np.uint8).repeat(128).view(_lib.REGION_DTYPE)
+        g_buckets = np.empty(n_h, dtype=np.int64)
+        g_matched = np.empty(n_h, dtype=np.bool_)
+        g_prev = np.empty(n_h, dtype=np.int32)
+        g_seg = np.empty(max(n_h, 1), dtype=np.int64)
+        n_m = C.c_int(-1)
+        rc = lib.oa_region_rows_host(
+            n_h, offsets.ctypes.data, cen.ctypes.data, _lib.dtype_code(cdt),
+            bulk.ctypes.data if bulk is not None else None,
+            _lib.dtype_code(bdt), ids_cur.ctypes.data,
+            ids_prev.ctypes.data if n_p else None, n_p,
+            p_off.ctypes.data if n_p else None,
+            p_buckets.ctypes.data if n_p else None, got.ctypes.data,
+            g_buckets.ctypes.data, g_matched.ctypes.data, g_prev.ctypes.data,
+            g_seg.ctypes.data, C.byref(n_m))
+        assert rc == 0
+        assert got.tobytes() == rows.tobytes()
+        assert np.array_equal(g_buckets, buckets)
+        assert np.array_equal(g_matched, matched)
+        assert n_m.value == int(matched.sum())
+        assert np.array_equal(g_seg[:n_m.value], rows['prev_begin'][matched])
+        exp_prev = np.full(n_h, -1, dtype=np.int32)
+        if n_h and n_p:
+            exp_prev[matched] = pos_c[matched]
+        assert np.array_equal(g_prev, exp_prev)
