@@ -48,10 +48,6 @@ def test_track_orbits_pjoin_matches_oracle(emul, pjoin_env, monkeypatch, case,
             sim.load_snapshot_data)
     from nbody_orbit_analysis_b200 import track_orbits
     with fake_cuda.install(emul) as fake:
-        if derived:
-            # (the bulk-velocity kernel has no host twin: give the rows the
-            # oracle's values where the kernel would have written them)
-            pytest.skip('derived bulk velocity needs oa_bulk_velocity')
         track_orbits.track_orbits(*args, f_dev, mode=mode, verbose=False,
                                   device='cpu')
         assert fake.calls.count('oa_pjoin_step') == ns
@@ -59,7 +55,7 @@ def test_track_orbits_pjoin_matches_oracle(emul, pjoin_env, monkeypatch, case,
     oracle.track_orbits(*args, f_cpu, mode=mode, storage=storage)
     got, exp = storage.tree(f_dev), storage.tree(f_cpu)
     assert sum(len(v) for k, v in exp.items() if k.endswith('er_IDs')) > 0
-    compare_track_trees(got, exp, data_f64=False)
+    compare_track_trees(got, exp, data_f64=False, derived_bulk=derived)
 
 
 def test_pjoin_rejects_what_it_does_not_cover(emul, pjoin_env):
