@@ -37,10 +37,12 @@
 #ifdef PJ_HOST_EMUL
 #define PJ_FN inline
 #define PJ_UNROLL4
+#define PJ_UNROLL_ALL
 #else
 #include <cuda_fp16.h>
 #define PJ_FN __device__ __forceinline__
 #define PJ_UNROLL4 _Pragma("unroll 4")
+#define PJ_UNROLL_ALL _Pragma("unroll")
 #endif
 
 namespace pj {
@@ -92,6 +94,7 @@ static_assert(SM_JOIN_SLOT % 16 == 0 && SM_HIST % 4 == 0, "alignment");
 static_assert(SM_SCAN_PART + THREADS * 4 <= SM_BODY, "scan scratch");
 static_assert((1 << MAX_BITS) <= THREADS * 8, "scan: 8 values per thread");
 static_assert(REC_CAP < 4095, "record index must fit 12 bits, 4095 is reserved");
+static_assert(TILE % THREADS == 0 && CTILE % (8 * THREADS) == 0, "tile loops");
 
 // launch constants derived on the host
 struct Const {
@@ -312,9 +315,18 @@ PJ_FN void stage_count(CX& cx, const oa_pjoin_args& a, const Work& w, int j, uin
     uint32_t* hist = reinterpret_cast<uint32_t*>(cx.smem() + SM_HIST);
     for (int p = cx.tid(); p < nP; p += THREADS) hist[p] = 0;
     cx.sync();
-    PJ_UNROLL4
-    for (int i = cx.tid(); i < cnt; i += THREADS)
-        cx.atomic_add(&hist[part_of(mix64((uint64_t)a.ids[begin + i]), bits)], 1u);
+    for (int k0 = 0; k0 < CTILE / THREADS; k0 += 8) {
+        int64_t id[8];
+        PJ_UNROLL_ALL
+        for (int k = 0; k < 8; ++k) {                           // 8 IDs in flight
+            const int i = cx.tid() + (k0 + k) * THREADS;
+            id[k] = i < cnt ? a.ids[begin + i] : 0;
+        }
+        PJ_UNROLL_ALL
+        for (int k = 0; k < 8; ++k)
+            if (cx.tid() + (k0 + k) * THREADS < cnt)
+                cx.atomic_add(&hist[part_of(mix64((uint64_t)id[k]), bits)], 1u);
+    }
     cx.sync();
     for (int p = cx.tid(); p < nP; p += THREADS)
         if (hist[p]) cx.atomic_add(&w.cursor[P.pb_cur + p], hist[p]);
@@ -368,12 +380,22 @@ PJ_FN void load_tile(CX& cx, const oa_pjoin_args& a, int64_t begin, int cnt) {
     float* s_vel = reinterpret_cast<float*>(cx.smem() + SM_VEL);
     // last use of the inputs: streaming loads, they must not displace the records
     // that wait in L2 for their JOIN
-    PJ_UNROLL4
-    for (int i = cx.tid(); i < cnt; i += THREADS) s_ids[i] = cx.ld_last(a.ids + begin + i);
-    PJ_UNROLL4
-    for (int i = cx.tid(); i < 3 * cnt; i += THREADS) {
-        s_pos[i] = cx.ld_last(a.pos + 3 * begin + i);
-        s_vel[i] = cx.ld_last(a.vel + 3 * begin + i);
+    // (fixed trip counts + predicates: fully unrolled, every load of the tile is
+    // in flight before the first shared-memory store)
+    PJ_UNROLL_ALL
+    for (int k = 0; k < TILE / THREADS; ++k) {
+        const int i = cx.tid() + k * THREADS;
+        if (i < cnt) s_ids[i] = cx.ld_last(a.ids + begin + i);
+    }
+    PJ_UNROLL_ALL
+    for (int k = 0; k < 3 * TILE / THREADS; ++k) {
+        const int i = cx.tid() + k * THREADS;
+        if (i < 3 * cnt) s_pos[i] = cx.ld_last(a.pos + 3 * begin + i);
+    }
+    PJ_UNROLL_ALL
+    for (int k = 0; k < 3 * TILE / THREADS; ++k) {
+        const int i = cx.tid() + k * THREADS;
+        if (i < 3 * cnt) s_vel[i] = cx.ld_last(a.vel + 3 * begin + i);
     }
 }
 
@@ -456,8 +478,14 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
         {   // previous records -> shared memory, 16 bytes per thread and step
             const U4* src = reinterpret_cast<const U4*>(rec_prev + bs);
             U4* dst = reinterpret_cast<U4*>(s_rec);
-            PJ_UNROLL4
-            for (int q = cx.tid(); q < 2 * nb; q += THREADS) dst[q] = cx.ld_stream(src + q);
+            constexpr int STEPS = (2 * REC_CAP + THREADS - 1) / THREADS;   // 12
+            for (int k0 = 0; k0 < STEPS; k0 += 6) {
+                PJ_UNROLL_ALL
+                for (int k = 0; k < 6; ++k) {                   // 6 x 16 B in flight
+                    const int q = cx.tid() + (k0 + k) * THREADS;
+                    if (q < 2 * nb) dst[q] = cx.ld_stream(src + q);
+                }
+            }
         }
         cx.sync();
         for (int i = cx.tid(); i < nb; i += THREADS) {
