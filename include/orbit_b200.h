@@ -239,11 +239,26 @@ size_t oa_track_args_size(void);
  * plus one end entry).  A small pre-kernel expands the plan into the explicit
  * item list (8 bytes per ticket, in the workspace) that the CTAs index by ticket.
  * ------------------------------------------------------------------------- */
-#define OA_PJOIN_THREADS 512
-#define OA_PJOIN_TILE 2048     /* particles per SCATTER item                  */
-#define OA_PJOIN_CTILE 8192    /* particles per COUNT item                    */
-#define OA_PJOIN_REC_CAP 2944
-#define OA_PJOIN_TARGET 2304
+/* Compile-time shape of the kernel (tuning builds override them with -D; the
+ * host reads them back with oa_pjoin_config, nothing else hard-codes them). */
+#ifndef OA_PJOIN_THREADS
+#define OA_PJOIN_THREADS 512   /* threads per CTA                              */
+#endif
+#ifndef OA_PJOIN_MIN_CTAS
+#define OA_PJOIN_MIN_CTAS 2    /* resident CTAs per SM the kernel is built for */
+#endif
+#ifndef OA_PJOIN_TILE
+#define OA_PJOIN_TILE 2048     /* particles per SCATTER item                   */
+#endif
+#ifndef OA_PJOIN_CTILE
+#define OA_PJOIN_CTILE 8192    /* particles per COUNT item                     */
+#endif
+#ifndef OA_PJOIN_REC_CAP
+#define OA_PJOIN_REC_CAP 2944  /* previous records per shared-memory table     */
+#endif
+#ifndef OA_PJOIN_TARGET
+#define OA_PJOIN_TARGET 2304   /* largest mean partition size                  */
+#endif
 #define OA_PJOIN_MAX_BITS 12
 
 typedef struct oa_pjoin_region {
@@ -315,6 +330,9 @@ int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
                        oa_pjoin_plan_info* info);
 size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries,
                                 uint32_t total_tickets);
+/* out[0..6] = THREADS, MIN_CTAS, TILE, CTILE, REC_CAP, TARGET, MAX_BITS,
+ * out[7] = dynamic shared memory per CTA in bytes. */
+void oa_pjoin_config(int32_t* out8);
 size_t oa_pjoin_args_size(void);
 int oa_pjoin_step(const oa_pjoin_args* args, void* stream);
 

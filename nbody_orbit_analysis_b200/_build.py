@@ -43,28 +43,43 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link the shared library."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every CUDA source for sm_100a and link the shared library.
+
+    ``extra_flags`` / ``out``: tuning builds (e.g. ``-DOA_PJOIN_THREADS=256``)
+    written next to the default library and selected with ``OA_LIB_PATH``."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build' if out is None else
+                          'build_' + os.path.basename(out).replace('.so', ''))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + [
+            '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas')
             cmd.insert(2, '-v')
             print(' '.join(cmd))
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + \
+    target = LIB if out is None else out
+    cmd = [nvcc, '-shared', '-o', target] + objs + \
         ['-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.run(cmd, check=True)
-    return LIB
+    return target
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    # python -m nbody_orbit_analysis_b200._build [--force] [-v]
+    #        [--out variants/liborbit_b200_small.so -DOA_PJOIN_THREADS=256 ...]
+    argv = sys.argv[1:]
+    out_path = None
+    if '--out' in argv:
+        out_path = os.path.abspath(argv[argv.index('--out') + 1])
+        os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    print(build(force='--force' in argv, verbose='-v' in argv,
+                extra_flags=[f for f in argv if f.startswith('-D')],
+                out=out_path))

@@ -176,6 +176,9 @@ _sig('oa_pjoin_step', C.c_int, _vp, _vp)
 from . import pjoin as _pjoin        # noqa: E402  (struct mirror of oa_pjoin_args)
 if lib.oa_pjoin_args_size() != C.sizeof(_pjoin.PJoinArgs):
     raise ImportError("oa_pjoin_args layout mismatch")
+lib.oa_pjoin_config.restype = None
+lib.oa_pjoin_config.argtypes = [C.POINTER(C.c_int32)]
+_pjoin.configure(lib)
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
@@ -196,7 +199,7 @@ EXPORTS = [
     'oa_split_quantiles', 'oa_pack_split', 'oa_merge_blocks',
     'oa_select_gather_events_ids', 'oa_pjoin_workspace_bytes',
     'oa_pjoin_args_size', 'oa_pjoin_step', 'oa_pjoin_plan_host',
-    'oa_region_rows_host',
+    'oa_region_rows_host', 'oa_pjoin_config',
 ]
 
 

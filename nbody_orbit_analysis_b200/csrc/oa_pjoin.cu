@@ -56,7 +56,7 @@ struct DevCtx {
     }
 };
 
-__global__ void __launch_bounds__(pj::THREADS, 2)
+__global__ void __launch_bounds__(pj::THREADS, OA_PJOIN_MIN_CTAS)
 oa_pjoin_kernel(const __grid_constant__ oa_pjoin_args a, const __grid_constant__ pj::Const k,
                 const __grid_constant__ pj::Work w) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -84,6 +84,17 @@ extern "C" size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries
 }
 
 extern "C" size_t oa_pjoin_args_size(void) { return sizeof(oa_pjoin_args); }
+
+extern "C" void oa_pjoin_config(int32_t* out8) {
+    out8[0] = pj::THREADS;
+    out8[1] = OA_PJOIN_MIN_CTAS;
+    out8[2] = pj::TILE;
+    out8[3] = pj::CTILE;
+    out8[4] = pj::REC_CAP;
+    out8[5] = OA_PJOIN_TARGET;
+    out8[6] = pj::MAX_BITS;
+    out8[7] = pj::SM_BYTES;
+}
 
 // host-side plan (restated in numpy in pjoin.py:make_plan, which the tests
 // compare with this function)

@@ -51,7 +51,9 @@ constexpr int THREADS = OA_PJOIN_THREADS;
 constexpr int TILE = OA_PJOIN_TILE;          // particles per SCATTER item
 constexpr int CTILE = OA_PJOIN_CTILE;        // particles per COUNT item
 constexpr int REC_CAP = OA_PJOIN_REC_CAP;    // previous records per table build
-constexpr int SLOTS = 4096;                  // shared-memory hash slots (power of 2)
+constexpr int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+constexpr int SLOTS = next_pow2(REC_CAP + REC_CAP / 3);   // shared-memory hash slots
+constexpr int SCAN_PER = (1 << OA_PJOIN_MAX_BITS) / THREADS;   // scan values per thread
 constexpr int MAX_BITS = OA_PJOIN_MAX_BITS;  // at most 2^12 partitions per region
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr uint16_t NO_EVENT = 0x8000u;       // = OA_NO_EVENT of the legacy path
@@ -92,7 +94,7 @@ constexpr int SM_BCAST = SM_BODY;            // 4 words of CTA-wide broadcast
 constexpr int SM_BYTES = SM_BCAST + 16;
 static_assert(SM_JOIN_SLOT % 16 == 0 && SM_HIST % 4 == 0, "alignment");
 static_assert(SM_SCAN_PART + THREADS * 4 <= SM_BODY, "scan scratch");
-static_assert((1 << MAX_BITS) <= THREADS * 8, "scan: 8 values per thread");
+static_assert(SCAN_PER * THREADS == (1 << MAX_BITS), "scan: whole values per thread");
 static_assert(REC_CAP < 4095, "record index must fit 12 bits, 4095 is reserved");
 static_assert(TILE % THREADS == 0 && CTILE % (8 * THREADS) == 0, "tile loops");
 
@@ -343,10 +345,10 @@ PJ_FN void stage_scan(CX& cx, const oa_pjoin_args& a, const Work& w, int j) {
     uint32_t* val = reinterpret_cast<uint32_t*>(cx.smem() + SM_SCAN_VAL);
     uint32_t* part = reinterpret_cast<uint32_t*>(cx.smem() + SM_SCAN_PART);
     const int tid = cx.tid();
-    // 8 consecutive values per thread, then a scan of the 512 partial sums
+    // SCAN_PER consecutive values per thread, then a scan of the partial sums
     uint32_t own = 0;
-    for (int e = 0; e < 8; ++e) {
-        const int p = tid * 8 + e;
+    for (int e = 0; e < SCAN_PER; ++e) {
+        const int p = tid * SCAN_PER + e;
         const uint32_t v = p < nP ? cx.ld_cg(&w.cursor[P.pb_cur + p]) : 0u;
         val[p] = own;                  // exclusive within the thread
         own += v;
@@ -360,8 +362,8 @@ PJ_FN void stage_scan(CX& cx, const oa_pjoin_args& a, const Work& w, int j) {
         cx.sync();
     }
     const uint32_t base = (uint32_t)R.cur_begin + part[tid] - own;
-    for (int e = 0; e < 8; ++e) {
-        const int p = tid * 8 + e;
+    for (int e = 0; e < SCAN_PER; ++e) {
+        const int p = tid * SCAN_PER + e;
         if (p < nP) {
             const uint32_t off = base + val[p];
             a.part_off_cur[P.pb_cur + p] = off;
@@ -478,7 +480,7 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
         {   // previous records -> shared memory, 16 bytes per thread and step
             const U4* src = reinterpret_cast<const U4*>(rec_prev + bs);
             U4* dst = reinterpret_cast<U4*>(s_rec);
-            constexpr int STEPS = (2 * REC_CAP + THREADS - 1) / THREADS;   // 12
+            constexpr int STEPS = (2 * REC_CAP + THREADS - 1) / THREADS;
             for (int k0 = 0; k0 < STEPS; k0 += 6) {
                 PJ_UNROLL_ALL
                 for (int k = 0; k < 6; ++k) {                   // 6 x 16 B in flight

@@ -12,6 +12,8 @@ import ctypes as C
 
 import numpy as np
 
+# Shape of the kernel as compiled (include/orbit_b200.h); `configure` replaces
+# these defaults with what the loaded library reports (tuning builds differ).
 THREADS = 512
 TILE = 2048            # OA_PJOIN_TILE  (particles per SCATTER item)
 CTILE = 8192           # OA_PJOIN_CTILE (particles per COUNT item)
@@ -53,6 +55,15 @@ class PJoinArgs(C.Structure):
     ]
 
 
+def configure(lib):
+    """Take the kernel's compile-time shape from the library."""
+    global THREADS, TILE, CTILE, REC_CAP, TARGET, MAX_BITS
+    out = (C.c_int32 * 8)()
+    lib.oa_pjoin_config(out)
+    THREADS, _, TILE, CTILE, REC_CAP, TARGET, MAX_BITS, _ = list(out)
+    return list(out)
+
+
 class PlanInfo(C.Structure):
     """``oa_pjoin_plan_info``."""
     _fields_ = [('n_part_entries', _i64), ('total_tickets', _u32),
@@ -66,18 +77,20 @@ class Plan:
                  'n_entries', 'n_groups', 'n_ranges', 'total')
 
 
-def need_bits(lens, target=TARGET):
+def need_bits(lens, target=None):
     """Smallest b with ``len <= target << b`` (at most MAX_BITS)."""
+    target = TARGET if target is None else target
     thr = np.int64(target) << np.arange(MAX_BITS + 1, dtype=np.int64)
     return np.minimum(np.searchsorted(thr, lens, side='left'),
                       MAX_BITS).astype(np.int32)
 
 
-def make_plan(offsets, prev_bits, prev_pb, target=TARGET,
-              lag_particles=LAG_PARTICLES):
+def make_plan(offsets, prev_bits, prev_pb, target=None, lag_particles=None):
     """``offsets``: (n_regions + 1,) block starts + n.  ``prev_bits`` /
     ``prev_pb``: per region of THIS snapshot, the partition bits and the first
     partition-offset entry of the same halo's previous block (bits -1: none)."""
+    target = TARGET if target is None else target
+    lag_particles = LAG_PARTICLES if lag_particles is None else lag_particles
     offsets = np.asarray(offsets, dtype=np.int64)
     n_h = len(offsets) - 1
     lens = np.diff(offsets)

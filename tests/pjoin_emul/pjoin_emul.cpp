@@ -60,11 +60,15 @@ void* thread_main(void* p) {
 
 }  // namespace
 
-extern "C" int pj_emul_sizes(int* threads, int* tile, int* rec_cap, int* smem_bytes) {
-    *threads = pj::THREADS;
-    *tile = pj::TILE + (pj::CTILE << 16);
-    *rec_cap = pj::REC_CAP;
-    *smem_bytes = pj::SM_BYTES;
+extern "C" int pj_emul_config(int32_t* out8) {
+    out8[0] = pj::THREADS;
+    out8[1] = OA_PJOIN_MIN_CTAS;
+    out8[2] = pj::TILE;
+    out8[3] = pj::CTILE;
+    out8[4] = pj::REC_CAP;
+    out8[5] = OA_PJOIN_TARGET;
+    out8[6] = pj::MAX_BITS;
+    out8[7] = pj::SM_BYTES;
     return (int)sizeof(oa_pjoin_args);
 }
 
@@ -95,6 +99,7 @@ extern "C" int pj_emul_step(const oa_pjoin_args* args, int n_ctas) {
     w.cursor = w.done_scatter + a.n_regions;
     for (int j = 0; j < a.n_regions; ++j)        // the expand pre-kernel
         for (int t = 0; t < 128; ++t) pj::expand_region(a, w.items, j, t, 128);
+
 
     std::vector<Cta> ctas(n_ctas);
     std::vector<ThreadArg> targs((size_t)n_ctas * pj::THREADS);

@@ -42,26 +42,46 @@ REC_DTYPE = np.dtype([('id', np.int64), ('rhat', np.float32, (3,)),
 NO_EVENT = 0x8000
 
 
-@pytest.fixture(scope='module')
-def emul():
+SMALL_SHAPE = ['-DOA_PJOIN_THREADS=256', '-DOA_PJOIN_MIN_CTAS=4',
+               '-DOA_PJOIN_TILE=1024', '-DOA_PJOIN_REC_CAP=1408',
+               '-DOA_PJOIN_TARGET=1152']
+
+
+def build_emul(flags=(), tag=''):
     gxx = shutil.which('g++')
     if gxx is None:
         pytest.skip('g++ not available')
+    out = LIB.replace('.so', tag + '.so')
     deps = [SRC, CORE, HDR]
-    if not os.path.exists(LIB) or any(
-            os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+    if not os.path.exists(out) or any(
+            os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run([gxx, '-O1', '-ffp-contract=off', '-pthread', '-shared',
-                        '-fPIC', '-std=c++17', '-DPJ_HOST_EMUL', '-o', LIB, SRC],
-                       check=True)
-    lib = C.CDLL(LIB)
+                        '-fPIC', '-std=c++17', '-DPJ_HOST_EMUL', *flags,
+                        '-o', out, SRC], check=True)
+    lib = C.CDLL(out)
     lib.pj_emul_step.argtypes = [C.POINTER(pjoin.PJoinArgs), C.c_int]
     lib.pj_emul_half_bits.argtypes = [C.c_float]
     lib.pj_emul_half_bits.restype = C.c_uint
-    sizes = [C.c_int() for _ in range(4)]
-    assert lib.pj_emul_sizes(*[C.byref(s) for s in sizes]) == \
-        C.sizeof(pjoin.PJoinArgs), 'PJoinArgs does not mirror oa_pjoin_args'
-    assert [s.value for s in sizes[:3]] == [
-        pjoin.THREADS, pjoin.TILE + (pjoin.CTILE << 16), pjoin.REC_CAP]
+    cfg = (C.c_int32 * 8)()
+    assert lib.pj_emul_config(cfg) == C.sizeof(pjoin.PJoinArgs), \
+        'PJoinArgs does not mirror oa_pjoin_args'
+    lib.shape = list(cfg)
+    return lib
+
+
+def use_shape(monkeypatch, lib):
+    """The plan must be made for the shape the (emulated) kernel was built with."""
+    for name, v in zip(('THREADS', None, 'TILE', 'CTILE', 'REC_CAP', 'TARGET',
+                        'MAX_BITS'), lib.shape):
+        if name:
+            monkeypatch.setattr(pjoin, name, v)
+
+
+@pytest.fixture(scope='module')
+def emul():
+    lib = build_emul()
+    assert lib.shape[:7] == [pjoin.THREADS, 2, pjoin.TILE, pjoin.CTILE,
+                             pjoin.REC_CAP, pjoin.TARGET, pjoin.MAX_BITS]
     return lib
 
 
@@ -80,8 +100,8 @@ class EmulTracker:
         self.lib, self.mode, self.n_ctas = lib, mode, n_ctas
         self.prev = None
 
-    def step(self, snap, halo_exists, centres, bulk, H=0.0, target=pjoin.TARGET,
-             lag=pjoin.LAG_PARTICLES):
+    def step(self, snap, halo_exists, centres, bulk, H=0.0, target=None,
+             lag=None):
         ids = np.ascontiguousarray(snap['ids'], dtype=np.int64)
         pos = np.ascontiguousarray(snap['coordinates'], dtype=np.float32)
         vel = np.ascontiguousarray(snap['velocities'], dtype=np.float32)
@@ -202,7 +222,7 @@ def run_case(lib, sim, mode='pericentric', targets=None, n_ctas=3, lag=1 << 12,
         with np.errstate(all='ignore'):
             state, exp = oracle.track_snapshot(snap, exists, pos, bulk, H, mode,
                                                prev_state)
-        target = targets[t % len(targets)] if targets else pjoin.TARGET
+        target = targets[t % len(targets)] if targets else None
         g, out = trk.step(snap, exists, pos, bulk, H, target, lag)
         check_state(g, trk.plan, state, trk.rows)
         if exp is not None:
@@ -351,3 +371,16 @@ def test_no_data_race_under_tsan(emul, tmp_path):
                     % out[-300:])
     assert 'WARNING: ThreadSanitizer' not in out, out[-3000:]
     assert 'tsan-run-complete' in out, out[-3000:]
+
+
+def test_small_cta_shape(monkeypatch):
+    """The same stage code built as 256-thread CTAs with 1408-record tables
+    (4 CTAs per SM on the device): a tuning build must not change results."""
+    lib = build_emul(SMALL_SHAPE, '_small')
+    assert lib.shape[:7] == [256, 4, 1024, 8192, 1408, 1152, 12]
+    use_shape(monkeypatch, lib)
+    sim = SynthSim(60000, 9, 4, dtype=np.float32, catalogue_dtype=np.float32)
+    st = run_case(lib, sim, targets=[None], n_ctas=4, lag=1 << 13)
+    assert max(st['bits']) >= 3 and max(st['maxlen']) > 2 * 1408
+    sim = SynthSim(30000, 3, 3, dtype=np.float32, catalogue_dtype=np.float32)
+    run_case(lib, sim, targets=[1 << 20], n_ctas=2)        # multi-batch joins
