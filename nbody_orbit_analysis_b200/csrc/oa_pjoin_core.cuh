@@ -462,6 +462,38 @@ PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const W
     signal(cx, &w.done_scatter[j]);
 }
 
+// one current record against the shared-memory table of previous records:
+// compare_radial_velocities + calc_angles (track_orbits.py:311-325, 330-351)
+PJ_FN void probe_one(const oa_pjoin_args& a, const Rec* s_rec, const uint32_t* slots,
+                     const Rec& cur, Rec* cur_global) {
+    const uint32_t h = (uint32_t)mix64((uint64_t)cur.id);
+    uint32_t s = h & (SLOTS - 1);
+    int hit = -1;
+    for (;;) {
+        const uint32_t v = slots[s];
+        if (v == EMPTY) break;
+        if ((v >> 12) == (h >> 12) && s_rec[v & 0xFFFu].id == cur.id) {
+            hit = (int)(v & 0xFFFu);
+            break;
+        }
+        s = (s + 1) & (SLOTS - 1);
+    }
+    if (hit < 0) return;                    // newly entered: accumulator stays 0
+    const Rec prev = s_rec[hit];
+    const float pr[3] = {prev.rx, prev.ry, prev.rz}, cr[3] = {cur.rx, cur.ry, cur.rz};
+    const float dang = acosf(dot3f(pr, cr));
+    bool ev;
+    if (a.mode == OA_MODE_PERICENTRIC) ev = (prev.vr < 0) && (cur.vr > 0);
+    else ev = (prev.vr > 0) && (cur.vr < 0);
+    float run = fadd(half_value(prev.angle), dang);
+    if (ev) {
+        a.mark_prev[prev.pos] = half_bits(run);
+        run = 0.0f;
+    }
+    // angle accumulator + "matched" flag: the last word of the record
+    reinterpret_cast<uint32_t*>(cur_global)[7] = (uint32_t)half_bits(run) | (1u << 16);
+}
+
 // ---- JOIN ----------------------------------------------------------------------------------------
 // previous records [pb, pe) against current records [cb, ce) (both of one halo,
 // the current range holds every particle whose hash falls in the previous one)
@@ -497,36 +529,18 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
             while (cx.atomic_cas(&slots[s], EMPTY, val) != EMPTY) s = (s + 1) & (SLOTS - 1);
         }
         cx.sync();
-        for (int c = cx.tid(); c < ncur; c += THREADS) {
-            const Rec cur = cx.load_rec_cg(rec_cur + cb + c);    // one 32-byte sector
-            if (multi && (cur.flags & 1u)) continue;
-            const uint32_t h = (uint32_t)mix64((uint64_t)cur.id);
-            uint32_t s = h & (SLOTS - 1);
-            int hit = -1;
-            for (;;) {
-                const uint32_t v = slots[s];
-                if (v == EMPTY) break;
-                if ((v >> 12) == (h >> 12) && s_rec[v & 0xFFFu].id == cur.id) {
-                    hit = (int)(v & 0xFFFu);
-                    break;
-                }
-                s = (s + 1) & (SLOTS - 1);
-            }
-            if (hit < 0) continue;
-            const Rec prev = s_rec[hit];
-            // compare_radial_velocities + calc_angles (track_orbits.py:311-325, 330-351)
-            const float pr[3] = {prev.rx, prev.ry, prev.rz}, cr[3] = {cur.rx, cur.ry, cur.rz};
-            const float dang = acosf(dot3f(pr, cr));
-            bool ev;
-            if (a.mode == OA_MODE_PERICENTRIC) ev = (prev.vr < 0) && (cur.vr > 0);
-            else ev = (prev.vr > 0) && (cur.vr < 0);
-            float run = fadd(half_value(prev.angle), dang);
-            if (ev) {
-                a.mark_prev[prev.pos] = half_bits(run);
-                run = 0.0f;
-            }
-            // angle accumulator + "matched" flag: the last word of the record
-            reinterpret_cast<uint32_t*>(rec_cur + cb + c)[7] = (uint32_t)half_bits(run) | (1u << 16);
+        // one record of lookahead: the load of the next record is in flight while
+        // this one is probed
+        int c = cx.tid();
+        Rec nxt = {};
+        if (c < ncur) nxt = cx.load_rec_cg(rec_cur + cb + c);
+        while (c < ncur) {
+            const Rec cur = nxt;
+            const int cn = c + THREADS;
+            if (cn < ncur) nxt = cx.load_rec_cg(rec_cur + cb + cn);
+            if (!(multi && (cur.flags & 1u)))
+                probe_one(a, s_rec, slots, cur, rec_cur + cb + c);
+            c = cn;
         }
         cx.sync();                     // the table is rebuilt by the next batch / item
     }
