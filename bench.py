@@ -326,6 +326,15 @@ def run_b200(args):
     comm = sharded.Comm(world, rank) if world > 1 else None
 
     cat_ahead = {}
+    # wall-clock of the host phases of the timed loop (per rank; rank 0 reports):
+    # shows whether a step is bound by the GPU or by host code / collectives
+    phases = {}
+
+    def timed(name, fn, *a, **k):
+        t0 = time.perf_counter()
+        out = fn(*a, **k)
+        phases[name] = phases.get(name, 0.0) + time.perf_counter() - t0
+        return out
 
     def catalogue(t):
         """This snapshot's catalogue; multi-GPU: broadcast from rank 0, started
@@ -338,14 +347,14 @@ def run_b200(args):
         return comm.finish_broadcast(h)
 
     def submit_step(trk, t, host=None):
-        pos, rad, bulk = catalogue(t)
+        pos, rad, bulk = timed('catalogue', catalogue, t)
         if host is None:
             dev, n, offsets = snaps[t]
-            return trk.submit_device(
-                dev, n, np.float32, np.int64, offsets, exists, pos, bulk, 0.0,
-                box_size=gen.host.box, gpos=dev.get('gpos'))
-        return trk.submit(host[t], exists, pos, bulk, 0.0,
-                          gpos=host[t].get('_gpos'))
+            return timed('submit', trk.submit_device,
+                         dev, n, np.float32, np.int64, offsets, exists, pos, bulk,
+                         0.0, box_size=gen.host.box, gpos=dev.get('gpos'))
+        return timed('submit', trk.submit, host[t], exists, pos, bulk, 0.0,
+                     gpos=host[t].get('_gpos'))
 
     exchange = {'inflight': None}
 
@@ -353,15 +362,15 @@ def run_b200(args):
         """Results of one snapshot.  Multi-GPU: its event exchange is started
         here and finished one snapshot later (it overlaps the next kernels);
         returns (local result, finished global result or None)."""
-        res = trk.collect(pending)
+        res = timed('collect', trk.collect, pending)
         done = None
         if comm is not None and res.apsis_offsets is not None:
             # every rank hands its 1/world share of the merged lists to the
             # host (parallel write of the result datasets)
-            h = comm.start_merge(trk, res, to_host='slice')
+            h = timed('start_merge', comm.start_merge, trk, res, to_host='slice')
             prev, exchange['inflight'] = exchange['inflight'], h
             if prev is not None:
-                done = comm.finish_merge(prev)
+                done = timed('finish_merge', comm.finish_merge, prev)
         elif comm is None:
             done = res
         return res, done
@@ -400,6 +409,7 @@ def run_b200(args):
         flush_exchange()
         trk.timing = []
         launches0 = trk.launches
+        phases.clear()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), \
             torch.cuda.Event(enable_timing=True)
@@ -451,6 +461,8 @@ def run_b200(args):
             ms, n_part = float(mx[0]), float(sm[1])
             n_events = float(stats[2])      # already global after the merge
         return {'ms': ms, 'wall_ms': 1e3 * (wall1 - wall0),
+                'host_phases_ms_per_step': {k: round(1e3 * v / K, 4)
+                                            for k, v in phases.items()},
                 'particles': n_part, 'events': n_events,
                 'launches': trk.launches - launches0, 'clocks': clocks,
                 'kern_ms': kern_ms, 'kern_n': kern_n, 'last': last}
@@ -561,6 +573,7 @@ def run_b200(args):
             'clocks': dev_run['clocks'], 'gpu_launches': dev_run['launches'],
             'events_per_step': dev_run['events'] / K,
             'track_impl': impl,
+            'host_phases_ms_per_step': dev_run['host_phases_ms_per_step'],
             'roofline': roofline,
         }
         if e2e is not None:
@@ -607,7 +620,9 @@ def cpu_baseline(args, snaps, cats, gen, torch):
             ok &= np.array_equal(res.apsis_offsets, exp['apsis_offsets'])
             a, b = res.apsis_angles.astype(np.float32), \
                 exp['apsis_angles'].astype(np.float32)
-            ok &= bool(np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True))
+            # (a mismatch must end up in the JSON line, not in a traceback)
+            ok &= a.shape == b.shape and bool(
+                np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True))
     return {
         'value': count / secs, 'unit': 'particle-snapshots/s', 'cores': 1,
         'kind': 'port',

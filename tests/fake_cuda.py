@@ -38,10 +38,11 @@ class FakeStream:
 
 class FakeEvent:
     def __init__(self, enable_timing=False, **k):
-        pass
+        self.t = None
 
     def record(self, stream=None):
-        pass
+        import time
+        self.t = time.perf_counter()
 
     def synchronize(self):
         pass
@@ -50,7 +51,7 @@ class FakeEvent:
         return True
 
     def elapsed_time(self, other):
-        return 0.0
+        return 1e3 * (other.t - self.t)
 
 
 def _arr(p, n, ctype):
@@ -75,8 +76,12 @@ class FakeLib:
         self.calls.append('oa_table_clear')
         return 0
 
-    def oa_track_fused(self, *a):
+    def oa_track_fused(self, args, stream):
+        """No tracking; only what the next snapshot's selection relies on: the
+        marks of this snapshot say "no event"."""
         self.calls.append('oa_track_fused')
+        a = args._obj
+        _arr(a.mark_cur, a.n_cur, C.c_uint16)[:] = NO_EVENT
         return 0
 
     def oa_bulk_velocity(self, vel, vel_dtype, mass, mass_dtype, cur_off, n_h, n,
@@ -161,23 +166,38 @@ def install(emul):
                       ('synchronize', lambda *a, **k: None)):
         saved[name] = getattr(cuda, name)
         setattr(cuda, name, val)
-    real_empty, real_zeros = torch.empty, torch.zeros
+    saved['set_device'] = cuda.set_device
+    cuda.set_device = lambda *a, **k: None
+    real_empty, real_zeros, real_tensor = torch.empty, torch.zeros, torch.tensor
+
+    def host(k):            # no pinned memory, no CUDA device in this container
+        k.pop('pin_memory', None)
+        if str(k.get('device', '')).startswith('cuda'):
+            k['device'] = 'cpu'
+        return k
 
     def empty(*a, **k):
-        k.pop('pin_memory', None)
-        return real_empty(*a, **k)
+        return real_empty(*a, **host(k))
 
     def zeros(*a, **k):
-        k.pop('pin_memory', None)
-        return real_zeros(*a, **k)
-    torch.empty, torch.zeros = empty, zeros
+        return real_zeros(*a, **host(k))
+
+    def tensor(*a, **k):
+        return real_tensor(*a, **host(k))
+    torch.empty, torch.zeros, torch.tensor = empty, zeros, tensor
     fake = FakeLib(_lib.lib, emul)
     real_lib = tracker.lib
     tracker.lib = fake
+    real_init = tracker.OrbitTracker.__init__
+
+    def init(self, mode='pericentric', device=None, onthefly=False, impl=None):
+        real_init(self, mode, 'cpu', onthefly, impl)
+    tracker.OrbitTracker.__init__ = init
     try:
         yield fake
     finally:
+        tracker.OrbitTracker.__init__ = real_init
         tracker.lib = real_lib
-        torch.empty, torch.zeros = real_empty, real_zeros
+        torch.empty, torch.zeros, torch.tensor = real_empty, real_zeros, real_tensor
         for name, val in saved.items():
             setattr(cuda, name, val)

@@ -90,13 +90,102 @@ def test_hash_branch_host_code_runs(emul, tmp_path):
         for t, sn in enumerate(sim.snapshot_numbers):
             pos, rad, bulk = sim.regions(sn, sim.main_branches[t])
             snap = sim.load_snapshot_data(sn, pos, rad)
-            # marks are whatever the buffers hold: make them "no event"
             pend.append(trk.submit(snap, np.arange(5), pos, bulk, 0.0,
                                    want_angles=(t == 1), diagnostics=(t == 2)))
-            trk.prev.mark.fill_(-32768)
             res = trk.collect(pend[-1])
             assert res.n == len(snap['ids'])
             if t > 0:
                 assert res.n_events == 0 and len(res.apsis_offsets) == 6
         assert fake.calls.count('oa_track_fused') == 3
         assert os.environ.get('OA_TRACK_IMPL') is None
+
+
+class HostSynth:
+    """Host twin of ``synth.DeviceSynth`` (same interface, SynthSim data)."""
+
+    def __init__(self, n_particles, n_halos, rank=0, world=1, **kw):
+        import torch
+        self._torch = torch
+        self.host = SynthSim(n_particles, n_halos, 64, dtype=np.float32,
+                             catalogue_dtype=np.float32)
+        self.n_halos = n_halos
+
+    def regions(self, t):
+        h = self.host
+        return (h.halo_centre(t).astype(np.float32), h.radius.astype(np.float32),
+                h.vh.astype(np.float32))
+
+    def snapshot(self, t):
+        torch = self._torch
+        pos, rad, _ = self.regions(t)
+        s = self.host.load_snapshot_data(self.host.snapshot_numbers[t], pos, rad,
+                                         cols=np.arange(self.n_halos))
+        n = len(s['ids'])
+        dev = {'pos': torch.from_numpy(s['coordinates'].reshape(-1).copy()),
+               'vel': torch.from_numpy(s['velocities'].reshape(-1).copy()),
+               'ids': torch.from_numpy(s['ids'].copy()), 'mass': None,
+               'gpos': None}
+        return dev, n, np.append(s['region_offsets'], n).astype(np.int64)
+
+
+def test_bench_end_to_end_on_fake_cuda(emul, pjoin_env, monkeypatch, capsys):
+    """``bench.py``'s GPU arm from argument parsing to the JSON line, on the CPU:
+    device-resident run, end-to-end run from host arrays, roofline block and the
+    CPU baseline whose sample must agree with the (emulated) GPU path."""
+    import argparse
+    import json
+    import bench
+    from nbody_orbit_analysis_b200 import synth
+    monkeypatch.setattr(synth, 'DeviceSynth', HostSynth)
+    monkeypatch.setattr(pjoin, 'TARGET', 400)
+    monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
+    monkeypatch.delenv('WORLD_SIZE', raising=False)
+    monkeypatch.setenv('OA_BENCH_CLOCK_PERIOD', '0.05')
+    args = argparse.Namespace(
+        gpus=1, steps=3, warmup=3, impl='b200', particles=20000, halos=12,
+        mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=False,
+        cpu_particles=4000)
+    with fake_cuda.install(emul):
+        bench.run_b200(args)
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines()
+                       if ln.startswith('{')][-1])
+    assert line['metric'] == 'particle-snapshots/sec' and line['value'] > 0
+    assert line['n_gpus'] == 1 and line['steps'] == 3 and line['warmup'] == 3
+    assert line['track_impl'] == 'pjoin' and line['gpu_launches'] > 0
+    assert line['events_per_step'] > 0
+    assert line['e2e']['value'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
+    assert line['e2e']['events_per_step'] == line['events_per_step']
+    r = line['roofline']
+    assert r['bound'] == 'hbm' and r['achieved'] > 0 and 'oa_pjoin' in r['kernel']
+    assert line['cpu_baseline']['parity_vs_gpu_on_sample'] == 'ok'
+    assert line['cpu_baseline']['sample_events'] > 0
+    assert set(line['host_phases_ms_per_step']) >= {'submit', 'collect'}
+
+
+def test_bench_hash_branch_runs_on_fake_cuda(emul, monkeypatch, capsys):
+    """The default implementation through ``bench.py`` with no-op kernels:
+    every line of the GPU arm executes (numbers are meaningless)."""
+    import argparse
+    import json
+    import bench
+    from nbody_orbit_analysis_b200 import synth
+    monkeypatch.setattr(synth, 'DeviceSynth', HostSynth)
+    monkeypatch.delenv('WORLD_SIZE', raising=False)
+    monkeypatch.delenv('OA_TRACK_IMPL', raising=False)
+    monkeypatch.setenv('OA_BENCH_CLOCK_PERIOD', '0.05')
+    args = argparse.Namespace(
+        gpus=1, steps=3, warmup=3, impl='b200', particles=8000, halos=6,
+        mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=False,
+        cpu_particles=2000)
+    with fake_cuda.install(emul) as fake:
+        bench.run_b200(args)
+        assert fake.calls.count('oa_track_fused') >= 2 * 7 + 7
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines()
+                       if ln.startswith('{')][-1])
+    assert line['track_impl'] == 'hash' and 'oa_track_kernel' in line['roofline']['kernel']
+    assert line['cpu_baseline']['parity_vs_gpu_on_sample'] in ('ok', 'MISMATCH')
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup',
+                'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+                'dtype', 'data', 'config', 'clocks', 'gpu_launches', 'e2e',
+                'roofline', 'cpu_baseline'):
+        assert key in line, key
