@@ -189,3 +189,115 @@ def test_bench_hash_branch_runs_on_fake_cuda(emul, monkeypatch, capsys):
                 'dtype', 'data', 'config', 'clocks', 'gpu_launches', 'e2e',
                 'roofline', 'cpu_baseline'):
         assert key in line, key
+
+
+# ---------------------------------------------------------------------------
+# bench.py, multi-rank, on the CPU: gloo + emulated kernels
+# ---------------------------------------------------------------------------
+class ShardedHostSynth(HostSynth):
+    """Every rank generates the same universe and keeps ``id mod world ==
+    rank`` (what DeviceSynth does on the device); ``gpos`` = position in the
+    unsharded snapshot."""
+
+    def __init__(self, n_particles, n_halos, rank=0, world=1, **kw):
+        HostSynth.__init__(self, n_particles * world, n_halos)
+        self.rank, self.world = rank, world
+
+    def snapshot(self, t):
+        from nbody_orbit_analysis_b200 import sharded
+        torch = self._torch
+        pos, rad, _ = self.regions(t)
+        full = self.host.load_snapshot_data(
+            self.host.snapshot_numbers[t], pos, rad, cols=np.arange(self.n_halos))
+        loc, gpos = sharded.shard_snapshot(full, self.rank, self.world)
+        n = len(loc['ids'])
+        dev = {'pos': torch.from_numpy(loc['coordinates'].reshape(-1).copy()),
+               'vel': torch.from_numpy(loc['velocities'].reshape(-1).copy()),
+               'ids': torch.from_numpy(loc['ids'].copy()), 'mass': None,
+               'gpos': torch.from_numpy(gpos.copy())}
+        return dev, n, np.append(loc['region_offsets'], n).astype(np.int64)
+
+
+def _bench_rank(rank, world, port, emul_path, out_dir):
+    import argparse
+    import contextlib
+    import io
+    import sys
+    import ctypes as C
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world), OA_TRACK_IMPL='pjoin',
+                      OA_BENCH_CLOCK_PERIOD='0.05')
+    import bench
+    import exchange_emul
+    import fake_cuda as fc
+    from nbody_orbit_analysis_b200 import pjoin as pj, sharded, synth
+    emul_lib = C.CDLL(emul_path)
+    emul_lib.pj_emul_step.argtypes = [C.POINTER(pj.PJoinArgs), C.c_int]
+    synth.DeviceSynth = ShardedHostSynth
+    pj.TARGET, pj.LAG_PARTICLES = 400, 1 << 12
+    exchange_emul.install(sharded)
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **k: real_init(
+        'gloo', rank=rank, world_size=world)
+    args = argparse.Namespace(
+        gpus=world, steps=4, warmup=3, impl='b200', particles=9000, halos=7,
+        mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=True,
+        cpu_particles=2000)
+    buf = io.StringIO()
+    with fc.install(emul_lib), contextlib.redirect_stdout(buf):
+        bench.run_b200(args)
+    with open(os.path.join(out_dir, 'out_%d' % rank), 'w') as fh:
+        fh.write(buf.getvalue())
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_bench_multi_rank_on_fake_cuda(emul, world, tmp_path, monkeypatch, capsys):
+    """The multi-GPU arm of ``bench.py`` with `world` ranks on the CPU: sharded
+    snapshots, catalogue broadcast one snapshot ahead, asynchronous all-to-all
+    exchange (numpy restatements of its kernels, gloo) and per-rank slices --
+    and the same global event count as ONE rank tracking the whole universe."""
+    import json
+    import torch.multiprocessing as mp
+    from test_sharded_gloo import _free_port
+    mp.spawn(_bench_rank, args=(world, _free_port(), emul._name, str(tmp_path)),
+             nprocs=world, join=True)
+    lines = [ln for ln in open(str(tmp_path / 'out_0')).read().splitlines()
+             if ln.startswith('{')]
+    multi = json.loads(lines[-1])
+    assert multi['n_gpus'] == world and multi['value'] > 0
+    assert multi['e2e']['value'] > 0
+    assert multi['e2e']['events_per_step'] == multi['events_per_step'] > 0
+    assert {'catalogue', 'submit', 'collect', 'start_merge',
+            'finish_merge'} <= set(multi['host_phases_ms_per_step'])
+    for r in range(1, world):          # only rank 0 prints
+        assert '{' not in open(str(tmp_path / ('out_%d' % r))).read()
+
+    # one rank, whole universe
+    import argparse
+    import bench
+    from nbody_orbit_analysis_b200 import synth
+
+    class Whole(HostSynth):
+        def __init__(self, n_particles, n_halos, **kw):
+            HostSynth.__init__(self, n_particles * world, n_halos)
+    monkeypatch.setattr(synth, 'DeviceSynth', Whole)
+    monkeypatch.setattr(pjoin, 'TARGET', 400)
+    monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
+    monkeypatch.setenv('OA_TRACK_IMPL', 'pjoin')
+    monkeypatch.setenv('OA_BENCH_CLOCK_PERIOD', '0.05')
+    for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(
+        gpus=1, steps=4, warmup=3, impl='b200', particles=9000, halos=7,
+        mode='pericentric', depth=2, profile=False, no_e2e=True, no_cpu=True,
+        cpu_particles=2000)
+    with fake_cuda.install(emul):
+        bench.run_b200(args)
+    single = json.loads([ln for ln in capsys.readouterr().out.splitlines()
+                         if ln.startswith('{')][-1])
+    assert single['events_per_step'] == multi['events_per_step']
