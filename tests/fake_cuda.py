@@ -112,7 +112,8 @@ class FakeLib:
     # ---- partitioned join: the emulated kernel --------------------------------
     def oa_pjoin_step(self, args, stream):
         self.calls.append('oa_pjoin_step')
-        return self._emul.pj_emul_step(args, 3)
+        import os
+        return self._emul.pj_emul_step(args, int(os.environ.get('OA_FAKE_CTAS', '3')))
 
     # ---- ordered selection (numpy) ---------------------------------------------
     def _sel(self, marks, n):

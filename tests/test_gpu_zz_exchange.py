@@ -30,7 +30,12 @@ class _Backend:
             self.st = None
 
     def dev(self, arr):
-        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        if t.numel() == 0:
+            # an empty list still lives in a real buffer (the tracker's rings
+            # are never NULL; the C ABI rejects NULL arrays)
+            t = torch.zeros(1, dtype=t.dtype, device=self.device)[:0]
+        return t
 
     def empty(self, n, dtype):
         # poisoned, not zeroed: a kernel must write everything that is read

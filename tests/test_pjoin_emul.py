@@ -319,7 +319,7 @@ def test_small_regions_direct_join(emul):
 def test_partitioned_regions(emul, mode):
     """Partition target lowered to 300 particles: COUNT / SCAN / SCATTER / JOIN
     with up to 2^5 partitions per region, small regions mixed in."""
-    sim = SynthSim(60000, 9, 5, dtype=np.float32, catalogue_dtype=np.float32)
+    sim = SynthSim(40000, 9, 4, dtype=np.float32, catalogue_dtype=np.float32)
     st = run_case(emul, sim, mode, targets=[300])
     assert max(st['bits']) >= 3
 

@@ -231,7 +231,7 @@ def _bench_rank(rank, world, port, emul_path, out_dir):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
                       RANK=str(rank), LOCAL_RANK=str(rank),
                       WORLD_SIZE=str(world), OA_TRACK_IMPL='pjoin',
-                      OA_BENCH_CLOCK_PERIOD='0.05')
+                      OA_BENCH_CLOCK_PERIOD='0.05', OA_FAKE_CTAS='1')
     import bench
     import exchange_emul
     import fake_cuda as fc
@@ -245,7 +245,7 @@ def _bench_rank(rank, world, port, emul_path, out_dir):
     dist.init_process_group = lambda backend, **k: real_init(
         'gloo', rank=rank, world_size=world)
     args = argparse.Namespace(
-        gpus=world, steps=4, warmup=3, impl='b200', particles=9000, halos=7,
+        gpus=world, steps=3, warmup=3, impl='b200', particles=6000, halos=7,
         mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=True,
         cpu_particles=2000)
     buf = io.StringIO()
@@ -290,10 +290,11 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, tmp_path, monkeypatch, capsy
     monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
     monkeypatch.setenv('OA_TRACK_IMPL', 'pjoin')
     monkeypatch.setenv('OA_BENCH_CLOCK_PERIOD', '0.05')
+    monkeypatch.setenv('OA_FAKE_CTAS', '1')
     for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
         monkeypatch.delenv(k, raising=False)
     args = argparse.Namespace(
-        gpus=1, steps=4, warmup=3, impl='b200', particles=9000, halos=7,
+        gpus=1, steps=3, warmup=3, impl='b200', particles=6000, halos=7,
         mode='pericentric', depth=2, profile=False, no_e2e=True, no_cpu=True,
         cpu_particles=2000)
     with fake_cuda.install(emul):
