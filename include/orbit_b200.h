@@ -259,6 +259,9 @@ size_t oa_track_args_size(void);
 #ifndef OA_PJOIN_TARGET
 #define OA_PJOIN_TARGET 2304   /* largest mean partition size                  */
 #endif
+#ifndef OA_PJOIN_TMA
+#define OA_PJOIN_TMA 0         /* 1: table side of a JOIN loaded by one TMA bulk copy */
+#endif
 #define OA_PJOIN_MAX_BITS 12
 
 typedef struct oa_pjoin_region {

@@ -8,6 +8,7 @@ namespace {
 
 struct DevCtx {
     unsigned char* sm;
+    uint32_t parity;        // phase of the TMA mbarrier (same in every thread)
     OA_D int tid() const { return (int)threadIdx.x; }
     OA_D void sync() const { __syncthreads(); }
     OA_D unsigned char* smem() const { return sm; }
@@ -45,6 +46,32 @@ struct DevCtx {
                         "r"(w[6]), "r"(w[7])
                      : "memory");
     }
+    // global -> shared bulk copy, complete for every thread on return.  Called by
+    // all threads of the CTA after a barrier (the destination is not in use).
+    OA_D void bulk_load(void* dst, const void* src, uint32_t bytes) {
+        uint64_t* bar = reinterpret_cast<uint64_t*>(sm + pj::SM_MBAR);
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+        if (bytes == 0) return;
+        if (threadIdx.x == 0) {
+            // earlier generic-proxy accesses to `dst` are ordered before the
+            // async-proxy writes of the copy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         :: "r"(bar_a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+                            "r"(bar_a) : "memory");
+        }
+        uint32_t ok;
+        do {
+            asm volatile("{\n .reg .pred p;\n"
+                         " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                         " selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+        } while (!ok);
+        parity ^= 1u;
+    }
     OA_D int64_t ld_last(const int64_t* p) const { return __ldcs(p); }
     OA_D float ld_last(const float* p) const { return __ldcs(p); }
     // read-only for this launch and touched once: streaming, no L1 allocation
@@ -62,6 +89,15 @@ oa_pjoin_kernel(const __grid_constant__ oa_pjoin_args a, const __grid_constant__
     extern __shared__ __align__(128) unsigned char smem[];
     DevCtx cx;
     cx.sm = smem;
+    cx.parity = 0;
+#if OA_PJOIN_TMA
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(smem + pj::SM_MBAR)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+#endif
     pj::run(cx, a, k, w);
 }
 

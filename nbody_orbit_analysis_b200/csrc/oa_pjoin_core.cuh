@@ -91,7 +91,8 @@ constexpr int SM_SCAN_VAL = 0;
 constexpr int SM_SCAN_PART = SM_SCAN_VAL + (1 << MAX_BITS) * 4;
 constexpr int SM_BODY = SM_JOIN_END > SM_SCATTER_END ? SM_JOIN_END : SM_SCATTER_END;
 constexpr int SM_BCAST = SM_BODY;            // 4 words of CTA-wide broadcast
-constexpr int SM_BYTES = SM_BCAST + 16;
+constexpr int SM_MBAR = SM_BCAST + 16;       // one mbarrier (TMA build of the table)
+constexpr int SM_BYTES = SM_MBAR + 16;
 static_assert(SM_JOIN_SLOT % 16 == 0 && SM_HIST % 4 == 0, "alignment");
 static_assert(SM_SCAN_PART + THREADS * 4 <= SM_BODY, "scan scratch");
 static_assert(SCAN_PER * THREADS == (1 << MAX_BITS), "scan: whole values per thread");
@@ -509,6 +510,11 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
     for (uint32_t bs = pb; bs < pe; bs += REC_CAP) {
         const int nb = (int)(pe - bs < (uint32_t)REC_CAP ? pe - bs : (uint32_t)REC_CAP);
         for (int s = cx.tid(); s < SLOTS; s += THREADS) slots[s] = EMPTY;
+#if OA_PJOIN_TMA
+        // one TMA bulk copy (cp.async.bulk + mbarrier) instead of register staging;
+        // the slot clear above overlaps it
+        cx.bulk_load(s_rec, rec_prev + bs, (uint32_t)nb * 32u);
+#else
         {   // previous records -> shared memory, 16 bytes per thread and step
             const U4* src = reinterpret_cast<const U4*>(rec_prev + bs);
             U4* dst = reinterpret_cast<U4*>(s_rec);
@@ -521,6 +527,7 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
                 }
             }
         }
+#endif
         cx.sync();
         for (int i = cx.tid(); i < nb; i += THREADS) {
             const uint32_t h = (uint32_t)mix64((uint64_t)s_rec[i].id);

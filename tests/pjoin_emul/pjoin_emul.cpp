@@ -39,6 +39,10 @@ struct HostCtx {
     void fail() const { abort(); }
     uint32_t ld_cg(const uint32_t* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
     pj::U4 ld_stream(const pj::U4* p) const { return *p; }
+    void bulk_load(void* dst, const void* src, uint32_t bytes) const {
+        if (tid_ == 0) memcpy(dst, src, bytes);
+        sync();
+    }
     int64_t ld_last(const int64_t* p) const { return *p; }
     float ld_last(const float* p) const { return *p; }
     pj::Rec load_rec_cg(const pj::Rec* p) const { return *p; }

@@ -44,7 +44,7 @@ NO_EVENT = 0x8000
 
 SMALL_SHAPE = ['-DOA_PJOIN_THREADS=256', '-DOA_PJOIN_MIN_CTAS=4',
                '-DOA_PJOIN_TILE=1024', '-DOA_PJOIN_REC_CAP=1408',
-               '-DOA_PJOIN_TARGET=1152']
+               '-DOA_PJOIN_TARGET=1152', '-DOA_PJOIN_TMA=1']
 
 
 def build_emul(flags=(), tag=''):
