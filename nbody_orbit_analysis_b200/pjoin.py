@@ -20,7 +20,11 @@ CTILE = 8192           # OA_PJOIN_CTILE (particles per COUNT item)
 REC_CAP = 2944         # OA_PJOIN_REC_CAP
 TARGET = 2304          # OA_PJOIN_TARGET: particles per partition at most (mean)
 MAX_BITS = 12          # OA_PJOIN_MAX_BITS
-LAG_PARTICLES = 1 << 19   # particles per group of regions (pipeline granularity)
+# particles per group of regions: the pipeline granularity (a group's COUNT,
+# SCAN, SCATTER and JOIN items are one superstep apart; three groups of new
+# records wait in L2).  OA_PJOIN_LAG overrides it (tuning).
+import os as _os
+LAG_PARTICLES = int(_os.environ.get('OA_PJOIN_LAG', 1 << 19))
 
 JOIN, SCATTER, SCAN, COUNT = 0, 1, 2, 3
 _LAG = (3, 2, 1, 0)    # superstep s holds stage `st` of group s - _LAG[st]
