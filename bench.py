@@ -524,6 +524,9 @@ def run_b200(args):
                'd2h_bytes_per_step': int(ev_per_step * 10 + args.halos * 8 + 8),
                'ms_per_step': e2e_run['ms'] / K,
                'events_per_step': ev_per_step}
+        # what the end-to-end number is bound by: the host->device link
+        e2e['h2d_gb_per_s_per_gpu'] = e2e['h2d_bytes_per_step'] / (
+            e2e['ms_per_step'] * 1e-3) / 1e9
         if e2e_run['events'] != dev_run['events']:
             e2e['warning'] = 'event count differs from the device-resident run'
 
