@@ -469,18 +469,16 @@ PJ_FN void probe_one(const oa_pjoin_args& a, const Rec* s_rec, const uint32_t* s
                      const Rec& cur, Rec* cur_global) {
     const uint32_t h = (uint32_t)mix64((uint64_t)cur.id);
     uint32_t s = h & (SLOTS - 1);
-    int hit = -1;
+    Rec prev;
     for (;;) {
         const uint32_t v = slots[s];
-        if (v == EMPTY) break;
-        if ((v >> 12) == (h >> 12) && s_rec[v & 0xFFFu].id == cur.id) {
-            hit = (int)(v & 0xFFFu);
-            break;
+        if (v == EMPTY) return;             // newly entered: accumulator stays 0
+        if ((v >> 12) == (h >> 12)) {       // 20-bit fingerprint: the record is read
+            prev = s_rec[v & 0xFFFu];       // once, its ID settles the match
+            if (prev.id == cur.id) break;
         }
         s = (s + 1) & (SLOTS - 1);
     }
-    if (hit < 0) return;                    // newly entered: accumulator stays 0
-    const Rec prev = s_rec[hit];
     const float pr[3] = {prev.rx, prev.ry, prev.rz}, cr[3] = {cur.rx, cur.ry, cur.rz};
     const float dang = acosf(dot3f(pr, cr));
     bool ev;
