@@ -542,6 +542,10 @@ class OrbitTracker:
         done.record(self._main())
         p.compacted = done
         self.copy_stream.wait_event(done)
+        if prev is not None and prev.pjoin and d_small is not None:
+            # the event gather above read the PREVIOUS snapshot's ID array: its
+            # ring slot may only be refilled by the upload stream after this
+            self._consumed[(self._step - 1) % self.RING] = done
         p.h_ids = p.h_ang = None
         p.n_spec = 0
         if d_small is not None:
