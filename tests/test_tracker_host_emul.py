@@ -302,3 +302,28 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, tmp_path, monkeypatch, capsy
     single = json.loads([ln for ln in capsys.readouterr().out.splitlines()
                          if ln.startswith('{')][-1])
     assert single['events_per_step'] == multi['events_per_step']
+
+
+@pytest.mark.parametrize('dt,cdt', [(np.float32, np.float32),
+                                    (np.float64, np.float64),
+                                    (np.float32, np.float64)])
+def test_onthefly_and_f64_branches_host_code_runs(emul, dt, cdt):
+    """Host code of the remaining ``submit`` variants with no-op kernels:
+    on-the-fly (derived bulk velocity, per-match angle buffer), float64 frames,
+    mass arrays, vanishing halos."""
+    from nbody_orbit_analysis_b200.tracker import OrbitTracker
+    sim = SynthSim(6000, 5, 3, dtype=dt, catalogue_dtype=cdt, mass_array=True)
+    with fake_cuda.install(emul) as fake:
+        for onthefly in (True, False):
+            trk = OrbitTracker(device='cpu', onthefly=onthefly, impl='hash')
+            for t, sn in enumerate(sim.snapshot_numbers):
+                exists = np.arange(5) if t != 1 else np.array([0, 2, 3])
+                pos, rad, bulk = sim.regions(sn, sim.main_branches[t][exists])
+                snap = sim.load_snapshot_data(sn, pos, rad)
+                res = trk.step(snap, exists, pos, None if onthefly else bulk,
+                               0.0 if onthefly else 0.07, diagnostics=onthefly)
+                assert res.n == len(snap['ids'])
+                assert list(res.hinds) == ([] if t == 0 else
+                                           list(range(len(exists))) if t == 1
+                                           else [0, 2, 3])
+        assert fake.calls.count('oa_bulk_velocity') == 3
