@@ -35,7 +35,7 @@ if [ -f variants/liborbit_b200_small.so ]; then
   echo "bench pjoin small rc=$?"; grep -o '"value": [0-9.e+]*\|"kernel_ms": [0-9.]*' gpurun_out/r2_bench_pjoin_small.log | head -2
 fi
 for impl in hash pjoin; do
-  OA_TRACK_IMPL=$impl timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  OA_TRACK_IMPL=$impl timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
       --log-file gpurun_out/r2_launches_$impl.csv python bench.py --no-e2e --no-cpu --steps 4 --warmup 3 \
       > gpurun_out/r2_ncu_launches_$impl.log 2>&1
 done
