@@ -142,9 +142,9 @@ def test_bench_end_to_end_on_fake_cuda(emul, pjoin_env, monkeypatch, capsys):
     monkeypatch.delenv('WORLD_SIZE', raising=False)
     monkeypatch.setenv('OA_BENCH_CLOCK_PERIOD', '0.05')
     args = argparse.Namespace(
-        gpus=1, steps=3, warmup=3, impl='b200', particles=20000, halos=12,
+        gpus=1, steps=3, warmup=3, impl='b200', particles=10000, halos=8,
         mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=False,
-        cpu_particles=4000)
+        cpu_particles=3000)
     with fake_cuda.install(emul):
         bench.run_b200(args)
     line = json.loads([ln for ln in capsys.readouterr().out.splitlines()
@@ -246,8 +246,8 @@ def _bench_rank(rank, world, port, emul_path, out_dir):
         'gloo', rank=rank, world_size=world)
     args = argparse.Namespace(
         gpus=world, steps=3, warmup=3, impl='b200', particles=6000, halos=7,
-        mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=True,
-        cpu_particles=2000)
+        mode='pericentric', depth=2, profile=False, no_e2e=world > 2,
+        no_cpu=True, cpu_particles=2000)
     buf = io.StringIO()
     with fc.install(emul_lib), contextlib.redirect_stdout(buf):
         bench.run_b200(args)
@@ -270,8 +270,10 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, tmp_path, monkeypatch, capsy
              if ln.startswith('{')]
     multi = json.loads(lines[-1])
     assert multi['n_gpus'] == world and multi['value'] > 0
-    assert multi['e2e']['value'] > 0
-    assert multi['e2e']['events_per_step'] == multi['events_per_step'] > 0
+    assert multi['events_per_step'] > 0
+    if world == 2:
+        assert multi['e2e']['value'] > 0
+        assert multi['e2e']['events_per_step'] == multi['events_per_step']
     assert {'catalogue', 'submit', 'collect', 'start_merge',
             'finish_merge'} <= set(multi['host_phases_ms_per_step'])
     for r in range(1, world):          # only rank 0 prints
