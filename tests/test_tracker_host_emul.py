@@ -329,3 +329,39 @@ def test_onthefly_and_f64_branches_host_code_runs(emul, dt, cdt):
                                            list(range(len(exists))) if t == 1
                                            else [0, 2, 3])
         assert fake.calls.count('oa_bulk_velocity') == 3
+
+
+def test_pjoin_empty_block_and_vanishing_halo(emul, pjoin_env, monkeypatch, tmp_path):
+    """A halo disappears for one snapshot and comes back; a (large, partitioned)
+    block becomes empty from the second snapshot on -- partition counts never
+    shrink, so an empty block keeps its partitions (all of size 0)."""
+    from nbody_orbit_analysis_b200 import track_orbits
+    monkeypatch.setattr(pjoin, 'TARGET', 300)
+    monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
+    sim = SynthSim(20000, 6, 6, dtype=np.float32, catalogue_dtype=np.float32)
+    mb = sim.main_branches.copy()
+    mb[2, 4] = -1          # halo 4 vanishes at t=2 and returns at t=3
+    base_load = sim.load_snapshot_data
+    calls = {'n': 0}
+
+    def load(snap_no, pos, rad):
+        s = base_load(snap_no, pos, rad)
+        calls['n'] += 1
+        offs = np.append(s['region_offsets'], len(s['ids']))
+        if len(offs) > 3 and snap_no != sim.snapshot_numbers[0]:
+            lo, hi = offs[1], offs[2]              # empty the second block
+            keep = np.ones(len(s['ids']), dtype=bool)
+            keep[lo:hi] = False
+            for k in ('ids', 'coordinates', 'velocities'):
+                s[k] = s[k][keep]
+            offs[2:] -= hi - lo
+            s['region_offsets'] = offs[:-1]
+        return s
+
+    f_dev, f_cpu = str(tmp_path / 'd.h5'), str(tmp_path / 'c.h5')
+    with fake_cuda.install(emul):
+        track_orbits.track_orbits(sim.snapshot_numbers, mb, sim.regions, load,
+                                  f_dev, verbose=False, device='cpu')
+    oracle.track_orbits(sim.snapshot_numbers, mb, sim.regions, load, f_cpu,
+                        storage=storage)
+    compare_track_trees(storage.tree(f_dev), storage.tree(f_cpu), data_f64=False)
