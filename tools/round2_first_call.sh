@@ -25,15 +25,22 @@ except Exception as e:
     print(impl, 'FAILED', e)
 PY
 done
-# the 4-CTAs-per-SM build of the same kernel (built here, before the call:
+# tuning builds of the same kernel, if present (build them here, before the call):
 #   python -m nbody_orbit_analysis_b200._build --out variants/liborbit_b200_small.so \
 #     -DOA_PJOIN_THREADS=256 -DOA_PJOIN_MIN_CTAS=4 -DOA_PJOIN_TILE=1024 \
-#     -DOA_PJOIN_REC_CAP=1408 -DOA_PJOIN_TARGET=1152)
-if [ -f variants/liborbit_b200_small.so ]; then
-  OA_LIB_PATH=$PWD/variants/liborbit_b200_small.so OA_TRACK_IMPL=pjoin timeout 600 \
-      python bench.py --no-e2e --no-cpu > gpurun_out/r2_bench_pjoin_small.log 2>&1
-  echo "bench pjoin small rc=$?"; grep -o '"value": [0-9.e+]*\|"kernel_ms": [0-9.]*' gpurun_out/r2_bench_pjoin_small.log | head -2
-fi
+#     -DOA_PJOIN_REC_CAP=1408 -DOA_PJOIN_TARGET=1152
+#   python -m nbody_orbit_analysis_b200._build --out variants/liborbit_b200_tma.so -DOA_PJOIN_TMA=1
+for lib in variants/liborbit_b200_*.so; do
+  [ -f "$lib" ] || continue
+  tag=$(basename "$lib" .so)
+  OA_LIB_PATH=$PWD/$lib OA_TEST_PJOIN=1 OA_TRACK_IMPL=pjoin timeout 300 python -m pytest \
+      tests/test_gpu_zzz_pjoin.py -x -q -k "at_scale" > gpurun_out/r2_tests_$tag.log 2>&1
+  echo "$tag parity rc=$?"
+  OA_LIB_PATH=$PWD/$lib OA_TRACK_IMPL=pjoin timeout 600 python bench.py --no-e2e --no-cpu \
+      > gpurun_out/r2_bench_$tag.log 2>&1
+  echo "$tag bench rc=$?"
+  grep -o '"value": [0-9.e+]*\|"kernel_ms": [0-9.]*' gpurun_out/r2_bench_$tag.log | head -2
+done
 for impl in hash pjoin; do
   OA_TRACK_IMPL=$impl timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
       --log-file gpurun_out/r2_launches_$impl.csv python bench.py --no-e2e --no-cpu --steps 4 --warmup 3 \
