@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 14
+#define OA_ABI_VERSION 15
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -230,8 +230,15 @@ size_t oa_track_args_size(void);
  *                (bits_cur > 0 ? ceil(cur_count / OA_PJOIN_TILE) : 0);
  *   count_first = the same for COUNT tiles of OA_PJOIN_CTILE particles;
  *   scan_first = exclusive prefix of (bits_cur > 0);
- *   join_first = exclusive prefix of JOIN items (bits_cur == 0: 1;
- *                else bits_prev >= 0 ? 1 << bits_prev : 0).
+ *   join_first = exclusive prefix of JOIN items (bits_cur > 0:
+ *                bits_prev >= 0 ? 1 << bits_prev : 0; bits_cur == 0: 1 for the
+ *                first region of a PACK, 0 for its other members);
+ *   pack_len   = consecutive small regions (bits_cur == 0, same group) handled by
+ *                one item: at most OA_PJOIN_PACK_MAX regions, OA_PJOIN_TILE
+ *                particles and OA_PJOIN_REC_CAP previous records together -- so
+ *                that a catalogue of many tiny halos does not cost one CTA-wide
+ *                item per halo.  A region that exceeds these limits alone is a
+ *                pack of one.
  * Regions are grouped (group_first: first region of each group + n_regions);
  * range_start[4 * s + stage] = first ticket of stage `stage` (0 JOIN, 1
  * SCATTER, 2 SCAN, 3 COUNT) in superstep s, which holds the items of group
@@ -263,6 +270,7 @@ size_t oa_track_args_size(void);
 #define OA_PJOIN_TMA 0         /* 1: table side of a JOIN loaded by one TMA bulk copy */
 #endif
 #define OA_PJOIN_MAX_BITS 12
+#define OA_PJOIN_PACK_MAX 32   /* regions per pack of small regions            */
 
 typedef struct oa_pjoin_region {
     uint32_t pb_cur;
@@ -273,7 +281,9 @@ typedef struct oa_pjoin_region {
     uint32_t join_first;
     uint32_t scan_first;
     uint32_t count_first;
-} oa_pjoin_region;        /* 32 bytes */
+    uint32_t pack_len;    /* bits_cur == 0: regions of the pack that starts here */
+    uint32_t reserved[3]; /*               (0: member of an earlier pack)        */
+} oa_pjoin_region;        /* 48 bytes */
 
 typedef struct oa_pjoin_args {
     const float* pos;       /* (n_cur,3)                                      */
@@ -314,8 +324,9 @@ typedef struct oa_pjoin_args {
 /* The plan on the HOST (all pointers are host pointers; no CUDA call): fills
  * rows[n_regions + 1], bits_out / pb_out [n_regions] (kept by the caller for the
  * next snapshot), group_first (capacity n_regions + 1) and range_start (capacity
- * 4 * (n_regions + 3) + 1).  prev_bits[j] / prev_pb[j]: partition bits and first
- * part_off entry of the same halo's previous block, bits -1 = none.  Groups are
+ * 4 * (n_regions + 3) + 1).  prev_bits[j] / prev_pb[j] / prev_counts[j]: partition
+ * bits, first part_off entry and length of the same halo's previous block
+ * (bits -1 = none).  Groups are
  * runs of regions whose first particle lies in the same window of
  * `lag_particles` particles. */
 typedef struct oa_pjoin_plan_info {
@@ -327,6 +338,7 @@ typedef struct oa_pjoin_plan_info {
 } oa_pjoin_plan_info;
 int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
                        const int32_t* prev_bits, const int64_t* prev_pb,
+                       const int64_t* prev_counts,
                        int64_t target, int64_t lag_particles,
                        oa_pjoin_region* rows, int32_t* bits_out, int64_t* pb_out,
                        uint32_t* group_first, uint32_t* range_start,

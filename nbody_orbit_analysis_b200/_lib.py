@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 14
+ABI_VERSION = 15
 BUCKET_LOAD = 3          # OA_BUCKET_LOAD
 
 
@@ -170,8 +170,8 @@ _sig('oa_select_gather_events_ids', C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
      _vp)
 _sig('oa_pjoin_workspace_bytes', _sz, C.c_int, _i64, C.c_uint32)
 _sig('oa_pjoin_args_size', _sz)
-_sig('oa_pjoin_plan_host', C.c_int, _vp, C.c_int, _vp, _vp, _i64, _i64, _vp, _vp,
-     _vp, _vp, _vp, _vp)
+_sig('oa_pjoin_plan_host', C.c_int, _vp, C.c_int, _vp, _vp, _vp, _i64, _i64, _vp,
+     _vp, _vp, _vp, _vp, _vp)
 _sig('oa_pjoin_step', C.c_int, _vp, _vp)
 from . import pjoin as _pjoin        # noqa: E402  (struct mirror of oa_pjoin_args)
 if lib.oa_pjoin_args_size() != C.sizeof(_pjoin.PJoinArgs):

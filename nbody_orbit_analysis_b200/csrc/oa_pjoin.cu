@@ -136,17 +136,20 @@ extern "C" void oa_pjoin_config(int32_t* out8) {
 // compare with this function)
 extern "C" int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
                                   const int32_t* prev_bits, const int64_t* prev_pb,
+                                  const int64_t* prev_counts,
                                   int64_t target, int64_t lag_particles,
                                   oa_pjoin_region* rows, int32_t* bits_out, int64_t* pb_out,
                                   uint32_t* group_first, uint32_t* range_start,
                                   oa_pjoin_plan_info* info) {
     OA_REQUIRE(n_regions >= 0 && target >= 1 && lag_particles >= 1 && rows && group_first &&
                range_start && info && (n_regions == 0 || (offsets && prev_bits && prev_pb &&
-                                                          bits_out && pb_out)),
+                                                          prev_counts && bits_out && pb_out)),
                "oa_pjoin_plan_host: bad arguments");
     uint64_t pb = 0, tiles = 0, ctiles = 0, joins = 0, scans = 0;
     int n_groups = 0, max_bits = 0;
     int64_t gid_prev = -1;
+    int leader = -1;                       // first region of the open pack
+    int64_t pack_cur = 0, pack_prev = 0;
     for (int j = 0; j < n_regions; ++j) {
         const int64_t len = offsets[j + 1] - offsets[j];
         OA_REQUIRE(len >= 0, "oa_pjoin_plan_host: offsets must not decrease");
@@ -164,20 +167,40 @@ extern "C" int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
         r.count_first = (uint32_t)ctiles;
         r.join_first = (uint32_t)joins;
         r.scan_first = (uint32_t)scans;
+        r.pack_len = 0;
+        r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
         bits_out[j] = bits;
         pb_out[j] = (int64_t)pb;
         pb += ((uint64_t)1 << bits) + 1;
+        const int64_t gid = offsets[j] / lag_particles;
+        const bool new_group = j == 0 || gid != gid_prev;
+        if (new_group) group_first[n_groups++] = (uint32_t)j;
+        gid_prev = gid;
         if (bits > 0) {
             tiles += (uint64_t)((len + OA_PJOIN_TILE - 1) / OA_PJOIN_TILE);
             ctiles += (uint64_t)((len + OA_PJOIN_CTILE - 1) / OA_PJOIN_CTILE);
             scans += 1;
             if (prev_bits[j] >= 0) joins += (uint64_t)1 << prev_bits[j];
+            leader = -1;
         } else {
-            joins += 1;
+            // packs of consecutive small regions of one group
+            const int64_t plen = prev_bits[j] >= 0 ? prev_counts[j] : 0;
+            const bool fits = leader >= 0 && !new_group &&
+                              rows[leader].pack_len < OA_PJOIN_PACK_MAX &&
+                              pack_cur + len <= OA_PJOIN_TILE &&
+                              pack_prev + plen <= OA_PJOIN_REC_CAP;
+            if (fits) {
+                rows[leader].pack_len += 1;
+                pack_cur += len;
+                pack_prev += plen;
+            } else {
+                leader = j;
+                r.pack_len = 1;
+                pack_cur = len;
+                pack_prev = plen;
+                joins += 1;
+            }
         }
-        const int64_t gid = offsets[j] / lag_particles;
-        if (j == 0 || gid != gid_prev) group_first[n_groups++] = (uint32_t)j;
-        gid_prev = gid;
     }
     OA_REQUIRE(pb < ((uint64_t)1 << 32) && tiles + ctiles + joins + scans < ((uint64_t)1 << 32),
                "oa_pjoin_plan_host: plan does not fit 32-bit counters");
@@ -189,6 +212,8 @@ extern "C" int oa_pjoin_plan_host(const int64_t* offsets, int n_regions,
     e.count_first = (uint32_t)ctiles;
     e.join_first = (uint32_t)joins;
     e.scan_first = (uint32_t)scans;
+    e.pack_len = 0;
+    e.reserved[0] = e.reserved[1] = e.reserved[2] = 0;
     group_first[n_groups] = (uint32_t)n_regions;
 
     // ticket ranges: superstep s holds JOIN of group s-3, SCATTER s-2, SCAN s-1, COUNT s

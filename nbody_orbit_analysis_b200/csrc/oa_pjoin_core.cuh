@@ -92,7 +92,9 @@ constexpr int SM_SCAN_PART = SM_SCAN_VAL + (1 << MAX_BITS) * 4;
 constexpr int SM_BODY = SM_JOIN_END > SM_SCATTER_END ? SM_JOIN_END : SM_SCATTER_END;
 constexpr int SM_BCAST = SM_BODY;            // 4 words of CTA-wide broadcast
 constexpr int SM_MBAR = SM_BCAST + 16;       // one mbarrier (TMA build of the table)
-constexpr int SM_BYTES = SM_MBAR + 16;
+constexpr int PACK_MAX = OA_PJOIN_PACK_MAX;  // small regions per work item
+constexpr int SM_PACK = SM_MBAR + 16;        // member tables of a pack: 3 x (PACK_MAX + 1) words
+constexpr int SM_BYTES = SM_PACK + 3 * (PACK_MAX + 1) * 4 + 4;
 static_assert(SM_JOIN_SLOT % 16 == 0 && SM_HIST % 4 == 0, "alignment");
 static_assert(SM_SCAN_PART + THREADS * 4 <= SM_BODY, "scan scratch");
 static_assert(SCAN_PER * THREADS == (1 << MAX_BITS), "scan: whole values per thread");
@@ -465,8 +467,11 @@ PJ_FN void stage_scatter(CX& cx, const oa_pjoin_args& a, const Const& k, const W
 
 // one current record against the shared-memory table of previous records:
 // compare_radial_velocities + calc_angles (track_orbits.py:311-325, 330-351)
+// (prev_lo, prev_cnt): block range of the halo's previous block -- a table that
+// holds several halos (a pack) may contain the same ID once per halo
 PJ_FN void probe_one(const oa_pjoin_args& a, const Rec* s_rec, const uint32_t* slots,
-                     const Rec& cur, Rec* cur_global) {
+                     const Rec& cur, Rec* cur_global, uint32_t prev_lo = 0u,
+                     uint32_t prev_cnt = 0xFFFFFFFFu) {
     const uint32_t h = (uint32_t)mix64((uint64_t)cur.id);
     uint32_t s = h & (SLOTS - 1);
     Rec prev;
@@ -475,7 +480,7 @@ PJ_FN void probe_one(const oa_pjoin_args& a, const Rec* s_rec, const uint32_t* s
         if (v == EMPTY) return;             // newly entered: accumulator stays 0
         if ((v >> 12) == (h >> 12)) {       // 20-bit fingerprint: the record is read
             prev = s_rec[v & 0xFFFu];       // once, its ID settles the match
-            if (prev.id == cur.id) break;
+            if (prev.id == cur.id && prev.pos - prev_lo < prev_cnt) break;
         }
         s = (s + 1) & (SLOTS - 1);
     }
@@ -491,6 +496,29 @@ PJ_FN void probe_one(const oa_pjoin_args& a, const Rec* s_rec, const uint32_t* s
     }
     // angle accumulator + "matched" flag: the last word of the record
     reinterpret_cast<uint32_t*>(cur_global)[7] = (uint32_t)half_bits(run) | (1u << 16);
+}
+
+// every staged previous record -> open-addressing table (slot = 20-bit
+// fingerprint | 12-bit record index)
+template <class CX>
+PJ_FN void table_insert_all(CX& cx, const Rec* s_rec, uint32_t* slots, int nb) {
+    for (int i = cx.tid(); i < nb; i += THREADS) {
+        const uint32_t h = (uint32_t)mix64((uint64_t)s_rec[i].id);
+        const uint32_t val = ((h >> 12) << 12) | (uint32_t)i;
+        uint32_t s = h & (SLOTS - 1);
+        while (cx.atomic_cas(&slots[s], EMPTY, val) != EMPTY) s = (s + 1) & (SLOTS - 1);
+    }
+}
+
+// last m in [0, n) with arr[m] <= x (arr non-decreasing, arr[0] <= x): equal
+// entries belong to empty members and are skipped by taking the last
+PJ_FN int member_of(const uint32_t* arr, int n, uint32_t x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (arr[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
 
 // ---- JOIN ----------------------------------------------------------------------------------------
@@ -527,12 +555,7 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
         }
 #endif
         cx.sync();
-        for (int i = cx.tid(); i < nb; i += THREADS) {
-            const uint32_t h = (uint32_t)mix64((uint64_t)s_rec[i].id);
-            const uint32_t val = ((h >> 12) << 12) | (uint32_t)i;
-            uint32_t s = h & (SLOTS - 1);
-            while (cx.atomic_cas(&slots[s], EMPTY, val) != EMPTY) s = (s + 1) & (SLOTS - 1);
-        }
+        table_insert_all(cx, s_rec, slots, nb);
         cx.sync();
         // one record of lookahead: the load of the next record is in flight while
         // this one is probed
@@ -551,6 +574,74 @@ PJ_FN void join_ranges(CX& cx, const oa_pjoin_args& a, uint32_t pb, uint32_t pe,
     }
 }
 
+// ---- a pack of small regions -------------------------------------------------------------------
+// `L` consecutive regions j .. j+L-1, each a single partition in block order, at
+// most TILE particles and REC_CAP previous records together (host plan): one tile
+// of inputs, one table that holds the previous blocks of all members back to back.
+template <class CX>
+PJ_FN void stage_pack(CX& cx, const oa_pjoin_args& a, const Const& k, int j, int L) {
+    uint32_t* m_cur = reinterpret_cast<uint32_t*>(cx.smem() + SM_PACK);   // block starts + end
+    uint32_t* m_pre = m_cur + (PACK_MAX + 1);      // prefix of previous-record counts
+    uint32_t* m_pbeg = m_pre + (PACK_MAX + 1);     // previous block starts
+    Rec* s_rec = reinterpret_cast<Rec*>(cx.smem() + SM_JOIN_REC);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(cx.smem() + SM_JOIN_SLOT);
+    Rec* rec_cur = static_cast<Rec*>(a.rec_cur);
+    const Rec* rec_prev = static_cast<const Rec*>(a.rec_prev);
+    if (cx.tid() == 0) {
+        uint32_t acc = 0;
+        for (int m = 0; m < L; ++m) {
+            const oa_region& R = a.regions[j + m];
+            const oa_pjoin_region& P = a.plan[j + m];
+            const uint32_t pc = (P.bits_prev >= 0 && R.prev_count > 0) ? (uint32_t)R.prev_count : 0u;
+            m_cur[m] = (uint32_t)R.cur_begin;
+            m_pre[m] = acc;
+            m_pbeg[m] = pc ? (uint32_t)R.prev_begin : 0u;
+            acc += pc;
+            a.part_off_cur[P.pb_cur] = (uint32_t)R.cur_begin;
+            a.part_off_cur[P.pb_cur + 1] = (uint32_t)(R.cur_begin + R.cur_count);
+        }
+        const oa_region& last = a.regions[j + L - 1];
+        m_cur[L] = (uint32_t)(last.cur_begin + last.cur_count);
+        m_pre[L] = acc;
+    }
+    cx.sync();
+    const uint32_t begin = m_cur[0];
+    const int cnt = (int)(m_cur[L] - begin);
+    const int nb = (int)m_pre[L];
+    // frame + records of all members (block order), one tile
+    load_tile(cx, a, (int64_t)begin, cnt);
+    cx.sync();
+    for (int i = cx.tid(); i < cnt; i += THREADS) {
+        const uint32_t c = begin + (uint32_t)i;
+        const int m = member_of(m_cur, L, c);
+        cx.store_rec(rec_cur + c, make_record(cx, a, k, a.regions[j + m], i, (int64_t)c));
+        a.mark_cur[c] = NO_EVENT;
+    }
+    cx.sync();
+    if (nb == 0) return;                           // no member has a previous block
+    for (int s = cx.tid(); s < SLOTS; s += THREADS) slots[s] = EMPTY;
+    {
+        U4* dst = reinterpret_cast<U4*>(s_rec);
+        for (int q = cx.tid(); q < 2 * nb; q += THREADS) {
+            const uint32_t r = (uint32_t)q >> 1;
+            const int m = member_of(m_pre, L, r);
+            const U4* src = reinterpret_cast<const U4*>(rec_prev + m_pbeg[m] + (r - m_pre[m]));
+            dst[q] = cx.ld_stream(src + (q & 1));
+        }
+    }
+    cx.sync();
+    table_insert_all(cx, s_rec, slots, nb);
+    cx.sync();
+    for (int i = cx.tid(); i < cnt; i += THREADS) {
+        const uint32_t c = begin + (uint32_t)i;
+        const int m = member_of(m_cur, L, c);
+        const uint32_t pc = m_pre[m + 1] - m_pre[m];
+        if (pc == 0) continue;                     // a halo without a previous block
+        const Rec cur = cx.load_rec_cg(rec_cur + c);
+        probe_one(a, s_rec, slots, cur, rec_cur + c, m_pbeg[m], pc);
+    }
+}
+
 template <class CX>
 PJ_FN void stage_join(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w, int j,
                       uint32_t q) {
@@ -564,6 +655,10 @@ PJ_FN void stage_join(CX& cx, const oa_pjoin_args& a, const Const& k, const Work
         const uint32_t cb = cx.ld_cg(&a.part_off_cur[P.pb_cur + (q << db)]);
         const uint32_t ce = cx.ld_cg(&a.part_off_cur[P.pb_cur + ((q + 1) << db)]);
         join_ranges(cx, a, pb, pe, cb, ce);
+        return;
+    }
+    if (P.pack_len > 1) {
+        stage_pack(cx, a, k, j, (int)P.pack_len);
         return;
     }
     // small region (one partition = the block itself, in block order): frame and

@@ -20,6 +20,7 @@ CTILE = 8192           # OA_PJOIN_CTILE (particles per COUNT item)
 REC_CAP = 2944         # OA_PJOIN_REC_CAP
 TARGET = 2304          # OA_PJOIN_TARGET: particles per partition at most (mean)
 MAX_BITS = 12          # OA_PJOIN_MAX_BITS
+PACK_MAX = 32          # OA_PJOIN_PACK_MAX: small regions per work item
 # particles per group of regions: the pipeline granularity (a group's COUNT,
 # SCAN, SCATTER and JOIN items are one superstep apart; three groups of new
 # records wait in L2).  OA_PJOIN_LAG overrides it (tuning).
@@ -33,8 +34,9 @@ PLAN_DTYPE = np.dtype([
     ('pb_cur', np.uint32), ('pb_prev', np.uint32), ('bits_cur', np.int32),
     ('bits_prev', np.int32), ('tile_first', np.uint32),
     ('join_first', np.uint32), ('scan_first', np.uint32),
-    ('count_first', np.uint32)])
-assert PLAN_DTYPE.itemsize == 32
+    ('count_first', np.uint32), ('pack_len', np.uint32),
+    ('reserved', np.uint32, (3,))])
+assert PLAN_DTYPE.itemsize == 48
 
 _vp, _i64, _i32, _u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32
 
@@ -89,10 +91,13 @@ def need_bits(lens, target=None):
                       MAX_BITS).astype(np.int32)
 
 
-def make_plan(offsets, prev_bits, prev_pb, target=None, lag_particles=None):
+def make_plan(offsets, prev_bits, prev_pb, prev_counts=None, target=None,
+              lag_particles=None):
     """``offsets``: (n_regions + 1,) block starts + n.  ``prev_bits`` /
-    ``prev_pb``: per region of THIS snapshot, the partition bits and the first
-    partition-offset entry of the same halo's previous block (bits -1: none)."""
+    ``prev_pb`` / ``prev_counts``: per region of THIS snapshot, the partition
+    bits, the first partition-offset entry and the length of the same halo's
+    previous block (bits -1: none).  numpy restatement of
+    ``oa_pjoin_plan_host`` (the tests compare the two)."""
     target = TARGET if target is None else target
     lag_particles = LAG_PARTICLES if lag_particles is None else lag_particles
     offsets = np.asarray(offsets, dtype=np.int64)
@@ -107,6 +112,27 @@ def make_plan(offsets, prev_bits, prev_pb, target=None, lag_particles=None):
     ctiles = np.where(big, -(-lens // CTILE), 0)
     joins = np.where(big, np.where(has_prev,
                                    np.int64(1) << np.maximum(prev_bits, 0), 0), 1)
+    # groups of consecutive regions (by the position of their first particle)
+    gid = offsets[:-1] // lag_particles
+    # packs of consecutive small regions of one group (greedy, like the C loop)
+    prev_counts = np.zeros(n_h, dtype=np.int64) if prev_counts is None else \
+        np.where(has_prev, np.asarray(prev_counts, dtype=np.int64), 0)
+    pack_len = np.zeros(n_h, dtype=np.int64)
+    leader, pc, pp = -1, 0, 0
+    for j in range(n_h):
+        if big[j]:
+            leader = -1
+            continue
+        new_group = j == 0 or gid[j] != gid[j - 1]
+        if (leader >= 0 and not new_group and pack_len[leader] < PACK_MAX and
+                pc + lens[j] <= TILE and pp + prev_counts[j] <= REC_CAP):
+            pack_len[leader] += 1
+            pc += lens[j]
+            pp += prev_counts[j]
+            joins[j] = 0
+        else:
+            leader, pc, pp = j, int(lens[j]), int(prev_counts[j])
+            pack_len[j] = 1
 
     p = Plan()
     rows = np.zeros(n_h + 1, dtype=PLAN_DTYPE)
@@ -120,14 +146,13 @@ def make_plan(offsets, prev_bits, prev_pb, target=None, lag_particles=None):
     rows['bits_cur'][:n_h] = bits
     rows['bits_prev'][:n_h] = prev_bits
     rows['pb_prev'][:n_h] = np.where(has_prev, prev_pb, 0)
+    rows['pack_len'][:n_h] = pack_len
     p.rows = rows
     p.bits = bits
     p.pb = rows['pb_cur'][:n_h].astype(np.int64)
     p.n_entries = int(rows['pb_cur'][n_h])
 
-    # groups of consecutive regions (by the position of their first particle)
     if n_h:
-        gid = offsets[:-1] // lag_particles
         cut = np.flatnonzero(gid[1:] != gid[:-1]) + 1
         group_first = np.concatenate(([0], cut, [n_h]))
     else:
@@ -186,14 +211,16 @@ class Planner:
             self._range = np.zeros(4 * (cap + 3) + 1, dtype=np.uint32)
             self._cap = cap
 
-    def __call__(self, offsets, prev_bits, prev_pb, target=None,
-                 lag_particles=None):
+    def __call__(self, offsets, prev_bits, prev_pb, prev_counts=None,
+                 target=None, lag_particles=None):
         target = TARGET if target is None else target
         lag_particles = LAG_PARTICLES if lag_particles is None else lag_particles
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         prev_bits = np.ascontiguousarray(prev_bits, dtype=np.int32)
         prev_pb = np.ascontiguousarray(prev_pb, dtype=np.int64)
         n_h = len(offsets) - 1
+        prev_counts = np.zeros(n_h, dtype=np.int64) if prev_counts is None \
+            else np.ascontiguousarray(prev_counts, dtype=np.int64)
         self._reserve(n_h)
         bits = np.empty(n_h, dtype=np.int32)
         pb = np.empty(n_h, dtype=np.int64)
@@ -201,6 +228,7 @@ class Planner:
         vp = C.c_void_p
         rc = self._fn(offsets.ctypes.data_as(vp), n_h,
                       prev_bits.ctypes.data_as(vp), prev_pb.ctypes.data_as(vp),
+                      prev_counts.ctypes.data_as(vp),
                       int(target), int(lag_particles),
                       self._rows.ctypes.data_as(vp), bits.ctypes.data_as(vp),
                       pb.ctypes.data_as(vp), self._group.ctypes.data_as(vp),

@@ -579,13 +579,15 @@ class OrbitTracker:
         n, n_h = gen.n, len(lens)
         prev_bits = np.full(n_h, -1, dtype=np.int32)
         prev_pb = np.zeros(n_h, dtype=np.int64)
+        prev_counts = np.zeros(n_h, dtype=np.int64)
         if prev is not None and matched.any():
             k = prev_index[matched]
             prev_bits[matched] = prev.pj_bits[k]
             prev_pb[matched] = prev.pj_pb[k]
+            prev_counts[matched] = prev.offsets[k + 1] - prev.offsets[k]
         if self._planner is None:
             self._planner = pjoin.Planner(lib)
-        plan = self._planner(gen.offsets, prev_bits, prev_pb)
+        plan = self._planner(gen.offsets, prev_bits, prev_pb, prev_counts)
         gen.pj_bits, gen.pj_pb = plan.bits, plan.pb
         # one packed host->device copy: [plan rows | group_first | range_start]
         nb_rows = plan.rows.nbytes

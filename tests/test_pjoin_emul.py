@@ -117,6 +117,7 @@ class EmulTracker:
         rows['prev_begin'] = -1
         prev_bits = np.full(n_h, -1, dtype=np.int32)
         prev_pb = np.zeros(n_h, dtype=np.int64)
+        prev_counts = np.zeros(n_h, dtype=np.int64)
         matched = np.zeros(n_h, dtype=bool)
         if prev is not None and n_h and len(prev.halo_exists):
             k = np.minimum(np.searchsorted(prev.halo_exists, halo_exists),
@@ -127,7 +128,8 @@ class EmulTracker:
             rows['prev_count'][matched] = prev.offsets[km + 1] - prev.offsets[km]
             prev_bits[matched] = prev.bits[km]
             prev_pb[matched] = prev.pb[km]
-        plan = pjoin.make_plan(offsets, prev_bits, prev_pb, target, lag)
+            prev_counts[matched] = rows['prev_count'][matched]
+        plan = pjoin.make_plan(offsets, prev_bits, prev_pb, prev_counts, target, lag)
 
         g = Gen()
         g.n, g.ids, g.offsets, g.halo_exists = n, ids, offsets, np.asarray(halo_exists)
@@ -207,7 +209,7 @@ def run_case(lib, sim, mode='pericentric', targets=None, n_ctas=3, lag=1 << 12,
     trk = EmulTracker(lib, mode, n_ctas)
     prev_state = None
     n_events = 0
-    stats = {'bits': [], 'tickets': [], 'maxlen': []}
+    stats = {'bits': [], 'tickets': [], 'maxlen': [], 'packs': []}
     for t, sn in enumerate(sim.snapshot_numbers):
         exists = np.flatnonzero(np.asarray(sim.main_branches[t]) >= 0) \
             if hasattr(sim, 'main_branches') else np.arange(sim.n_halos)
@@ -234,6 +236,7 @@ def run_case(lib, sim, mode='pericentric', targets=None, n_ctas=3, lag=1 << 12,
         stats['bits'].append(int(trk.plan.bits.max()) if len(trk.plan.bits) else 0)
         stats['tickets'].append(trk.plan.total)
         stats['maxlen'].append(int(np.diff(g.offsets).max()))
+        stats['packs'].append(int(trk.plan.rows['pack_len'].max()))
         prev_state = state
     assert n_events > 0
     return stats
@@ -255,7 +258,9 @@ def test_plan_decode_covers_every_item_once():
     lens[20] = 70000
     offsets = np.concatenate(([0], np.cumsum(lens)))
     prev_bits = rng.integers(-1, 3, 60).astype(np.int32)
-    plan = pjoin.make_plan(offsets, prev_bits, np.zeros(60, np.int64), 2304, 1 << 14)
+    prev_counts = np.where(prev_bits >= 0, rng.integers(0, 3000, 60), 0)
+    plan = pjoin.make_plan(offsets, prev_bits, np.zeros(60, np.int64), prev_counts,
+                           2304, 1 << 14)
     seen = {}
     last_of = {}
     for tkt in range(plan.total):
@@ -268,7 +273,7 @@ def test_plan_decode_covers_every_item_once():
         tiles = -(-int(lens[j]) // pjoin.TILE) if bits[j] > 0 else 0
         ctiles = -(-int(lens[j]) // pjoin.CTILE) if bits[j] > 0 else 0
         joins = (1 << max(int(prev_bits[j]), 0) if prev_bits[j] >= 0 else 0) \
-            if bits[j] > 0 else 1
+            if bits[j] > 0 else int(plan.rows['pack_len'][j] > 0)
         assert all((pjoin.COUNT, j, i) in seen for i in range(ctiles))
         assert all((pjoin.SCATTER, j, i) in seen for i in range(tiles))
         assert ((pjoin.SCAN, j, 0) in seen) == (bits[j] > 0)
@@ -298,8 +303,15 @@ def test_c_plan_equals_numpy_plan():
         prev_pb = rng.integers(0, 10 ** 6, nh).astype(np.int64)
         target = int(rng.choice([300, 2304, 5000]))
         lag = int(rng.choice([1 << 12, 1 << 19]))
-        a = pjoin.make_plan(offsets, prev_bits, prev_pb, target, lag)
-        b = planner(offsets, prev_bits, prev_pb, target, lag)
+        prev_counts = rng.integers(0, 4000, nh).astype(np.int64)
+        if trial % 4 == 0:
+            lens = rng.integers(0, 400, nh)          # many tiny regions: packs
+            offsets = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+            prev_counts = rng.integers(0, 400, nh).astype(np.int64)
+        a = pjoin.make_plan(offsets, prev_bits, prev_pb, prev_counts, target, lag)
+        b = planner(offsets, prev_bits, prev_pb, prev_counts, target, lag)
+        if trial % 4 == 0 and nh > 40:
+            assert a.rows['pack_len'].max() > 1
         assert np.array_equal(a.rows, b.rows)
         assert np.array_equal(a.group_first, b.group_first)
         assert np.array_equal(a.range_start, b.range_start)
@@ -384,3 +396,53 @@ def test_small_cta_shape(monkeypatch):
     assert max(st['bits']) >= 3 and max(st['maxlen']) > 2 * 1408
     sim = SynthSim(30000, 3, 3, dtype=np.float32, catalogue_dtype=np.float32)
     run_case(lib, sim, targets=[1 << 20], n_ctas=2)        # multi-batch joins
+
+
+def test_packs_of_tiny_regions(emul):
+    """Hundreds of halos with a few dozen particles each: consecutive small
+    regions share one work item (one tile of inputs, one table holding the
+    previous blocks of all members) -- with a particle allowed in two halos."""
+    sim = SynthSim(9000, 300, 4, dtype=np.float32, catalogue_dtype=np.float32,
+                   late_halos=0.2)
+    st = run_case(emul, sim, lag=1 << 11)
+    assert max(st['bits']) == 0
+    assert max(st['packs']) >= 8 and max(st['tickets']) < 120
+    # tiny and partitioned regions mixed
+    sim = SynthSim(30000, 60, 4, dtype=np.float32, catalogue_dtype=np.float32)
+    st = run_case(emul, sim, targets=[300], lag=1 << 12)
+    assert max(st['bits']) >= 2 and max(st['packs']) >= 2
+
+
+def test_pack_with_the_same_particles_in_two_halos(emul):
+    """Overlapping regions: the same IDs sit in two blocks of one pack, so the
+    shared table holds every ID twice -- the match must stay inside the halo."""
+    sim = SynthSim(1400, 2, 4, dtype=np.float32, catalogue_dtype=np.float32)
+    trk = EmulTracker(emul)
+    prev_state = None
+    n_events = 0
+    for t, sn in enumerate(sim.snapshot_numbers):
+        pos, rad, bulk = sim.regions(sn, sim.main_branches[t])
+        s = sim.load_snapshot_data(sn, pos, rad)
+        n0 = int(s['region_offsets'][1])
+        # blocks: [halo 0 | halo 1 | halo 0 again, seen from a shifted centre and
+        # in reversed order]
+        dup = slice(0, n0)
+        snap = dict(s)
+        for key in ('ids', 'coordinates', 'velocities'):
+            snap[key] = np.concatenate((s[key], s[key][dup][::-1]))
+        snap['region_offsets'] = np.append(s['region_offsets'], len(s['ids']))
+        pos3 = np.vstack((pos, pos[0] + np.float32(0.01)))
+        bulk3 = np.vstack((bulk, bulk[0] * np.float32(0.5)))
+        exists = np.arange(3)
+        with np.errstate(all='ignore'):
+            state, exp = oracle.track_snapshot(snap, exists, pos3, bulk3, 0.0,
+                                               'pericentric', prev_state)
+        g, out = trk.step(snap, exists, pos3, bulk3, 0.0, lag=1 << 16)
+        assert trk.plan.rows['pack_len'][0] == 3
+        check_state(g, trk.plan, state, trk.rows)
+        if exp is not None:
+            assert np.array_equal(out['apsis_ids'], exp['apsis_ids'])
+            assert np.array_equal(out['apsis_offsets'], exp['apsis_offsets'])
+            n_events += len(exp['apsis_ids'])
+        prev_state = state
+    assert n_events > 0
