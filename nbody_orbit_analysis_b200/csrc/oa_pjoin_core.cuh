@@ -690,18 +690,20 @@ PJ_FN void stage_join(CX& cx, const oa_pjoin_args& a, const Const& k, const Work
 template <class CX>
 PJ_FN void run(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w) {
     uint32_t* bc = reinterpret_cast<uint32_t*>(cx.smem() + SM_BCAST);
-    for (;;) {
-        if (cx.tid() == 0) bc[0] = cx.atomic_add(w.ticket, 1u);
+    // ONE barrier per item hands out the next ticket and separates the items'
+    // uses of shared memory: the ticket word alternates between two slots, so the
+    // word of item n is not rewritten before every thread has passed the barrier
+    // of item n + 1, i.e. has read it.
+    for (uint32_t n = 0;; ++n) {
+        if (cx.tid() == 0) bc[n & 1u] = cx.atomic_add(w.ticket, 1u);
         cx.sync();
-        const uint32_t t = bc[0];
-        cx.sync();
+        const uint32_t t = bc[n & 1u];
         if (t >= k.total_tickets) break;
         const Item it = decode_item(w.items[t]);
         if (it.stage == COUNT) stage_count(cx, a, w, it.region, it.idx);
         else if (it.stage == SCAN) stage_scan(cx, a, w, it.region);
         else if (it.stage == SCATTER) stage_scatter(cx, a, k, w, it.region, it.idx);
         else stage_join(cx, a, k, w, it.region, it.idx);
-        cx.sync();                     // shared memory is reused by the next item
     }
 }
 

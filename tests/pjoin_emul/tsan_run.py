@@ -22,4 +22,7 @@ assert max(st['bits']) >= 4
 sim = SynthSim(16000, 2, 3, dtype=np.float32, catalogue_dtype=np.float32)
 st = T.run_case(lib, sim, targets=[1 << 20], n_ctas=2)
 assert max(st['maxlen']) > 2 * pjoin.REC_CAP
+sim = SynthSim(5000, 150, 3, dtype=np.float32, catalogue_dtype=np.float32)
+st = T.run_case(lib, sim, n_ctas=3, lag=1 << 11)          # packs of tiny regions
+assert max(st['packs']) >= 4
 print('tsan-run-complete')
