@@ -479,7 +479,7 @@ int oa_merge_gathered(const void* gathered, int world, int n_seg, int64_t cap,
  *                        send buffer = `world` blocks of oa_exchange_bytes(0, cap)
  *                        bytes; counts[n_seg] = this rank's per-halo counts;
  *                        bnd_ws: world+1 int64;
- *   (all-to-all of the blocks, all-reduce of counts)
+ *   (all-to-all of the blocks; the per-halo counts are summed over the ranks)
  *   oa_merge_blocks    : this rank's slice in key order, info = [size | largest
  *                        received block before truncation (> cap: repeat)]. */
 int oa_split_quantiles(const int64_t* gpos, const int64_t* sel, const int64_t* small,

@@ -301,7 +301,10 @@ class Comm:
             blk = lib.oa_exchange_bytes(0, cap)
             send = torch.empty(W * blk, **u8)
             recv = torch.empty(W * blk, **u8)
-            counts = torch.empty(max(n_seg, 1), **i64)
+            # [slice size | largest block | per-halo counts of this rank]: one
+            # buffer, so that ONE all-gather carries the sizes and the counts
+            meta = torch.empty(2 + max(n_seg, 1), **i64)
+            info, counts = meta[:2], meta[2:]
             bnd = torch.empty(W + 1, **i64)
             check(lib.oa_pack_split(
                 ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
@@ -310,22 +313,19 @@ class Comm:
             dist.all_to_all_single(recv, send)
             h.ids = torch.empty(W * cap, **i64)
             h.ang = torch.empty(W * cap, dtype=torch.int16, device=self.device)
-            info = torch.empty(2, **i64)
             check(lib.oa_merge_blocks(ptr(recv), W, cap, ptr(h.ids), ptr(h.ang),
                                       ptr(info), st))
-            info_all = torch.empty(2 * W, **i64)
-            dist.all_gather_into_tensor(info_all, info)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+            meta_all = torch.empty(W * meta.numel(), **i64)
+            dist.all_gather_into_tensor(meta_all, meta)
             tracker.launches += 5
             done = self._event()
             done.record(self.stream)
             tracker.wait_before_submit = done
-            h.keep = (send, recv, prop, prop_all, bnd, info)
+            h.keep = (send, recv, prop, prop_all, bnd, meta)
         # small read-back into pinned buffers OWNED by the handle (torch's host
         # allocator caches them): any number of exchanges -- repeats included --
         # may be launched before this one is finished
-        h.h_info, h.h_counts, h.ready = tracker.to_host_async(
-            info_all, counts, stream=self.stream)
+        h.h_meta, h.ready = tracker.to_host_async(meta_all, stream=self.stream)
         return h
 
     def _round_cap(self, largest):
@@ -419,7 +419,8 @@ class Comm:
 
     def _finish_split(self, h):
         W = self.world
-        info = h.h_info.numpy().reshape(W, 2)
+        meta = h.h_meta.numpy().reshape(W, -1)
+        info = meta[:, :2]
         sizes = info[:, 0]
         # info[:, 1] = largest (source, destination) block, in records, that
         # each rank was sent; every rank reads the same all-gathered numbers
@@ -438,8 +439,10 @@ class Comm:
         lo = int(sizes[:self.rank].sum())
         hi = lo + int(sizes[self.rank])
         res.n_events = total
+        # global per-halo counts = sum over the ranks (the "all-reduce" of
+        # SURVEY 8(e), done on the gathered rows)
         res.apsis_offsets = np.concatenate(
-            ([0], np.cumsum(h.h_counts.numpy()[:h.n_seg]))).astype(np.int64)
+            ([0], np.cumsum(meta[:, 2:2 + h.n_seg].sum(axis=0)))).astype(np.int64)
         res.d_ids, res.d_ang = h.ids[:hi - lo], h.ang[:hi - lo]
         res.host_slice = (lo, hi)
         if h.to_host:
