@@ -86,6 +86,7 @@ class Comm:
         self._cap = None             # records per rank in the send buffers
         self._last_total = 0
         self._results = 0            # finished exchanges: pinned slot of their lists
+        self._splitters = None       # all ranks' quantile keys of the last exchange
         self._repeats = 0            # consecutive repeats after an overflow
 
     # -- catalogue ---------------------------------------------------------------
@@ -279,7 +280,13 @@ class Comm:
                 "finish_merge() no later than one snapshot after start_merge() "
                 "or raise Comm.HEADROOM")
 
-    def _launch_split(self, tracker, res, cap, to_host):
+    def _launch_split(self, tracker, res, cap, to_host, splitters=None):
+        """``splitters``: the all-gathered quantile proposals to split by (a
+        repeat uses those of the attempt it repeats).  Default: the proposals
+        that travelled with the PREVIOUS exchange's sizes -- the key ranges lag
+        one snapshot behind (the event density over the key space changes
+        slowly; an imbalance beyond the headroom ends in a repeat), and an
+        exchange costs two collectives: the all-to-all and one all-gather."""
         gen = res.prev_gen
         W = self.world
         n_seg = len(res.apsis_offsets) - 1
@@ -292,19 +299,25 @@ class Comm:
             st = C.c_void_p(self.stream.cuda_stream)
             i64 = dict(dtype=torch.int64, device=self.device)
             u8 = dict(dtype=torch.uint8, device=self.device)
-            prop = torch.empty(max(W - 1, 1), **i64)
+            n_prop = max(W - 1, 1)
+            # [slice size | largest block | per-halo counts of this rank | this
+            # rank's quantile proposals]: one buffer, so that ONE all-gather
+            # carries the sizes, the counts and the next exchange's splitters
+            n_cnt = max(n_seg, 1)
+            meta = torch.empty(2 + n_cnt + n_prop, **i64)
+            info, counts, prop = meta[:2], meta[2:2 + n_cnt], meta[2 + n_cnt:]
             check(lib.oa_split_quantiles(ptr(gen.gpos), ptr(res.d_sel),
                                          ptr(res.d_small), n_seg, W, ptr(prop),
                                          st))
-            prop_all = torch.empty(W * max(W - 1, 1), **i64)
-            dist.all_gather_into_tensor(prop_all, prop)
+            prop_all = splitters if splitters is not None else self._splitters
+            if prop_all is None:
+                # first exchange: nothing to lag behind
+                prop_all = torch.empty(W * n_prop, **i64)
+                dist.all_gather_into_tensor(prop_all, prop.contiguous())
+            h.splitters = prop_all
             blk = lib.oa_exchange_bytes(0, cap)
             send = torch.empty(W * blk, **u8)
             recv = torch.empty(W * blk, **u8)
-            # [slice size | largest block | per-halo counts of this rank]: one
-            # buffer, so that ONE all-gather carries the sizes and the counts
-            meta = torch.empty(2 + max(n_seg, 1), **i64)
-            info, counts = meta[:2], meta[2:]
             bnd = torch.empty(W + 1, **i64)
             check(lib.oa_pack_split(
                 ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
@@ -317,11 +330,13 @@ class Comm:
                                       ptr(info), st))
             meta_all = torch.empty(W * meta.numel(), **i64)
             dist.all_gather_into_tensor(meta_all, meta)
+            # the proposals of all ranks, [W][W - 1], for the next exchange
+            self._splitters = meta_all.view(W, -1)[:, 2 + n_cnt:].contiguous()
             tracker.launches += 5
             done = self._event()
             done.record(self.stream)
             tracker.wait_before_submit = done
-            h.keep = (send, recv, prop, prop_all, bnd, meta)
+            h.keep = (send, recv, prop_all, bnd, meta)
         # small read-back into pinned buffers OWNED by the handle (torch's host
         # allocator caches them): any number of exchanges -- repeats included --
         # may be launched before this one is finished
@@ -431,7 +446,8 @@ class Comm:
             self._check_inputs_alive(h)
             self._cap = max(self._cap, self._round_cap(largest * W))
             return self.finish_merge(self._launch_split(
-                h.tracker, h.res, self._block_cap(), h.to_host))
+                h.tracker, h.res, self._block_cap(), h.to_host,
+                splitters=h.splitters))
         self._repeats = 0
         self._cap = max(self._cap, self._round_cap(int(sizes.max())))
         res = h.res
@@ -443,6 +459,7 @@ class Comm:
         # SURVEY 8(e), done on the gathered rows)
         res.apsis_offsets = np.concatenate(
             ([0], np.cumsum(meta[:, 2:2 + h.n_seg].sum(axis=0)))).astype(np.int64)
+        # (meta rows: [size | largest | counts | proposals for the next exchange])
         res.d_ids, res.d_ang = h.ids[:hi - lo], h.ang[:hi - lo]
         res.host_slice = (lo, hi)
         if h.to_host:
