@@ -363,21 +363,36 @@ def run_b200(args):
         here and finished one snapshot later (it overlaps the next kernels);
         returns (local result, finished global result or None)."""
         res = timed('collect', trk.collect, pending)
-        done = None
+        done = []
         if comm is not None and res.apsis_offsets is not None:
+            if comm.batch_size > 1:
+                # OA_EXCHANGE_BATCH=K: K snapshots per exchange, finished one
+                # batch behind
+                timed('start_merge', comm.stage_merge, trk, res)
+                while len(comm._launched) > 1:
+                    done += timed('finish_merge', comm.finish_batch,
+                                  comm._launched[0])
+                return res, done
             # every rank hands its 1/world share of the merged lists to the
             # host (parallel write of the result datasets)
             h = timed('start_merge', comm.start_merge, trk, res, to_host='slice')
             prev, exchange['inflight'] = exchange['inflight'], h
             if prev is not None:
-                done = timed('finish_merge', comm.finish_merge, prev)
+                done.append(timed('finish_merge', comm.finish_merge, prev))
         elif comm is None:
-            done = res
+            done.append(res)
         return res, done
 
     def flush_exchange():
+        """Finish whatever exchange is still in flight; list of results."""
+        if comm is not None and comm.batch_size > 1:
+            comm.launch_batch(flush_exchange.trk)
+            done = []
+            while comm._launched:
+                done += comm.finish_batch(comm._launched[0])
+            return done
         h, exchange['inflight'] = exchange['inflight'], None
-        return comm.finish_merge(h) if h is not None else None
+        return [comm.finish_merge(h)] if h is not None else []
 
     def timed_run(host=None):
         """W+1 untimed snapshots, then K timed ones.  Up to `depth` snapshots
@@ -385,6 +400,7 @@ def run_b200(args):
         (software pipeline: host-side collection, H2D and D2H overlap the
         kernels of the following snapshots)."""
         trk = OrbitTracker(mode=args.mode)
+        flush_exchange.trk = trk
         trk.events_on_device = comm is not None
         if comm is not None:       # room for the NCCL kernels of the exchange
             trk.sm_reserve = int(os.environ.get('OA_SM_RESERVE', '12'))
@@ -422,8 +438,7 @@ def run_b200(args):
             nonlocal n_part, n_events, last
             last, done = collect_step(trk, p)
             n_part += last.n
-            if done is not None:
-                n_events += done.n_events
+            n_events += sum(d.n_events for d in done)
         prof = None
         if args.profile and rank == 0:
             import cProfile
@@ -435,9 +450,7 @@ def run_b200(args):
                 take(queue.popleft())
         while queue:
             take(queue.popleft())
-        done = flush_exchange()
-        if done is not None:
-            n_events += done.n_events
+        n_events += sum(d.n_events for d in flush_exchange())
         if prof is not None:
             import pstats
             prof.disable()

@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 15
+#define OA_ABI_VERSION 16
 
 int oa_abi_version(void);
 const char* oa_last_error(void);
@@ -490,6 +490,17 @@ int oa_pack_split(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
                   int64_t* bnd_ws, void* out, int64_t* counts, void* stream);
 int oa_merge_blocks(const void* recv, int world, int64_t cap, int64_t* ids_out,
                     uint16_t* angles_out, int64_t* info, void* stream);
+/* Batched exchange (several snapshots per exchange): append the local events of
+ * one snapshot to a staging area -- keys = gpos[sel[i]] | tag (tag = snapshot
+ * slot << 58), IDs, angles at [ev_base, ev_base + n_local); its n_seg segment
+ * offsets, shifted by ev_base, at out_small[0..n_seg) and the running total at
+ * out_small[n_seg].  The staged arrays of a batch are exchanged like ONE
+ * snapshot with the concatenated segments (keys order snapshot-major). */
+int oa_stage_events(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
+                    const uint16_t* angles, const int64_t* small, int n_seg,
+                    int64_t n_local, int64_t tag, int64_t ev_base,
+                    int64_t* out_keys, int64_t* out_ids, uint16_t* out_angles,
+                    int64_t* out_small, void* stream);
 /* min and max of an int64 array -> out_dev[0], out_dev[1] (device). */
 int oa_minmax_i64(const int64_t* x, int64_t n, int64_t* out_dev, void* stream);
 

@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 15
+ABI_VERSION = 16
 BUCKET_LOAD = 3          # OA_BUCKET_LOAD
 
 
@@ -164,6 +164,8 @@ _sig('oa_synth_fill', C.c_int, C.POINTER(SynthParams), _vp, _i64, C.c_int,
 _sig('oa_synth_params_size', _sz)
 if lib.oa_synth_params_size() != C.sizeof(SynthParams):
     raise ImportError("oa_synth_params layout mismatch")
+_sig('oa_stage_events', C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64, _i64,
+     _vp, _vp, _vp, _vp, _vp)
 _sig('oa_region_rows_host', C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
      _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int))
 _sig('oa_select_gather_events_ids', C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
@@ -199,7 +201,7 @@ EXPORTS = [
     'oa_split_quantiles', 'oa_pack_split', 'oa_merge_blocks',
     'oa_select_gather_events_ids', 'oa_pjoin_workspace_bytes',
     'oa_pjoin_args_size', 'oa_pjoin_step', 'oa_pjoin_plan_host',
-    'oa_region_rows_host', 'oa_pjoin_config',
+    'oa_region_rows_host', 'oa_pjoin_config', 'oa_stage_events',
 ]
 
 

@@ -282,6 +282,32 @@ __global__ void pack_split_kernel(const int64_t* __restrict__ gpos,
     }
 }
 
+// Batched exchange: the local events of one snapshot are appended to a staging
+// area that collects several snapshots (keys tagged with the snapshot's slot in
+// their high bits, segment offsets shifted by the events staged before), so that
+// ONE exchange orders the events of all of them.  stage_small[n_seg] = running
+// total (the next snapshot overwrites it with its first offset, the same value).
+__global__ void stage_events_kernel(const int64_t* __restrict__ gpos,
+                                    const int64_t* __restrict__ sel,
+                                    const int64_t* __restrict__ ids,
+                                    const uint16_t* __restrict__ angles,
+                                    const int64_t* __restrict__ small, int n_seg,
+                                    int64_t n_local, int64_t tag, int64_t ev_base,
+                                    int64_t* __restrict__ out_keys,
+                                    int64_t* __restrict__ out_ids,
+                                    uint16_t* __restrict__ out_angles,
+                                    int64_t* __restrict__ out_small) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t s = t0; s < n_seg; s += stride) out_small[s] = small[s] + ev_base;
+    if (t0 == 0) out_small[n_seg] = ev_base + n_local;
+    for (int64_t i = t0; i < n_local; i += stride) {
+        out_keys[ev_base + i] = gpos[sel[i]] | tag;
+        out_ids[ev_base + i] = ids[i];
+        out_angles[ev_base + i] = angles[i];
+    }
+}
+
 // merge of the `world` received blocks (same layout, block r from rank r) into
 // this rank's slice; info = [slice size | largest received block before
 // truncation to cap (> cap: overflow, the exchange must be repeated)]
@@ -420,6 +446,27 @@ extern "C" int oa_pack_split(const int64_t* gpos, const int64_t* sel, const int6
     pack_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         gpos, sel, ids, angles, small, n_seg, bnd_ws, world, cap,
         static_cast<unsigned char*>(out), counts);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_stage_events(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
+                               const uint16_t* angles, const int64_t* small, int n_seg,
+                               int64_t n_local, int64_t tag, int64_t ev_base,
+                               int64_t* out_keys, int64_t* out_ids, uint16_t* out_angles,
+                               int64_t* out_small, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OA_REQUIRE(small && out_small && n_seg >= 0 && n_local >= 0 && ev_base >= 0 &&
+               (n_local == 0 || (gpos && sel && ids && angles && out_keys && out_ids &&
+                                 out_angles)),
+               "oa_stage_events: bad arguments");
+    int64_t work = n_local > n_seg ? n_local : n_seg;
+    int64_t blocks = (work + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 4096) blocks = 4096;
+    stage_events_kernel<<<(unsigned)blocks, 256, 0, st>>>(gpos, sel, ids, angles, small, n_seg,
+                                                          n_local, tag, ev_base, out_keys,
+                                                          out_ids, out_angles, out_small);
     OA_LAUNCH_CHECK();
     return OA_OK;
 }

@@ -87,6 +87,10 @@ class Comm:
         self._last_total = 0
         self._results = 0            # finished exchanges: pinned slot of their lists
         self._splitters = None       # all ranks' quantile keys of the last exchange
+        import os
+        self.batch_size = max(1, min(31, int(os.environ.get('OA_EXCHANGE_BATCH', '1'))))
+        self._open, self._launched, self._batches = None, [], 0
+        self._stage_sets = {}
         self._repeats = 0            # consecutive repeats after an overflow
 
     # -- catalogue ---------------------------------------------------------------
@@ -273,6 +277,8 @@ class Comm:
                 "the event exchange overflowed its send buffers %d times; the "
                 "event lists are not a uniform sample per rank (is the sharding "
                 "by particle ID?)" % self._repeats)
+        if getattr(h.res, 'persistent', False):
+            return           # (a batch is exchanged from its own staging buffers)
         if h.tracker._step - h.step0 > h.tracker.RING:
             raise _lib.OrbitB200Error(
                 "the event exchange of a snapshot overflowed its send buffers "
@@ -294,7 +300,8 @@ class Comm:
         h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
         h.split = True
         h.step0 = getattr(res, 'step', tracker._step)
-        self.stream.wait_event(res.compacted)
+        if res.compacted is not None:
+            self.stream.wait_event(res.compacted)
         with self._on_stream():
             st = C.c_void_p(self.stream.cuda_stream)
             i64 = dict(dtype=torch.int64, device=self.device)
@@ -474,6 +481,126 @@ class Comm:
             res.host_ready = ready
         h.keep = None
         return res
+
+    # -- events: several snapshots per exchange -----------------------------------
+    # The tracking of later snapshots does not need the merged events, so the
+    # exchange can lag: the local events of up to BATCH snapshots are staged in
+    # HBM (one kernel per snapshot, no collective) and exchanged like ONE snapshot
+    # whose halos are the concatenated halos of all of them -- the snapshot's slot
+    # in the high bits of the order key keeps the snapshots apart.  The host work
+    # and the collectives of an exchange are then paid once per batch.
+    TAG_SHIFT = 58           # order keys stay below 2^58; at most 31 slots
+
+    def stage_merge(self, tracker, res):
+        """Append one snapshot's local events to the open batch (launching its
+        exchange when ``batch_size`` snapshots are staged).  Returns the batch;
+        ``finish_batch`` yields the snapshots' global results."""
+        gen = res.prev_gen
+        if gen is None or gen.gpos is None or res.d_small is None:
+            raise _lib.OrbitB200Error(
+                "stage_merge needs gpos= and OrbitTracker.events_on_device")
+        if self.stream is None:
+            self.stream = _HostStream() if self.device.type != 'cuda' \
+                else torch.cuda.Stream(self.device)
+        b = self._open
+        if b is None:
+            b = self._open = _Exchange()
+            b.items, b.n_local, b.n_seg, b.h = [], 0, 0, None
+            b.slot = self._batches % 3          # staging set (2 batches alive)
+            self._batches += 1
+        n_local, n_seg = int(res.n_events), len(res.apsis_offsets) - 1
+        st_set = self._staging(b.slot, b.n_local + n_local, b.n_seg + n_seg + 1)
+        if res.compacted is not None:
+            self.stream.wait_event(res.compacted)
+        with self._on_stream():
+            check(lib.oa_stage_events(
+                ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+                ptr(res.d_ang_buf), ptr(res.d_small), n_seg, n_local,
+                len(b.items) << self.TAG_SHIFT, b.n_local, ptr(st_set['keys']),
+                ptr(st_set['ids']), ptr(st_set['ang']),
+                ptr(st_set['small'][b.n_seg:]), C.c_void_p(self.stream.cuda_stream)))
+            tracker.launches += 1
+            done = self._event()
+            done.record(self.stream)
+            tracker.wait_before_submit = done   # the ring buffers were read
+        b.items.append((res, n_seg, b.n_seg, n_local))
+        b.n_local += n_local
+        b.n_seg += n_seg
+        b.ids_dtype = gen.ids_dtype
+        if len(b.items) >= self.batch_size:
+            self.launch_batch(tracker)
+        return b
+
+    def _staging(self, slot, n_events, n_small):
+        """Staging arrays of a batch (kept and grown geometrically)."""
+        st_set = self._stage_sets.setdefault(slot, {})
+        def grow(name, n, dtype, keep):
+            old = st_set.get(name)
+            if old is None or old.numel() < n:
+                new = torch.empty(max(int(1.5 * n), 4096), dtype=dtype,
+                                  device=self.device)
+                if old is not None and keep:
+                    with self._on_stream():
+                        new[:keep].copy_(old[:keep])
+                st_set[name] = new
+        b = self._open
+        grow('keys', n_events, torch.int64, b.n_local)
+        grow('ids', n_events, torch.int64, b.n_local)
+        grow('ang', n_events, torch.int16, b.n_local)
+        grow('small', n_small, torch.int64, b.n_seg + 1)
+        iota = st_set.get('iota')
+        if iota is None or iota.numel() < st_set['keys'].numel():
+            st_set['iota'] = torch.arange(st_set['keys'].numel(),
+                                          dtype=torch.int64, device=self.device)
+        return st_set
+
+    def launch_batch(self, tracker):
+        """Exchange the open batch (full or not); no-op without one."""
+        b, self._open = self._open, None
+        if b is None or not b.items:
+            return None
+        st_set = self._stage_sets[b.slot]
+        if self._cap is None:
+            t = torch.tensor([b.n_local], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self._cap = self._round_cap(int(t.item()))
+        # the batch as ONE snapshot: keys, identity selection, concatenated halos
+        pseudo = _Exchange()
+        pseudo.prev_gen = _Exchange()
+        pseudo.prev_gen.gpos, pseudo.prev_gen.ids_dtype = st_set['keys'], b.ids_dtype
+        pseudo.d_sel, pseudo.d_ids_buf = st_set['iota'], st_set['ids']
+        pseudo.d_ang_buf, pseudo.d_small = st_set['ang'], st_set['small']
+        pseudo.apsis_offsets = np.zeros(b.n_seg + 1, dtype=np.int64)
+        pseudo.n_events, pseudo.compacted = b.n_local, None
+        pseudo.persistent, pseudo.step = True, tracker._step
+        b.h = self._launch_split(tracker, pseudo, self._block_cap(), 'slice')
+        self._launched.append(b)
+        return b
+
+    def finish_batch(self, b):
+        """Global results of the snapshots of a launched batch, in order: like
+        ``finish_merge(to_host='slice')`` per snapshot (``host_slice`` is this
+        rank's part of that snapshot's list, possibly empty)."""
+        big = self.finish_merge(b.h)
+        if big.host_ready is not None:
+            big.host_ready.synchronize()
+        lo, hi = big.host_slice
+        off = big.apsis_offsets
+        out = []
+        for res, n_seg, seg_base, _ in b.items:
+            g0, g1 = int(off[seg_base]), int(off[seg_base + n_seg])
+            a, z = min(max(lo, g0), g1), min(max(hi, g0), g1)
+            res.n_events = g1 - g0
+            res.apsis_offsets = off[seg_base:seg_base + n_seg + 1] - g0
+            res.host_slice = (a - g0, z - g0)
+            res.d_ids, res.d_ang = big.d_ids[a - lo:z - lo], big.d_ang[a - lo:z - lo]
+            res.apsis_ids = big.apsis_ids[a - lo:z - lo]
+            res.apsis_angles = big.apsis_angles[a - lo:z - lo]
+            res.host_ready = None
+            out.append(res)
+        if b in self._launched:
+            self._launched.remove(b)
+        return out
 
     def merge_events(self, tracker, res, to_host=True):
         """``start_merge`` + ``finish_merge`` + wait for the host copy."""

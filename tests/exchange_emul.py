@@ -136,6 +136,19 @@ class EmulLib:
         return 0
 
     @staticmethod
+    def oa_stage_events(gpos, sel, ids, ang, small, n_seg, n_local, tag, ev_base,
+                        out_keys, out_ids, out_ang, out_small, st=None):
+        gpos, sel, ids, ang, small, out_keys, out_ids, out_ang, out_small = map(
+            _np, (gpos, sel, ids, ang, small, out_keys, out_ids, out_ang, out_small))
+        out_small[:n_seg] = small[:n_seg] + ev_base
+        out_small[n_seg] = ev_base + n_local
+        out_keys[ev_base:ev_base + n_local] = gpos[sel[:n_local]] | tag
+        out_ids[ev_base:ev_base + n_local] = ids[:n_local]
+        out_ang.view(np.uint16)[ev_base:ev_base + n_local] = \
+            ang[:n_local].view(np.uint16)
+        return 0
+
+    @staticmethod
     def oa_merge_blocks(recv, world, cap, ids_out, ang_out, info, st=None):
         recv, ids_out, ang_out, info = map(_np, (recv, ids_out, ang_out, info))
         k_off, i_off, a_off, nb = layout(0, cap)

@@ -239,3 +239,61 @@ def test_exchange_kernels_gather(case):
 def test_exchange_kernels_overflow():
     check_split_overflow(_Backend('cuda'), 4, 40000, 9000, 40)
     check_split_overflow(_Backend('cuda'), 8, 200000, 60000, 300)
+
+
+# -- staging of several snapshots for one exchange (oa_stage_events) -----------
+def check_stage(be):
+    """Three snapshots staged back to back; the staged arrays exchanged as ONE
+    snapshot give every snapshot's list in order (keys tagged by slot)."""
+    lib, ptr, check, st = be.lib, be.ptr, be.check, be.st
+    world, n_prev = 3, 20000
+    specs = [(1500, 6), (0, 4), (4200, 9)]            # (events, halos) per snapshot
+    globs, staged = [], []
+    for r in range(world):
+        staged.append({'keys': be.empty(9000, torch.int64),
+                       'ids': be.empty(9000, torch.int64),
+                       'ang': be.empty(9000, torch.int16),
+                       'small': be.empty(32, torch.int64), 'n': 0, 'seg': 0})
+    for slot, (m, n_halos) in enumerate(specs):
+        glob, ranks = make_world(world, n_prev, m, n_halos, seed=40 + slot)
+        globs.append(glob)
+        for r, rk in enumerate(ranks):
+            d = {k: be.dev(v) for k, v in rk.items()}
+            s = staged[r]
+            n_local = len(rk['sel'])
+            small_out = s['small'][s['seg']:]
+            check(lib.oa_stage_events(
+                ptr(d['gpos']), ptr(d['sel']), ptr(d['ids']), ptr(d['ang']),
+                ptr(d['small']), n_halos, n_local, slot << 58, s['n'],
+                ptr(s['keys']), ptr(s['ids']), ptr(s['ang']), ptr(small_out), st))
+            s['n'] += n_local
+            s['seg'] += n_halos
+    # the batch as one snapshot per rank: identity selection over the staged keys
+    n_seg = sum(h for _, h in specs)
+    batch_ranks = []
+    for s in staged:
+        n = s['n']
+        small = s['small'][:n_seg + 1].cpu().numpy()
+        assert small[-1] == n and np.all(np.diff(small) >= 0)
+        batch_ranks.append({'gpos': s['keys'][:n].cpu().numpy(),
+                            'sel': np.arange(n, dtype=np.int64),
+                            'ids': s['ids'][:n].cpu().numpy(),
+                            'ang': s['ang'][:n].cpu().numpy(), 'small': small})
+    cap = max(r_['small'][-1] for r_ in batch_ranks) // world * 2 + 64
+    out, counts, _, _ = run_split(be, batch_ranks, world, n_seg, int(cap))
+    ids = np.concatenate([o[0] for o in out])
+    ang = np.concatenate([o[1] for o in out])
+    assert np.array_equal(ids, np.concatenate([g['ids'] for g in globs]))
+    assert np.array_equal(ang, np.concatenate(
+        [g['ang'].view(np.int16) for g in globs]))
+    exp_counts = np.concatenate([np.diff(g['offsets']) for g in globs])
+    assert np.array_equal(counts, exp_counts)
+
+
+def test_stage_events_emulation():
+    check_stage(_Backend('cpu'))
+
+
+@pytest.mark.gpu
+def test_stage_events_kernel():
+    check_stage(_Backend('cuda'))

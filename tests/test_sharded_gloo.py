@@ -240,3 +240,83 @@ def test_catalogue_staging_ring_is_round_robin():
     assert other.data_ptr() not in seq
     for i in range(len(seq) - comm.CAT_RING + 1):
         assert len(set(seq[i:i + comm.CAT_RING])) == comm.CAT_RING
+
+
+def _batch_worker(rank, world, port, K, out_dir):
+    """Several snapshots per exchange (Comm.stage_merge / finish_batch): the
+    per-snapshot global lists must be those of the unbatched exchange."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['OA_EXCHANGE_BATCH'] = str(K)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nbody_orbit_analysis_b200 import sharded
+        import exchange_emul as emul
+        emul.install(sharded)
+        comm = sharded.Comm(world, rank, device=torch.device('cpu'))
+        assert comm.batch_size == K
+        trk = emul.EmulTracker()
+        n_prev = 50000
+        counts = [0, 300, 4000, 3800, 20000, 35000, 90, 0, 25000, 5, 700, 1200, 33000]
+        halos = [7, 7, 5, 9, 7, 7, 3, 7, 7, 1, 7, 8, 7]
+        rng = np.random.default_rng(21)
+        expected, finished = {}, []
+
+        def check(results):
+            for res in results:
+                exp_ids, exp_ang, exp_off = expected.pop(res.step)
+                assert res.n_events == len(exp_ids), (res.step, res.n_events)
+                assert np.array_equal(res.apsis_offsets, exp_off)
+                lo, hi = res.host_slice
+                assert 0 <= lo <= hi <= res.n_events
+                assert np.array_equal(res.apsis_ids, exp_ids[lo:hi])
+                assert np.array_equal(res.apsis_angles.view(np.int16),
+                                      exp_ang[lo:hi].view(np.int16))
+                assert np.array_equal(res.d_ids.numpy(), exp_ids[lo:hi])
+                finished.append((res.step, lo, hi, res.n_events))
+
+        for k, (m, n_halos) in enumerate(zip(counts, halos)):
+            starts = np.concatenate(([0], np.sort(rng.choice(
+                np.arange(1, n_prev), n_halos - 1, replace=False)))) \
+                if n_halos > 1 else np.array([0])
+            pid = rng.permutation(n_prev).astype(np.int64) + 10 ** 12
+            ev_pos = np.sort(rng.choice(n_prev, m, replace=False))
+            ev_ang = rng.standard_normal(n_prev).astype(np.float16)
+            expected[k] = (pid[ev_pos], ev_ang[ev_pos], np.append(
+                np.searchsorted(ev_pos, starts), m).astype(np.int64))
+            mine = np.flatnonzero(pid % world == rank)
+            ev_local = np.flatnonzero(np.isin(mine, ev_pos))
+            res = emul.EmulResult(
+                k, mine.astype(np.int64), ev_local.astype(np.int64),
+                pid[mine][ev_local], ev_ang[mine][ev_local],
+                np.searchsorted(mine, starts))
+            trk._step = k + 2
+            comm.stage_merge(trk, res)
+            while len(comm._launched) > 1:           # lag one batch behind
+                check(comm.finish_batch(comm._launched[0]))
+        comm.launch_batch(trk)                         # the partial last batch
+        while comm._launched:
+            check(comm.finish_batch(comm._launched[0]))
+        assert [f[0] for f in finished] == list(range(len(counts)))
+        all_fin = [None] * world
+        dist.all_gather_object(all_fin, finished)
+        for k in range(len(counts)):                   # slices tile every list
+            edges = sorted((f[k][1], f[k][2]) for f in all_fin)
+            covered = 0
+            for a, z in edges:
+                assert a == covered or a == z
+                covered = max(covered, z)
+            assert covered == counts[k]
+        open(os.path.join(out_dir, 'ok_%d' % rank), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,K', [(2, 4), (3, 5)])
+def test_batched_exchange(world, K, tmp_path):
+    mp.spawn(_batch_worker, args=(world, _free_port(), K, str(tmp_path)),
+             nprocs=world, join=True)
+    assert all(os.path.exists(str(tmp_path / ('ok_%d' % r)))
+               for r in range(world))

@@ -218,7 +218,7 @@ class ShardedHostSynth(HostSynth):
         return dev, n, np.append(loc['region_offsets'], n).astype(np.int64)
 
 
-def _bench_rank(rank, world, port, emul_path, out_dir):
+def _bench_rank(rank, world, port, emul_path, out_dir, batch=1):
     import argparse
     import contextlib
     import io
@@ -231,7 +231,8 @@ def _bench_rank(rank, world, port, emul_path, out_dir):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
                       RANK=str(rank), LOCAL_RANK=str(rank),
                       WORLD_SIZE=str(world), OA_TRACK_IMPL='pjoin',
-                      OA_BENCH_CLOCK_PERIOD='0.05', OA_FAKE_CTAS='1')
+                      OA_BENCH_CLOCK_PERIOD='0.05', OA_FAKE_CTAS='1',
+                      OA_EXCHANGE_BATCH=str(batch))
     import bench
     import exchange_emul
     import fake_cuda as fc
@@ -255,17 +256,19 @@ def _bench_rank(rank, world, port, emul_path, out_dir):
         fh.write(buf.getvalue())
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_bench_multi_rank_on_fake_cuda(emul, world, tmp_path, monkeypatch, capsys):
+@pytest.mark.parametrize('world,batch', [(2, 1), (3, 1), (2, 3)])
+def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch,
+                                       capsys):
     """The multi-GPU arm of ``bench.py`` with `world` ranks on the CPU: sharded
     snapshots, catalogue broadcast one snapshot ahead, asynchronous all-to-all
     exchange (numpy restatements of its kernels, gloo) and per-rank slices --
-    and the same global event count as ONE rank tracking the whole universe."""
+    and the same global event count as ONE rank tracking the whole universe
+    (also with three snapshots per exchange, OA_EXCHANGE_BATCH=3)."""
     import json
     import torch.multiprocessing as mp
     from test_sharded_gloo import _free_port
-    mp.spawn(_bench_rank, args=(world, _free_port(), emul._name, str(tmp_path)),
-             nprocs=world, join=True)
+    mp.spawn(_bench_rank, args=(world, _free_port(), emul._name, str(tmp_path),
+                                batch), nprocs=world, join=True)
     lines = [ln for ln in open(str(tmp_path / 'out_0')).read().splitlines()
              if ln.startswith('{')]
     multi = json.loads(lines[-1])
@@ -274,8 +277,9 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, tmp_path, monkeypatch, capsy
     if world == 2:
         assert multi['e2e']['value'] > 0
         assert multi['e2e']['events_per_step'] == multi['events_per_step']
-    assert {'catalogue', 'submit', 'collect', 'start_merge',
-            'finish_merge'} <= set(multi['host_phases_ms_per_step'])
+    assert {'catalogue', 'submit', 'collect', 'start_merge'} | (
+        {'finish_merge'} if batch == 1 else set()) <= set(
+            multi['host_phases_ms_per_step'])
     for r in range(1, world):          # only rank 0 prints
         assert '{' not in open(str(tmp_path / ('out_%d' % r))).read()
 

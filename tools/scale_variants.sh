@@ -23,6 +23,7 @@ PY
 }
 run default
 run default_again                       # events/step must equal the first run's
+run batch8 OA_EXCHANGE_BATCH=8
 run mainstream OA_EXCHANGE_STREAM=main OA_SM_RESERVE=0
 run fewctas NCCL_MAX_CTAS=4 OA_SM_RESERVE=8
 run nccl_info NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,GRAPH
