@@ -460,7 +460,10 @@ int oa_merge_event_lists(const int64_t* keys, const int64_t* ids,
  *   (one NCCL all-gather of oa_exchange_bytes(n_seg, cap) bytes per rank)
  *   oa_merge_gathered -> merged ID / angle lists in key order and
  *                        info = [total | global offsets[n_seg+1] | sizes[world] |
- *                        overflow flag (some rank had more than `cap` events)]. */
+ *                        overflow flag (some rank had more than `cap` events)].
+ * gpos / sel / ids / angles may be NULL when the local event list is empty
+ * (the count is read from `small` on the device); same for oa_split_quantiles
+ * and oa_pack_split. */
 size_t oa_exchange_bytes(int n_seg, int64_t cap);
 int oa_pack_events(const int64_t* gpos, const int64_t* sel, const int64_t* ids,
                    const uint16_t* angles, const int64_t* small, int n_seg,

@@ -393,8 +393,10 @@ extern "C" int oa_pack_events(const int64_t* gpos, const int64_t* sel, const int
                               const uint16_t* angles, const int64_t* small, int n_seg,
                               int64_t cap, void* out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    OA_REQUIRE(gpos && sel && ids && angles && small && out && n_seg >= 0 && cap >= 1,
-               "oa_pack_events: bad arguments");
+    // (the event count is read from small[n_seg] on the device: gpos / sel / ids /
+    // angles are never dereferenced for an empty list and may then be NULL -- a
+    // zero-element torch tensor has data_ptr() == 0)
+    OA_REQUIRE(small && out && n_seg >= 0 && cap >= 1, "oa_pack_events: bad arguments");
     int64_t blocks = (cap + 255) / 256;
     if (blocks > 4096) blocks = 4096;
     pack_events_kernel<<<(unsigned)blocks, 256, 0, st>>>(
@@ -423,7 +425,8 @@ extern "C" int oa_split_quantiles(const int64_t* gpos, const int64_t* sel,
                                   const int64_t* small, int n_seg, int world,
                                   int64_t* q_out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    OA_REQUIRE(gpos && sel && small && q_out && world >= 1 && world <= 64,
+    // (gpos / sel may be NULL for an empty list, see oa_pack_events)
+    OA_REQUIRE(small && q_out && world >= 1 && world <= 64,
                "oa_split_quantiles: bad arguments");
     if (world == 1) return OA_OK;
     quantile_keys_kernel<<<1, 64, 0, st>>>(gpos, sel, small, n_seg, world, q_out);
@@ -436,7 +439,8 @@ extern "C" int oa_pack_split(const int64_t* gpos, const int64_t* sel, const int6
                              const int64_t* proposals, int world, int64_t cap,
                              int64_t* bnd_ws, void* out, int64_t* counts, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    OA_REQUIRE(gpos && sel && ids && angles && small && bnd_ws && out && counts &&
+    // (gpos / sel / ids / angles may be NULL for an empty list, see oa_pack_events)
+    OA_REQUIRE(small && bnd_ws && out && counts &&
                world >= 1 && world <= 64 && cap >= 1 && (world == 1 || proposals),
                "oa_pack_split: bad arguments");
     split_bounds_kernel<<<1, 96, 0, st>>>(proposals, world, gpos, sel, small, n_seg, bnd_ws);

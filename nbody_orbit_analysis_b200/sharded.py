@@ -278,7 +278,13 @@ class Comm:
                 "event lists are not a uniform sample per rank (is the sharding "
                 "by particle ID?)" % self._repeats)
         if getattr(h.res, 'persistent', False):
-            return           # (a batch is exchanged from its own staging buffers)
+            # a batch is exchanged from its own staging set, which is reused by
+            # the third batch after it
+            if self._batches - h.res.batch_seq >= 3:
+                raise _lib.OrbitB200Error(
+                    "the exchange of a batch overflowed after its staging "
+                    "buffers had been reused; call finish_batch() earlier")
+            return
         if h.tracker._step - h.step0 > h.tracker.RING:
             raise _lib.OrbitB200Error(
                 "the event exchange of a snapshot overflowed its send buffers "
@@ -343,7 +349,10 @@ class Comm:
             done = self._event()
             done.record(self.stream)
             tracker.wait_before_submit = done
-            h.keep = (send, recv, prop_all, bnd, meta)
+            # (meta_all is read by the copy stream below: it must stay allocated
+            # until the handle is finished, or the caching allocator hands its
+            # block to the next exchange while the copy is still queued)
+            h.keep = (send, recv, prop_all, bnd, meta, meta_all)
         # small read-back into pinned buffers OWNED by the handle (torch's host
         # allocator caches them): any number of exchanges -- repeats included --
         # may be launched before this one is finished
@@ -532,26 +541,38 @@ class Comm:
         return b
 
     def _staging(self, slot, n_events, n_small):
-        """Staging arrays of a batch (kept and grown geometrically)."""
+        """Staging arrays of a batch (kept and grown geometrically).  Everything
+        here -- allocation, the grow-copy, the identity selection -- is issued on
+        the EXCHANGE stream, the only stream that touches these arrays; a
+        replaced array stays referenced by the open batch until the batch is
+        finished, so its block cannot be recycled under a pending copy."""
         st_set = self._stage_sets.setdefault(slot, {})
+        b = self._open
+        retired = b.__dict__.setdefault('retired', [])
+
         def grow(name, n, dtype, keep):
             old = st_set.get(name)
             if old is None or old.numel() < n:
                 new = torch.empty(max(int(1.5 * n), 4096), dtype=dtype,
                                   device=self.device)
-                if old is not None and keep:
-                    with self._on_stream():
+                if old is not None:
+                    if keep:
                         new[:keep].copy_(old[:keep])
+                    retired.append(old)
                 st_set[name] = new
-        b = self._open
-        grow('keys', n_events, torch.int64, b.n_local)
-        grow('ids', n_events, torch.int64, b.n_local)
-        grow('ang', n_events, torch.int16, b.n_local)
-        grow('small', n_small, torch.int64, b.n_seg + 1)
-        iota = st_set.get('iota')
-        if iota is None or iota.numel() < st_set['keys'].numel():
-            st_set['iota'] = torch.arange(st_set['keys'].numel(),
-                                          dtype=torch.int64, device=self.device)
+
+        with self._on_stream():
+            grow('keys', n_events, torch.int64, b.n_local)
+            grow('ids', n_events, torch.int64, b.n_local)
+            grow('ang', n_events, torch.int16, b.n_local)
+            grow('small', n_small, torch.int64, b.n_seg + 1)
+            iota = st_set.get('iota')
+            if iota is None or iota.numel() < st_set['keys'].numel():
+                if iota is not None:
+                    retired.append(iota)
+                st_set['iota'] = torch.arange(st_set['keys'].numel(),
+                                              dtype=torch.int64,
+                                              device=self.device)
         return st_set
 
     def launch_batch(self, tracker):
@@ -573,6 +594,7 @@ class Comm:
         pseudo.apsis_offsets = np.zeros(b.n_seg + 1, dtype=np.int64)
         pseudo.n_events, pseudo.compacted = b.n_local, None
         pseudo.persistent, pseudo.step = True, tracker._step
+        pseudo.batch_seq = self._batches
         b.h = self._launch_split(tracker, pseudo, self._block_cap(), 'slice')
         self._launched.append(b)
         return b

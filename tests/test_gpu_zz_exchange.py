@@ -30,12 +30,9 @@ class _Backend:
             self.st = None
 
     def dev(self, arr):
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
-        if t.numel() == 0:
-            # an empty list still lives in a real buffer (the tracker's rings
-            # are never NULL; the C ABI rejects NULL arrays)
-            t = torch.zeros(1, dtype=t.dtype, device=self.device)[:0]
-        return t
+        # (an empty list is a zero-element tensor, data_ptr() == 0: the C ABI
+        # accepts NULL arrays for empty lists, like Tracker._to_device produces)
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
 
     def empty(self, n, dtype):
         # poisoned, not zeroed: a kernel must write everything that is read
