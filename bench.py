@@ -426,6 +426,12 @@ def run_b200(args):
         trk.timing = []
         launches0 = trk.launches
         phases.clear()
+        # profiling builds of the partitioned join (-DOA_PJOIN_STATS=1) count
+        # cycles per stage: cleared here, read after the timed steps
+        import ctypes as _C
+        from nbody_orbit_analysis_b200._lib import lib as _oalib
+        pj_stats = (_C.c_uint64 * 16)()
+        _oalib.oa_pjoin_stats(pj_stats, 1)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), \
             torch.cuda.Event(enable_timing=True)
@@ -462,6 +468,7 @@ def run_b200(args):
         wall1 = time.time()
         ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+        stats_on = _oalib.oa_pjoin_stats(pj_stats, 0)
         kern_ms = [a.elapsed_time(b) for a, b, _ in trk.timing]
         kern_n = [n for _, _, n in trk.timing]
         stats = torch.tensor([ms, float(n_part), float(n_events)],
@@ -478,7 +485,8 @@ def run_b200(args):
                                             for k, v in phases.items()},
                 'particles': n_part, 'events': n_events,
                 'launches': trk.launches - launches0, 'clocks': clocks,
-                'kern_ms': kern_ms, 'kern_n': kern_n, 'last': last}
+                'kern_ms': kern_ms, 'kern_n': kern_n, 'last': last,
+                'pj_stats': list(pj_stats) if stats_on else None}
 
     dev_run = timed_run()
     value = dev_run['particles'] / (dev_run['ms'] * 1e-3)
@@ -592,6 +600,17 @@ def run_b200(args):
             'host_phases_ms_per_step': dev_run['host_phases_ms_per_step'],
             'roofline': roofline,
         }
+        if dev_run.get('pj_stats'):
+            st = dev_run['pj_stats']
+            names = ('join', 'scatter', 'scan', 'count')
+            tot = float(st[12]) or 1.0
+            line['pjoin_stage_profile'] = {
+                'share_of_cta_cycles': {n: round(st[i] / tot, 4)
+                                        for i, n in enumerate(names)},
+                'waiting_share': round(st[4] / tot, 4),
+                'items': {n: int(st[8 + i]) for i, n in enumerate(names)},
+                'cycles_per_item': {n: round(st[i] / max(st[8 + i], 1), 1)
+                                    for i, n in enumerate(names)}}
         if e2e is not None:
             line['e2e'] = e2e
         elif not args.no_e2e:

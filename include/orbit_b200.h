@@ -349,6 +349,10 @@ size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries,
  * out[7] = dynamic shared memory per CTA in bytes. */
 void oa_pjoin_config(int32_t* out8);
 size_t oa_pjoin_args_size(void);
+/* Profiling builds (-DOA_PJOIN_STATS=1) only: out16 = [cycles per stage JOIN,
+ * SCATTER, SCAN, COUNT | cycles waiting for dependencies | ... | items per stage
+ * at [8..11] | CTA cycles at [12]]; returns 0 when built without the counters. */
+int oa_pjoin_stats(uint64_t* out16, int reset);
 int oa_pjoin_step(const oa_pjoin_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------

@@ -181,6 +181,7 @@ if lib.oa_pjoin_args_size() != C.sizeof(_pjoin.PJoinArgs):
 lib.oa_pjoin_config.restype = None
 lib.oa_pjoin_config.argtypes = [C.POINTER(C.c_int32)]
 _pjoin.configure(lib)
+_sig('oa_pjoin_stats', C.c_int, _vp, C.c_int)
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
@@ -202,6 +203,7 @@ EXPORTS = [
     'oa_select_gather_events_ids', 'oa_pjoin_workspace_bytes',
     'oa_pjoin_args_size', 'oa_pjoin_step', 'oa_pjoin_plan_host',
     'oa_region_rows_host', 'oa_pjoin_config', 'oa_stage_events',
+    'oa_pjoin_stats',
 ]
 
 

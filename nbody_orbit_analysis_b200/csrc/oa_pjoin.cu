@@ -4,9 +4,25 @@
 #include "oa_common.cuh"
 #include "oa_pjoin_core.cuh"
 
+#ifndef OA_PJOIN_STATS
+#define OA_PJOIN_STATS 0
+#endif
+// profiling builds: [0..3] cycles per stage (thread 0 of every CTA), [4] cycles
+// waiting for dependencies, [8..11] items per stage, [12] CTA cycles in the kernel
+__device__ unsigned long long g_pj_stats[16];
+
 namespace {
 
 struct DevCtx {
+#if OA_PJOIN_STATS
+    OA_D uint64_t clock() const { return (uint64_t)clock64(); }
+    OA_D void stat_add(int i, uint64_t v) const {
+        atomicAdd(&g_pj_stats[i], (unsigned long long)v);
+    }
+#else
+    OA_D uint64_t clock() const { return 0; }
+    OA_D void stat_add(int, uint64_t) const {}
+#endif
     unsigned char* sm;
     uint32_t parity;        // phase of the TMA mbarrier (same in every thread)
     OA_D int tid() const { return (int)threadIdx.x; }
@@ -98,7 +114,9 @@ oa_pjoin_kernel(const __grid_constant__ oa_pjoin_args a, const __grid_constant__
     }
     __syncthreads();
 #endif
+    const uint64_t t0 = cx.clock();
     pj::run(cx, a, k, w);
+    if (threadIdx.x == 0) cx.stat_add(12, cx.clock() - t0);
 }
 
 // one block per region writes the region's work items (see pj::expand_region)
@@ -117,6 +135,20 @@ size_t work_words(int n_regions, int64_t n_part_entries) {
 extern "C" size_t oa_pjoin_workspace_bytes(int n_regions, int64_t n_part_entries,
                                            uint32_t total_tickets) {
     return 8 * (size_t)total_tickets + 4 * work_words(n_regions, n_part_entries);
+}
+
+// profiling builds (-DOA_PJOIN_STATS=1): read (and optionally clear) the counters;
+// returns 0 when the library was built without them
+extern "C" int oa_pjoin_stats(uint64_t* out16, int reset) {
+    if (!out16) return 0;
+    unsigned long long h[16];
+    if (cudaMemcpyFromSymbol(h, g_pj_stats, sizeof(h)) != cudaSuccess) return 0;
+    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    if (reset) {
+        for (int i = 0; i < 16; ++i) h[i] = 0;
+        if (cudaMemcpyToSymbol(g_pj_stats, h, sizeof(h)) != cudaSuccess) return 0;
+    }
+    return OA_PJOIN_STATS;
 }
 
 extern "C" size_t oa_pjoin_args_size(void) { return sizeof(oa_pjoin_args); }

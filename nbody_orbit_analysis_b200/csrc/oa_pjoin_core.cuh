@@ -238,10 +238,12 @@ template <class CX>
 PJ_FN void wait_ge(CX& cx, const uint32_t* p, uint32_t need) {
     if (cx.tid() == 0) {
         uint32_t spins = 0;
+        const uint64_t t0 = cx.clock();
         while (cx.load_acquire(p) < need) {
             cx.backoff();
             if (++spins > MAX_SPINS) cx.fail();
         }
+        cx.stat_add(4, cx.clock() - t0);      // cycles spent waiting for a dependency
     }
     cx.sync();
 }
@@ -700,10 +702,16 @@ PJ_FN void run(CX& cx, const oa_pjoin_args& a, const Const& k, const Work& w) {
         const uint32_t t = bc[n & 1u];
         if (t >= k.total_tickets) break;
         const Item it = decode_item(w.items[t]);
+        const uint64_t t0 = cx.clock();
         if (it.stage == COUNT) stage_count(cx, a, w, it.region, it.idx);
         else if (it.stage == SCAN) stage_scan(cx, a, w, it.region);
         else if (it.stage == SCATTER) stage_scatter(cx, a, k, w, it.region, it.idx);
         else stage_join(cx, a, k, w, it.region, it.idx);
+        // (profiling builds only, -DOA_PJOIN_STATS=1: cycles and items per stage)
+        if (cx.tid() == 0) {
+            cx.stat_add(it.stage, cx.clock() - t0);
+            cx.stat_add(8 + it.stage, 1);
+        }
     }
 }
 

@@ -47,6 +47,8 @@ struct HostCtx {
     float ld_last(const float* p) const { return *p; }
     pj::Rec load_rec_cg(const pj::Rec* p) const { return *p; }
     void store_rec(pj::Rec* p, const pj::Rec& r) const { *p = r; }
+    uint64_t clock() const { return 0; }
+    void stat_add(int, uint64_t) const {}
 };
 
 struct ThreadArg {
