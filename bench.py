@@ -223,12 +223,79 @@ def _reference_worker(job):
     return secs, count, len(snaps[-1]['ids'])
 
 
+def reference_available():
+    """The unmodified reference package is importable (mounted tree in the build
+    container, or the copy vendored into oracle/_ref by `make -C oracle ref`)."""
+    try:
+        from oracle import reference_harness
+        return reference_harness.available()
+    except Exception:
+        return False
+
+
+def reference_track(snaps, cats, main_branches, snapshot_numbers, mode,
+                    first_timed):
+    """Run the UNMODIFIED reference `track_orbits` (single process, npool=None:
+    its pathos pool is a slow-down) over prebuilt host
+    snapshots.  Returns (seconds, particle-snapshots) of the iterations
+    `first_timed` .. end: from the moment the loader callback of iteration
+    `first_timed` returns until the call returns (tracking + result assembly +
+    file write through the h5py stand-in; the callbacks only look data up)."""
+    import tempfile
+    from oracle.reference_harness import load_reference
+    ref = load_reference()
+    index = {int(sn): t for t, sn in enumerate(snapshot_numbers)}
+    marks = {}
+
+    def regions(snapshot_number, halo_ids):
+        return cats[index[int(snapshot_number)]]
+
+    def loader(snapshot_number, positions, radii):
+        t = index[int(snapshot_number)]
+        marks[t] = time.perf_counter()
+        return snaps[t]
+    tmp = tempfile.mkdtemp(prefix='oa_refarm_')
+    with np.errstate(all='ignore'):
+        ref.track_orbits.track_orbits(
+            snapshot_numbers, main_branches, regions, loader,
+            os.path.join(tmp, 'ref.h5'), mode=mode, npool=None, verbose=False)
+    end = time.perf_counter()
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    count = sum(len(snaps[t]['ids']) for t in range(first_timed, len(snaps)))
+    return end - marks[first_timed], count
+
+
+def _reference_worker_real(job):
+    """One host core: two halos of the configuration through the real
+    reference; generation untimed, the last K snapshots timed."""
+    particles, halos, cols, warmup, steps, mode = job
+    import warnings
+    warnings.filterwarnings('ignore')
+    from nbody_orbit_analysis_b200.synth import SynthSim
+    n_steps = warmup + steps
+    sim = SynthSim(particles, halos, n_steps + 1, dtype=np.float32,
+                   catalogue_dtype=np.float32)
+    cols = np.array(sorted(cols))
+    snaps, cats = [], []
+    for t in range(n_steps + 1):
+        pos = sim.halo_centre(t)[cols].astype(np.float32)
+        cats.append((pos, sim.radius[cols].astype(np.float32),
+                     sim.vh[cols].astype(np.float32)))
+        snaps.append(sim.load_snapshot_data(sim.snapshot_numbers[t], pos, None,
+                                            cols=cols))
+    secs, count = reference_track(snaps, cats, sim.main_branches[:, cols],
+                                  sim.snapshot_numbers, mode, warmup + 1)
+    return secs, count, len(snaps[-1]['ids'])
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path on this host's cores.
 
-    The reference is pure Python/numpy and cannot travel to the GPU box, so the
-    oracle port (numpy restatement pinned against it, oracle/orbit_oracle.py)
-    is what runs.  The reference's own parallel axis is "one halo per worker"
+    The unmodified reference package runs (vendored into oracle/_ref by `make
+    -C oracle ref`, so that it travels to the GPU box; the oracle port only if
+    that copy is missing, or with OA_REF_ARM=port).  The reference's own
+    parallel axis is "one halo per worker"
     (track_orbits.py:189-194); its pathos pool re-pickles the whole snapshot
     per task and is a slow-down, so the fair CPU arm is
     one forked worker per core, each tracking one halo of the configuration
@@ -248,15 +315,20 @@ def run_reference(args):
     jobs = [(args.particles, args.halos, (4 + w, 4 + 2 * cores - 1 - w),
              args.warmup, args.steps, args.mode) for w in range(cores)]
     wall0 = time.perf_counter()
+    real = reference_available() and os.environ.get('OA_REF_ARM') != 'port'
     with mp.get_context('fork').Pool(cores) as pool:
-        out = pool.map(_reference_worker, jobs, chunksize=1)
+        out = pool.map(_reference_worker_real if real else _reference_worker,
+                       jobs, chunksize=1)
     wall = time.perf_counter() - wall0
     secs = max(o[0] for o in out)
     count = sum(o[1] for o in out)
     value = count / secs
-    sample = ('halos 4..%d of %d (two per core, %d particles/snapshot in total) '
+    sample = ('%s; halos 4..%d of %d (two per core, %d particles/snapshot in total) '
               'of the %d-particle configuration, %d timed snapshots; '
               'generation untimed, whole run %.0f s' % (
+                  'UNMODIFIED reference orbitanalysis.track_orbits (npool=None) in '
+                  'one forked worker per core, h5py replaced by the in-repo '
+                  'stand-in' if real else 'oracle port (reference not importable)',
                   3 + 2 * cores, args.halos, sum(o[2] for o in out),
                   args.particles, args.steps, wall))
     line = {
@@ -268,7 +340,8 @@ def run_reference(args):
         'data': 'synthetic',
         'config': workload_config(args),
         'cpu_baseline': {'value': value, 'unit': 'particle-snapshots/s',
-                         'cores': cores, 'kind': 'port', 'sample': sample},
+                         'cores': cores, 'kind': 'reference' if real else 'port',
+                         'sample': sample},
         'e2e': {'value': value, 'unit': 'particle-snapshots/s',
                 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -639,7 +712,8 @@ def cpu_baseline(args, snaps, cats, gen, torch):
             'coordinates': dev['pos'][:3 * hi].cpu().numpy().reshape(-1, 3),
             'velocities': dev['vel'][:3 * hi].cpu().numpy().reshape(-1, 3),
             'masses': 1.0, 'region_offsets': offsets[:ncols].copy(),
-            'box_size': gen.host.box, 'redshift': 0.0})
+            'box_size': gen.host.box, 'redshift': 0.0, 'H0': 0.0,
+            'Omega_m': 0.3, 'Omega_L': 0.7})
         pos, rad, bulk = cats[t]
         cat.append((pos[:ncols], rad[:ncols], bulk[:ncols]))
     secs, count, outs = cpu_track(host, cat, args.mode)
@@ -658,7 +732,7 @@ def cpu_baseline(args, snaps, cats, gen, torch):
             # (a mismatch must end up in the JSON line, not in a traceback)
             ok &= a.shape == b.shape and bool(
                 np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True))
-    return {
+    out = {
         'value': count / secs, 'unit': 'particle-snapshots/s', 'cores': 1,
         'kind': 'port',
         'sample': 'first %d halos (%d particles/snapshot) x %d snapshots of '
@@ -669,6 +743,22 @@ def cpu_baseline(args, snaps, cats, gen, torch):
         'parity_vs_gpu_on_sample': 'ok' if ok else 'MISMATCH',
         'sample_events': n_ev,
     }
+    if reference_available():
+        # the UNMODIFIED reference on the same sample, one core (npool=None is
+        # its fastest setting); the port's figure stays as a second number
+        mb = np.tile(np.arange(ncols, dtype=np.int64), (n_s, 1))
+        r_secs, r_count = reference_track(host, cat, mb, np.arange(n_s), args.mode, 1)
+        out.update({
+            'value': r_count / r_secs, 'kind': 'reference', 'seconds': r_secs,
+            'port_value': count / secs,
+            'sample': 'first %d halos (%d particles/snapshot) x %d snapshots of '
+                      'this run through the UNMODIFIED reference '
+                      'orbitanalysis.track_orbits (npool=None, 1 core, h5py '
+                      'replaced by the in-repo stand-in); parity of the sample '
+                      'checked between the GPU path and the oracle port; host '
+                      'has %d cores' % (ncols, len(host[-1]['ids']), n_s - 1,
+                                        os.cpu_count())})
+    return out
 
 
 if __name__ == '__main__':

@@ -12,19 +12,37 @@ here, so two stand-ins are registered first:
 * ``pathos.multiprocessing.Pool`` -> ``multiprocess.Pool`` (that is what pathos
   re-exports).
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there may
-import this module.
+``/root/reference`` does not exist on the GPU box; there the pip-installed copy
+under ``oracle/_ref`` (``make -C oracle ref``, run by ``__graft_entry__.build()``
+in the build container) is imported instead.  Only ``bench.py``'s CPU legs
+(``--impl reference``, ``cpu_baseline``) and the golden-vector generator use
+this module.
 """
 import importlib
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('OA_REFERENCE_ROOT', '/root/reference')
+# where the unmodified reference package is importable from: the mounted tree in
+# the build container, else the pip-installed copy that `make -C oracle ref`
+# vendors into oracle/_ref (git-ignored; it travels with the snapshot to the GPU
+# box, where /root/reference does not exist)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get('OA_REFERENCE_ROOT', '/root/reference'),
+               os.path.join(_HERE, '_ref')]
+REFERENCE_ROOT = next((c for c in _CANDIDATES
+                       if os.path.isdir(os.path.join(c, 'orbitanalysis'))),
+                      _CANDIDATES[0])
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'orbitanalysis'))
+
+
+def vendored():
+    """True when the copy in oracle/_ref (not the mounted tree) is in use."""
+    return available() and os.path.abspath(REFERENCE_ROOT) == \
+        os.path.join(_HERE, '_ref')
 
 
 def load_reference():
