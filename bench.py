@@ -504,7 +504,9 @@ def run_b200(args):
         import ctypes as _C
         from nbody_orbit_analysis_b200._lib import lib as _oalib
         pj_stats = (_C.c_uint64 * 16)()
-        _oalib.oa_pjoin_stats(pj_stats, 1)
+        stats_fn = _oalib.oa_pj2_stats if os.environ.get(
+            'OA_TRACK_IMPL') == 'pj2' else _oalib.oa_pjoin_stats
+        stats_fn(pj_stats, 1)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), \
             torch.cuda.Event(enable_timing=True)
@@ -541,7 +543,7 @@ def run_b200(args):
         wall1 = time.time()
         ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-        stats_on = _oalib.oa_pjoin_stats(pj_stats, 0)
+        stats_on = stats_fn(pj_stats, 0)
         kern_ms = [a.elapsed_time(b) for a, b, _ in trk.timing]
         kern_n = [n for _, _, n in trk.timing]
         stats = torch.tensor([ms, float(n_part), float(n_events)],
@@ -621,8 +623,9 @@ def run_b200(args):
         # what the end-to-end number is bound by: the host->device link
         e2e['h2d_gb_per_s_per_gpu'] = e2e['h2d_bytes_per_step'] / (
             e2e['ms_per_step'] * 1e-3) / 1e9
-        if e2e_run['events'] != dev_run['events']:
-            e2e['warning'] = 'event count differs from the device-resident run'
+        # same data, two passes: the global event totals must be identical
+        e2e['events_equal_device_run'] = bool(
+            e2e_run['events'] == dev_run['events'])
 
     # ---- roofline of the fused kernel ------------------------------------------
     peak, peak_kind = measured_peak()
@@ -631,11 +634,13 @@ def run_b200(args):
     achieved = k_n * B_ALG_F32 / (k_ms * 1e-3) / 1e9
     impl = os.environ.get('OA_TRACK_IMPL', 'hash')
     roofline = {
-        'kernel': 'oa_track_kernel<float,float,double> (fused frame + hash '
-                  'match + apsis + angle update + table insert)'
-                  if impl == 'hash' else
-                  'oa_pjoin_kernel (frame + partition scatter + shared-memory '
-                  'hash join + apsis + angle update)',
+        'kernel': {'hash': 'oa_track_kernel<float,float,double> (fused frame + '
+                           'hash match + apsis + angle update + table insert)',
+                   'pjoin': 'oa_pjoin_kernel (frame + partition scatter + '
+                            'shared-memory hash join + apsis + angle update)',
+                   'pj2': 'oa_pj2_kernel (TMA-staged frame + fixed-capacity '
+                          'partition scatter + shared-memory hash join + apsis + '
+                          'angle update)'}[impl],
         'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
         'algorithmic_bytes_per_particle': B_ALG_F32,
@@ -650,7 +655,8 @@ def run_b200(args):
         try:
             with open(traffic_file) as fh:
                 roofline['traffic'] = json.load(fh).get(
-                    'oa_track_kernel' if impl == 'hash' else 'oa_pjoin_kernel')
+                    {'hash': 'oa_track_kernel', 'pjoin': 'oa_pjoin_kernel',
+                     'pj2': 'oa_pj2_kernel'}[impl])
         except (OSError, ValueError):
             pass
 
@@ -658,6 +664,10 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args, snaps, cats, gen, torch)
+    multi_parity = None
+    if world > 1 and not args.no_cpu:
+        multi_parity = multi_rank_parity(args, snaps, cats, gen, comm, world,
+                                         rank, torch, dist)
 
     if rank == 0:
         line = {
@@ -673,7 +683,19 @@ def run_b200(args):
             'host_phases_ms_per_step': dev_run['host_phases_ms_per_step'],
             'roofline': roofline,
         }
-        if dev_run.get('pj_stats'):
+        if dev_run.get('pj_stats') and impl == 'pj2':
+            st = dev_run['pj_stats']
+            tot = float(st[12]) or 1.0      # cycles of thread 0 of every CTA
+            line['pj2_stage_profile'] = {
+                'consumer_share': {'scatter': round(st[0] / tot, 4),
+                                   'join': round(st[1] / tot, 4),
+                                   'wait_full_stage': round(st[6] / tot, 4)},
+                'producer_share': {'wait_dependency': round(st[4] / tot, 4),
+                                   'wait_free_stage': round(st[5] / tot, 4)},
+                'items': {'scatter': int(st[8]), 'join': int(st[9])},
+                'cycles_per_item': {'scatter': round(st[0] / max(st[8], 1), 1),
+                                    'join': round(st[1] / max(st[9], 1), 1)}}
+        elif dev_run.get('pj_stats'):
             st = dev_run['pj_stats']
             names = ('join', 'scatter', 'scan', 'count')
             tot = float(st[12]) or 1.0
@@ -690,9 +712,103 @@ def run_b200(args):
             line['e2e_skipped'] = e2e_skipped
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if multi_parity is not None:
+            line['parity_multi_gpu'] = multi_parity
+        bad = (multi_parity is not None
+               and multi_parity['parity_vs_oracle'] != 'ok') or (
+            e2e is not None and not e2e['events_equal_device_run']) or (
+            cpu is not None and cpu['parity_vs_gpu_on_sample'] != 'ok')
+        line['parity'] = 'MISMATCH' if bad else 'ok'
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_rank_parity(args, snaps, cats, gen, comm, world, rank, torch, dist):
+    """N > 1: a sample of WHOLE halos (the last halos of the configuration, all
+    ranks' shards of them put back together in the global block order) is
+    tracked (i) by the oracle on rank 0's host and (ii) by all ranks through
+    OrbitTracker + both exchange paths (all-gather to every rank, all-to-all
+    slices); the merged global event lists must equal the oracle's.
+    Reference order: track_orbits.py:199-217, 315-316."""
+    from nbody_orbit_analysis_b200 import sharded
+    from nbody_orbit_analysis_b200.tracker import OrbitTracker
+    sizes = gen.host.sizes
+    n_h = len(sizes)
+    tail = np.cumsum(sizes[::-1]) * world
+    ncols = int(min(np.searchsorted(tail, args.cpu_particles) + 1, n_h))
+    h0 = n_h - ncols
+    n_s = min(len(snaps), 5)
+    full, cat = [], []
+    for t in range(n_s):
+        dev, n, offsets = snaps[t]
+        lo = int(offsets[h0])
+        mine = {'ids': dev['ids'][lo:n].cpu().numpy(),
+                'pos': dev['pos'][3 * lo:3 * n].cpu().numpy().reshape(-1, 3),
+                'vel': dev['vel'][3 * lo:3 * n].cpu().numpy().reshape(-1, 3),
+                'key': dev['gpos'][lo:n].cpu().numpy(),
+                'halo': np.repeat(np.arange(ncols), np.diff(offsets[h0:]))}
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        # global block order: by halo, then by the order key (comparable across
+        # the ranks: position / shuffle key in the unsharded block)
+        key = np.concatenate([p['key'] for p in parts])
+        halo = np.concatenate([p['halo'] for p in parts])
+        order = np.lexsort((key, halo))
+        halo = halo[order]
+        full.append({
+            'ids': np.concatenate([p['ids'] for p in parts])[order],
+            'coordinates': np.concatenate([p['pos'] for p in parts])[order],
+            'velocities': np.concatenate([p['vel'] for p in parts])[order],
+            'masses': 1.0,
+            'region_offsets': np.searchsorted(halo, np.arange(ncols)).astype(np.int64),
+            'box_size': gen.host.box, 'redshift': 0.0, 'H0': 0.0,
+            'Omega_m': 0.3, 'Omega_L': 0.7})
+        pos, rad, bulk = cats[t]
+        cat.append((pos[h0:], rad[h0:], bulk[h0:]))
+    outs = None
+    if rank == 0:
+        _, _, outs = cpu_track(full, cat, args.mode)
+    exists = np.arange(ncols)
+    report = {'halos': ncols, 'snapshots': n_s - 1,
+              'particles_per_snapshot': int(len(full[-1]['ids']))}
+    ok_all = True
+    for path in (True, 'slice'):
+        trk = OrbitTracker(mode=args.mode)
+        trk.events_on_device = True
+        c = sharded.Comm(world, rank)
+        ok, n_ev = True, 0
+        for t in range(n_s):
+            local, gpos = sharded.shard_snapshot(full[t], rank, world)
+            res = trk.step(local, exists, cat[t][0], cat[t][2], 0.0, gpos=gpos)
+            if t == 0:
+                continue
+            res = c.merge_events(trk, res, to_host=path)
+            lo, hi = res.host_slice
+            piece = (lo, np.array(res.apsis_ids[:hi - lo]),
+                     np.array(res.apsis_angles[:hi - lo]))
+            if path == 'slice':
+                pieces = [None] * world
+                dist.all_gather_object(pieces, piece)
+                pieces.sort(key=lambda q: q[0])
+                ids = np.concatenate([q[1] for q in pieces])
+                ang = np.concatenate([q[2] for q in pieces])
+            else:
+                ids, ang = piece[1], piece[2]
+            if rank == 0:
+                exp = outs[t]
+                n_ev += len(exp['apsis_ids'])
+                ok &= np.array_equal(ids, exp['apsis_ids'])
+                ok &= np.array_equal(res.apsis_offsets, exp['apsis_offsets'])
+                a, b = ang.astype(np.float32), exp['apsis_angles'].astype(np.float32)
+                ok &= a.shape == b.shape and bool(
+                    np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True))
+        report['all_gather' if path is True else 'all_to_all'] = \
+            'ok' if ok else 'MISMATCH'
+        report['sample_events'] = n_ev
+        ok_all &= ok
+    report['parity_vs_oracle'] = 'ok' if ok_all else 'MISMATCH'
+    return report
 
 
 def cpu_baseline(args, snaps, cats, gen, torch):

@@ -356,6 +356,146 @@ int oa_pjoin_stats(uint64_t* out16, int reset);
 int oa_pjoin_step(const oa_pjoin_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Partitioned hash join, second generation (oa_pj2_step, csrc/oa_pj2.cu): the
+ * same step as oa_pjoin_step -- track(j) = region_frame +
+ * compare_radial_velocities + calc_angles (track_orbits.py:147-185, 247-351;
+ * utils.py:4-33) for float32 data and a float32 catalogue -- built around what
+ * the first generation's profile showed (profiles/r02_c1_*): it was bound by
+ * CTA-wide barriers and exposed load latency, not by HBM.
+ *
+ *   - Partitions have a FIXED capacity, so there is no COUNT / SCAN pass: region
+ *     j owns P_j partitions (a power of two) of cap_j record slots each;
+ *     partition p = record slots [base_j + p cap_j, ... + fill[pb_j + p]).  A
+ *     particle's partition is the top log2(P_j) bits of hash32(ID).  P_j never
+ *     shrinks for a halo, so cur partition p joins prev partition p >> shift.
+ *     cap_j = mean + OA_PJ2_SIGMAS sqrt(mean) + 16, mean = ceil(len_j / P_j); a
+ *     partition that still overflows drops the record and counts it in
+ *     `overflow` (the snapshot's result is then invalid; the host raises).
+ *   - Two kinds of work items: SCATTER (tile of OA_PJ2_TILE consecutive
+ *     particles of the snapshot, whatever regions they belong to: halo frame,
+ *     32 B record -> its partition, slot taken with one atomic on the fill
+ *     word) and JOIN (cur partition p of region j against prev partition
+ *     p >> shift in a shared-memory table: sign test, arccos, float16
+ *     accumulator written back into the record, event mark at the previous
+ *     particle's block position).  Items are taken by ticket; the ticket order
+ *     interleaves SCATTER of group g with JOIN of group g - OA_PJ2_LAG (groups =
+ *     runs of regions of ~group_particles particles), so that new records are
+ *     re-read from L2.  A JOIN waits for its group's tile counter.
+ *   - Every CTA has a PRODUCER warp: it takes tickets, waits for the item's
+ *     dependency and moves the item's inputs (tile: IDs, positions, velocities;
+ *     join: both partitions) into one of two shared-memory stages with TMA bulk
+ *     copies (cp.async.bulk + mbarrier complete_tx) while the consumer warps
+ *     work on the other stage.  Consumers never wait for global loads and
+ *     synchronise among themselves with one named barrier per JOIN.
+ * ------------------------------------------------------------------------- */
+#ifndef OA_PJ2_THREADS
+#define OA_PJ2_THREADS 480     /* CONSUMER threads per CTA (+ one producer warp) */
+#endif
+#ifndef OA_PJ2_MIN_CTAS
+#define OA_PJ2_MIN_CTAS 2
+#endif
+#ifndef OA_PJ2_TILE
+#define OA_PJ2_TILE 1408       /* particles per SCATTER item (multiple of 4)   */
+#endif
+#ifndef OA_PJ2_CAP
+#define OA_PJ2_CAP 704         /* record slots per partition at most (<= 1024) */
+#endif
+#ifndef OA_PJ2_TARGET
+#define OA_PJ2_TARGET 416      /* mean records per partition at most           */
+#endif
+#ifndef OA_PJ2_SIGMAS
+#define OA_PJ2_SIGMAS 8        /* head room of a partition in Poisson sigmas   */
+#endif
+#ifndef OA_PJ2_LAG
+#define OA_PJ2_LAG 1           /* groups between a region's SCATTER and its JOIN */
+#endif
+
+typedef struct oa_pj2_region {
+    uint32_t P_cur;       /* partitions of this block (power of two, >= 1)     */
+    uint32_t cap_cur;     /* record slots per partition                        */
+    uint32_t base_cur;    /* first record slot of partition 0                  */
+    uint32_t pb_cur;      /* entry of partition 0 in the fill array            */
+    uint32_t P_prev;      /* 0: the halo has no previous block                 */
+    uint32_t cap_prev;
+    uint32_t base_prev;
+    uint32_t pb_prev;
+    uint32_t shift;       /* P_cur = P_prev << shift                           */
+    uint32_t group;       /* group of regions this block belongs to            */
+    uint32_t join_first;  /* JOIN items before this region (P_cur each when P_prev > 0) */
+    uint32_t reserved;
+} oa_pj2_region;          /* 48 bytes */
+
+typedef struct oa_pj2_args {
+    const float* pos;       /* (n_cur,3), 16-byte aligned (TMA)                */
+    const float* vel;
+    const int64_t* ids;
+    int64_t n_cur;
+    const oa_region* regions;      /* (n_regions,)                             */
+    const oa_pj2_region* plan;     /* (n_regions + 1,)                         */
+    const uint32_t* group_first;   /* (n_groups + 1,) first region of a group  */
+    const uint32_t* group_off;     /* (n_groups + 1,) first particle of a group */
+    const uint32_t* range_start;   /* (n_ranges + 1,) first ticket of a range  */
+    int32_t n_regions;
+    int32_t n_groups;
+    int32_t n_ranges;              /* 2 * (n_groups + OA_PJ2_LAG): range 2 s = SCATTER of group s, 2 s + 1 = JOIN of group s - LAG */
+    int32_t centre_f32;            /* must be 1 (float32 catalogue)            */
+    int32_t bulk_f32;
+    int32_t periodic;
+    int32_t mode;
+    int32_t hubble_on;
+    double box[3];
+    double hubble;
+    double one_plus_z;
+    const void* rec_prev;          /* previous generation: record slots,       */
+    const uint32_t* fill_prev;     /*   fill per partition,                    */
+    uint16_t* mark_prev;           /*   event marks in BLOCK order (n_prev,)   */
+    int64_t n_prev;
+    void* rec_cur;                 /* (n_rec_slots,) 32-byte records           */
+    uint32_t* fill_cur;            /* (n_part_entries,) zeroed by the call     */
+    uint16_t* mark_cur;            /* (n_cur,) written: "no event"             */
+    void* workspace;               /* oa_pj2_workspace_bytes()                 */
+    size_t workspace_bytes;
+    int64_t n_part_entries;
+    int64_t n_rec_slots;
+    int32_t sm_reserve;
+    uint32_t total_tickets;
+    uint32_t* overflow;            /* device word, += 1 per dropped record (never cleared here) */
+} oa_pj2_args;
+
+typedef struct oa_pj2_plan_info {
+    int64_t n_part_entries;
+    int64_t n_rec_slots;
+    uint32_t total_tickets;
+    int32_t n_groups;
+    int32_t n_ranges;
+    uint32_t max_P;
+} oa_pj2_plan_info;
+/* The plan on the HOST (host pointers, no CUDA call).  Per region of THIS
+ * snapshot: prev_P / prev_cap / prev_base / prev_pb of the same halo's previous
+ * block (prev_P 0 = none or empty).  Writes rows[n_regions + 1], the carried
+ * P_out / cap_out / base_out / pb_out [n_regions], group_first and group_off
+ * (capacity n_regions + 1 each), range_start (capacity 2 * (n_regions +
+ * OA_PJ2_LAG) + 1).  `target` <= 0: OA_PJ2_TARGET. */
+int oa_pj2_plan_host(const int64_t* offsets, int n_regions, const uint32_t* prev_P,
+                     const uint32_t* prev_cap, const uint32_t* prev_base,
+                     const uint32_t* prev_pb, int64_t group_particles, int32_t target,
+                     oa_pj2_region* rows, uint32_t* P_out, uint32_t* cap_out,
+                     uint32_t* base_out, uint32_t* pb_out, uint32_t* group_first,
+                     uint32_t* group_off, uint32_t* range_start,
+                     oa_pj2_plan_info* info);
+size_t oa_pj2_workspace_bytes(int n_groups, uint32_t total_tickets);
+/* out[0..7] = THREADS (consumers), MIN_CTAS, TILE, CAP, TARGET, SIGMAS, LAG,
+ * dynamic shared memory per CTA in bytes. */
+void oa_pj2_config(int32_t* out8);
+size_t oa_pj2_args_size(void);
+/* Profiling builds (-DOA_PJ2_STATS=1): out16 = [consumer cycles SCATTER, JOIN |
+ * producer cycles waiting for a dependency, for a free stage | consumer cycles
+ * waiting for a full stage | ... | items at [8..9] | CTA cycles at [12]];
+ * returns 0 without the counters. */
+int oa_pj2_stats(uint64_t* out16, int reset);
+int oa_pj2_step(const oa_pj2_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Ordered selection ("np.argwhere(cond).flatten()", track_orbits.py:315 and
  * the result assembly :199-217): positions i (ascending) of marks that satisfy
  * a predicate, plus per-segment offsets.

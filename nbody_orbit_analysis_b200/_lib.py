@@ -182,6 +182,18 @@ lib.oa_pjoin_config.restype = None
 lib.oa_pjoin_config.argtypes = [C.POINTER(C.c_int32)]
 _pjoin.configure(lib)
 _sig('oa_pjoin_stats', C.c_int, _vp, C.c_int)
+_sig('oa_pj2_workspace_bytes', _sz, C.c_int, C.c_uint32)
+_sig('oa_pj2_args_size', _sz)
+_sig('oa_pj2_plan_host', C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int32,
+     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
+_sig('oa_pj2_step', C.c_int, _vp, _vp)
+_sig('oa_pj2_stats', C.c_int, _vp, C.c_int)
+from . import pj2 as _pj2            # noqa: E402  (struct mirror of oa_pj2_args)
+if lib.oa_pj2_args_size() != C.sizeof(_pj2.PJ2Args):
+    raise ImportError("oa_pj2_args layout mismatch")
+lib.oa_pj2_config.restype = None
+lib.oa_pj2_config.argtypes = [C.POINTER(C.c_int32)]
+_pj2.configure(lib)
 
 EXPORTS = [
     'oa_abi_version', 'oa_last_error', 'oa_device_info', 'oa_record_bytes',
@@ -203,7 +215,8 @@ EXPORTS = [
     'oa_select_gather_events_ids', 'oa_pjoin_workspace_bytes',
     'oa_pjoin_args_size', 'oa_pjoin_step', 'oa_pjoin_plan_host',
     'oa_region_rows_host', 'oa_pjoin_config', 'oa_stage_events',
-    'oa_pjoin_stats',
+    'oa_pjoin_stats', 'oa_pj2_workspace_bytes', 'oa_pj2_args_size',
+    'oa_pj2_plan_host', 'oa_pj2_step', 'oa_pj2_stats', 'oa_pj2_config',
 ]
 
 

@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, pjoin
+from . import _lib, pjoin, pj2
 from ._lib import lib, check, ptr
 
 _F = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
@@ -41,7 +41,10 @@ class Generation:
                  'halo_ids64',
                  # partitioned-join generations (impl='pjoin'): records are
                  # stored partitioned, events take their IDs from `ids`
-                 'pjoin', 'ids', 'part_off', 'pj_bits', 'pj_pb')
+                 'pjoin', 'ids', 'part_off', 'pj_bits', 'pj_pb',
+                 # second-generation partitioned join (impl='pj2'): fixed-
+                 # capacity partitions, fill word per partition
+                 'pj2', 'fill', 'pj2_plan')
 
 
 class StepResult:
@@ -88,10 +91,10 @@ class OrbitTracker:
         #          and catalogue, plain tracking without per-particle outputs)
         import os
         impl = impl or os.environ.get('OA_TRACK_IMPL', 'hash')
-        if impl not in ('hash', 'pjoin'):
-            raise ValueError("impl must be 'hash' or 'pjoin'")
-        if impl == 'pjoin' and onthefly:
-            raise ValueError("impl='pjoin' does not cover the on-the-fly path")
+        if impl not in ('hash', 'pjoin', 'pj2'):
+            raise ValueError("impl must be 'hash', 'pjoin' or 'pj2'")
+        if impl != 'hash' and onthefly:
+            raise ValueError("impl=%r does not cover the on-the-fly path" % impl)
         self.impl = impl
         self._planner = None
         if mode not in _lib.OA_MODE:
@@ -405,19 +408,21 @@ class OrbitTracker:
         gen.halo_ids64 = hx
         gen.gpos = gpos
         gen.buckets = buckets
-        gen.pjoin = self.impl == 'pjoin'
+        gen.pjoin = self.impl in ('pjoin', 'pj2')
+        gen.pj2 = self.impl == 'pj2'
         gen.ids = dev['ids']
         diag = dangle = out_angle = None
         if gen.pjoin:
             if frame_f64 or x64 or not centre_f32 or want_angles or diagnostics:
                 raise _lib.OrbitB200Error(
-                    "impl='pjoin' needs float32 data and region centres and "
+                    "impl=%r needs float32 data and region centres and "
                     "has no per-particle outputs (checkpoint angles, "
-                    "diagnostics); use impl='hash'")
-            if prev is not None and not prev.pjoin:
+                    "diagnostics); use impl='hash'" % self.impl)
+            if prev is not None and (not prev.pjoin or prev.pj2 != gen.pj2):
                 raise _lib.OrbitB200Error("generations of two implementations")
-            self._launch_pjoin(gen, prev, dev, d_rows, prev_index, matched,
-                               lens, bulk_f32, box_size, H, redshift, st)
+            launch = self._launch_pj2 if gen.pj2 else self._launch_pjoin
+            launch(gen, prev, dev, d_rows, prev_index, matched,
+                   lens, bulk_f32, box_size, H, redshift, st)
             tile_ws = a = None
         else:
             # ---- new generation buffers ------------------------------------------
@@ -561,6 +566,9 @@ class OrbitTracker:
                                               reserve=cap // 6)
                 p.h_ang = self._to_host_async(p.d_ang, p.n_spec, 'h_ang',
                                               reserve=cap // 6)
+        p.h_overflow = None
+        if gen.pj2:
+            p.h_overflow = self._to_host_async(self._pj2_overflow, 1, 'h_ovf')
         if derive_bulk:
             p.h_bulk = self._to_host_async(d_bulk_out, 3 * n_h, 'h_bulk')
             p.keep += (d_bulk_out,)
@@ -644,6 +652,79 @@ class OrbitTracker:
         self.launches += 3          # memset, item expansion, persistent kernel
         self._pj_keep = (a, d_pack, ws)
 
+    def _launch_pj2(self, gen, prev, dev, d_rows, prev_index, matched, lens,
+                    bulk_f32, box_size, H, redshift, st):
+        """Enqueue ``oa_pj2_step`` for the current snapshot (see pj2.py)."""
+        n, n_h = gen.n, len(lens)
+        prev_plan = np.zeros((4, n_h), dtype=np.uint32)
+        if prev is not None and matched.any():
+            k = prev_index[matched]
+            nonempty = (prev.offsets[k + 1] - prev.offsets[k]) > 0
+            cols = np.flatnonzero(matched)[nonempty]
+            prev_plan[:, cols] = prev.pj2_plan[:, k[nonempty]]
+        if self._planner is None:
+            self._planner = pj2.Planner(lib)
+            self._pj2_overflow = torch.zeros(4, dtype=torch.int32,
+                                             device=self.device)
+        plan = self._planner(gen.offsets, *prev_plan)
+        gen.pj2_plan = np.stack((plan.P, plan.cap, plan.base, plan.pb))
+        # one packed host->device copy: [rows | group_first | group_off | range_start]
+        parts = (plan.rows, plan.group_first, plan.group_off, plan.range_start)
+        sizes = [-(-v.nbytes // 16) * 16 for v in parts]
+        pack = self._hbuf('pj2pack', sum(sizes), torch.uint8)
+        hp = pack.numpy()
+        at, starts = 0, []
+        for v, sz in zip(parts, sizes):
+            hp[at:at + v.nbytes] = v.view(np.uint8).reshape(-1)
+            starts.append(at)
+            at += sz
+        d_pack = self._buf('pj2pack', pack.numel(), torch.uint8)
+        d_pack.copy_(pack, non_blocking=True)
+        gen.rec = self._buf('rec', max(plan.n_slots, 1) * 32, torch.uint8)
+        gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16)
+        gen.fill = self._buf('fill', max(plan.n_entries, 1), torch.int32)
+        ws_bytes = lib.oa_pj2_workspace_bytes(plan.n_groups, plan.total)
+        ws = self._buf('pj_ws', ws_bytes, torch.uint8)
+
+        a = pj2.PJ2Args()
+        a.pos, a.vel, a.ids = ptr(dev['pos']), ptr(dev['vel']), ptr(dev['ids'])
+        a.n_cur = n
+        a.regions = ptr(d_rows)
+        a.plan = ptr(d_pack[starts[0]:])
+        a.group_first = ptr(d_pack[starts[1]:])
+        a.group_off = ptr(d_pack[starts[2]:])
+        a.range_start = ptr(d_pack[starts[3]:])
+        a.n_regions, a.n_groups, a.n_ranges = n_h, plan.n_groups, plan.n_ranges
+        a.centre_f32, a.bulk_f32 = 1, int(bulk_f32)
+        a.periodic = int(box_size is not None)
+        if box_size is not None:
+            box = np.broadcast_to(np.asarray(box_size, dtype=np.float64), (3,))
+            a.box[0], a.box[1], a.box[2] = float(box[0]), float(box[1]), \
+                float(box[2])
+        a.mode = _lib.OA_MODE[self.mode]
+        a.hubble_on, a.hubble = int(float(H) != 0.0), float(H)
+        a.one_plus_z = 1 + float(redshift)
+        if prev is not None:
+            a.rec_prev, a.fill_prev = ptr(prev.rec), ptr(prev.fill)
+            a.mark_prev, a.n_prev = ptr(prev.mark), prev.n
+        a.rec_cur, a.fill_cur = ptr(gen.rec), ptr(gen.fill)
+        a.mark_cur = ptr(gen.mark)
+        a.workspace, a.workspace_bytes = ptr(ws), ws_bytes
+        a.n_part_entries, a.n_rec_slots = plan.n_entries, plan.n_slots
+        a.total_tickets = plan.total
+        a.sm_reserve = self.sm_reserve
+        a.overflow = ptr(self._pj2_overflow)
+        if self.timing is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), \
+                torch.cuda.Event(enable_timing=True)
+            ev0.record(self._main())
+        check(lib.oa_pj2_step(C.byref(a), st))
+        if self.timing is not None:
+            ev1.record(self._main())
+            self.timing.append((ev0, ev1, n))
+        self.launches += 4          # 2 memsets, item expansion, persistent kernel
+        self._pj_keep = (a, d_pack, ws)
+
     def collect_keep(self, p):
         """``collect`` that leaves the snapshot's device inputs and per-particle
         outputs (``p.keep``, ``p.diag``, ``p.dangle``) alive for the caller."""
@@ -666,6 +747,11 @@ class OrbitTracker:
         res.compacted = p.compacted
         res.prev_gen = p.prev
         p.small_done.synchronize()
+        if p.h_overflow is not None and int(p.h_overflow[0]) != 0:
+            raise _lib.OrbitB200Error(
+                "impl='pj2': %d records did not fit their ID-hash partition "
+                "(head room of %d sigmas exceeded: duplicated or adversarial "
+                "IDs?); use impl='hash'" % (int(p.h_overflow[0]), pj2.SIGMAS))
         if p.derive_bulk:
             res.bulk_velocities = p.h_bulk.numpy().reshape(p.n_h, 3).astype(
                 p.bulk_dtype)

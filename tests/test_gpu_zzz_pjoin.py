@@ -4,19 +4,15 @@ and, at sizes the oracle does not reach, against the hash-table kernel on the
 same device (events, offsets AND float16 angles bit-identical: both paths do
 the same arithmetic with the same CUDA ``acosf``).
 
-Round 1 ended without GPU time to run this kernel on hardware (its stage code is
-validated on the CPU, tests/test_pjoin_emul.py): the tests are opt-in,
-``OA_TEST_PJOIN=1``, so that an unverified kernel cannot take the suite down.
+Both generations of the partitioned join run here: ``impl='pjoin'``
+(csrc/oa_pjoin.cu: COUNT / SCAN / SCATTER / JOIN stages) and ``impl='pj2'``
+(csrc/oa_pj2.cu: fixed-capacity partitions, producer warp + TMA stages).
 """
-import os
-
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('OA_TEST_PJOIN') != '1',
-                                 reason='set OA_TEST_PJOIN=1 (kernel not yet '
-                                        'run on hardware)')]
+pytestmark = [pytest.mark.gpu]
+IMPLS = ['pjoin', 'pj2']
 
 CASES = [
     (60000, 37, 6, {}),
@@ -28,20 +24,25 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('target', [None, 300])
 @pytest.mark.parametrize('mode', ['pericentric', 'apocentric'])
 @pytest.mark.parametrize('case', CASES, ids=[
     'plain', 'late', 'hubble_300h', 'nobulk', 'nfw_nonperiodic', 'tiny_blocks'])
-def test_track_orbits_pjoin_matches_oracle(case, mode, target, tmp_path,
+def test_track_orbits_pjoin_matches_oracle(case, mode, target, impl, tmp_path,
                                            monkeypatch):
     from test_gpu_track import compare_track_trees
-    from nbody_orbit_analysis_b200 import pjoin, storage, track_orbits
+    from nbody_orbit_analysis_b200 import pj2, pjoin, storage, track_orbits
     from nbody_orbit_analysis_b200.synth import SynthSim
     from oracle import orbit_oracle as oracle
-    monkeypatch.setenv('OA_TRACK_IMPL', 'pjoin')
+    monkeypatch.setenv('OA_TRACK_IMPL', impl)
     if target is not None:       # small partitions: every stage at these sizes
         monkeypatch.setattr(pjoin, 'TARGET', target)
         monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
+        # (pj2: partitions of ~40 records, many groups, regions that grow and
+        # shrink across partition counts)
+        monkeypatch.setattr(pj2, 'TARGET', 40)
+        monkeypatch.setattr(pj2, 'GROUP_PARTICLES', 1 << 12)
     n, nh, ns, kw = case
     sim = SynthSim(n, nh, ns, dtype=np.float32, catalogue_dtype=np.float32, **kw)
     f_gpu, f_cpu = str(tmp_path / 'gpu.h5'), str(tmp_path / 'cpu.h5')
@@ -55,8 +56,9 @@ def test_track_orbits_pjoin_matches_oracle(case, mode, target, tmp_path,
                         derived_bulk=not kw.get('catalogue_bulk', True))
 
 
+@pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('n,halos', [(3000000, 40), (2000000, 2000)])
-def test_pjoin_equals_hash_kernel_at_scale(n, halos):
+def test_pjoin_equals_hash_kernel_at_scale(n, halos, impl):
     """Default partition size, regions of up to ~10^5 particles, several
     groups of regions in flight: identical event lists from both kernels."""
     import torch
@@ -64,18 +66,18 @@ def test_pjoin_equals_hash_kernel_at_scale(n, halos):
     from nbody_orbit_analysis_b200.tracker import OrbitTracker
     gen = DeviceSynth(n, halos)
     exists = np.arange(halos)
-    trk = {impl: OrbitTracker(impl=impl) for impl in ('hash', 'pjoin')}
+    trk = {i: OrbitTracker(impl=i) for i in ('hash', impl)}
     n_events = 0
     for t in range(5):
         dev, m, offsets = gen.snapshot(t)
         pos, rad, bulk = gen.regions(t)
-        res = {impl: tr.step_device(dev, m, np.float32, np.int64, offsets,
-                                    exists, pos, bulk, 0.0,
-                                    box_size=gen.host.box)
-               for impl, tr in trk.items()}
+        res = {i: tr.step_device(dev, m, np.float32, np.int64, offsets,
+                                 exists, pos, bulk, 0.0,
+                                 box_size=gen.host.box)
+               for i, tr in trk.items()}
         if t == 0:
             continue
-        a, b = res['hash'], res['pjoin']
+        a, b = res['hash'], res[impl]
         assert a.n_events == b.n_events > 0
         assert np.array_equal(a.apsis_offsets, b.apsis_offsets)
         assert np.array_equal(a.apsis_ids, b.apsis_ids)

@@ -248,7 +248,7 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1):
     args = argparse.Namespace(
         gpus=world, steps=3, warmup=3, impl='b200', particles=6000, halos=7,
         mode='pericentric', depth=2, profile=False, no_e2e=world > 2,
-        no_cpu=True, cpu_particles=2000)
+        no_cpu=batch > 1, cpu_particles=2000)
     buf = io.StringIO()
     with fc.install(emul_lib), contextlib.redirect_stdout(buf):
         bench.run_b200(args)
@@ -274,6 +274,13 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch
     multi = json.loads(lines[-1])
     assert multi['n_gpus'] == world and multi['value'] > 0
     assert multi['events_per_step'] > 0
+    assert multi['parity'] == 'ok'
+    if batch == 1:
+        # a sample of whole halos, put back together from all ranks' shards,
+        # through both exchange paths against the oracle on rank 0
+        par = multi['parity_multi_gpu']
+        assert par['parity_vs_oracle'] == 'ok' and par['sample_events'] > 0
+        assert par['all_gather'] == par['all_to_all'] == 'ok'
     if world == 2:
         assert multi['e2e']['value'] > 0
         assert multi['e2e']['events_per_step'] == multi['events_per_step']
