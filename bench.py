@@ -484,9 +484,10 @@ def run_b200(args):
             sampler.start()
         from collections import deque
         depth = max(1, args.depth)     # snapshots in flight (tracker ring = 3)
-        if comm is not None:
+        if comm is not None and comm.batch_size == 1:
             # the exchange of snapshot k is finished one snapshot later and may
             # have to be repeated from k's device buffers: keep them un-recycled
+            # (a batch is exchanged from staging buffers of its own)
             depth = 1
         queue = deque()
         for t in range(0, W + 1):      # same pipelined pattern as the timed loop
@@ -536,8 +537,8 @@ def run_b200(args):
             import pstats
             prof.disable()
             st_ = pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime')
-            st_.print_stats(12)
-            st_.print_callers('torch.empty')
+            st_.print_stats(45)
+            st_.sort_stats('cumulative').print_stats(30)
         ev1.record()
         barrier()
         wall1 = time.time()
@@ -773,38 +774,64 @@ def multi_rank_parity(args, snaps, cats, gen, comm, world, rank, torch, dist):
     report = {'halos': ncols, 'snapshots': n_s - 1,
               'particles_per_snapshot': int(len(full[-1]['ids']))}
     ok_all = True
-    for path in (True, 'slice'):
+    def check(t, ids, ang, offsets):
+        exp = outs[t]
+        a, b = ang.astype(np.float32), exp['apsis_angles'].astype(np.float32)
+        return (np.array_equal(ids, exp['apsis_ids'])
+                and np.array_equal(offsets, exp['apsis_offsets'])
+                and a.shape == b.shape and bool(
+                    np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True)))
+
+    def whole(res):
+        """This rank's slice of a merged result -> the global lists (rank 0)."""
+        lo, hi = res.host_slice
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (lo, np.array(res.apsis_ids[:hi - lo]),
+                                        np.array(res.apsis_angles[:hi - lo])))
+        pieces.sort(key=lambda q: q[0])
+        return (np.concatenate([q[1] for q in pieces]),
+                np.concatenate([q[2] for q in pieces]))
+
+    for path in (True, 'slice', 'batch'):
         trk = OrbitTracker(mode=args.mode)
         trk.events_on_device = True
         c = sharded.Comm(world, rank)
-        ok, n_ev = True, 0
+        if path == 'batch':
+            c.batch_size = 3          # 4 event-bearing snapshots: a full batch + a flushed one
+        ok, n_ev, staged = True, 0, []
         for t in range(n_s):
             local, gpos = sharded.shard_snapshot(full[t], rank, world)
             res = trk.step(local, exists, cat[t][0], cat[t][2], 0.0, gpos=gpos)
             if t == 0:
                 continue
+            if path == 'batch':
+                c.stage_merge(trk, res)
+                staged.append(t)
+                if t == n_s - 1:
+                    c.launch_batch(trk)
+                done = []
+                while c._launched:
+                    done += c.finish_batch(c._launched[0])
+                for r in done:
+                    tt = staged.pop(0)
+                    ids, ang = whole(r)
+                    if rank == 0:
+                        n_ev += len(outs[tt]['apsis_ids'])
+                        ok &= check(tt, ids, ang, r.apsis_offsets)
+                continue
             res = c.merge_events(trk, res, to_host=path)
-            lo, hi = res.host_slice
-            piece = (lo, np.array(res.apsis_ids[:hi - lo]),
-                     np.array(res.apsis_angles[:hi - lo]))
             if path == 'slice':
-                pieces = [None] * world
-                dist.all_gather_object(pieces, piece)
-                pieces.sort(key=lambda q: q[0])
-                ids = np.concatenate([q[1] for q in pieces])
-                ang = np.concatenate([q[2] for q in pieces])
+                ids, ang = whole(res)
             else:
-                ids, ang = piece[1], piece[2]
+                lo, hi = res.host_slice
+                ids, ang = np.array(res.apsis_ids[:hi - lo]), \
+                    np.array(res.apsis_angles[:hi - lo])
             if rank == 0:
-                exp = outs[t]
-                n_ev += len(exp['apsis_ids'])
-                ok &= np.array_equal(ids, exp['apsis_ids'])
-                ok &= np.array_equal(res.apsis_offsets, exp['apsis_offsets'])
-                a, b = ang.astype(np.float32), exp['apsis_angles'].astype(np.float32)
-                ok &= a.shape == b.shape and bool(
-                    np.allclose(a, b, rtol=2e-3, atol=2e-3, equal_nan=True))
-        report['all_gather' if path is True else 'all_to_all'] = \
-            'ok' if ok else 'MISMATCH'
+                n_ev += len(outs[t]['apsis_ids'])
+                ok &= check(t, ids, ang, res.apsis_offsets)
+        ok &= not staged
+        report[{True: 'all_gather', 'slice': 'all_to_all',
+                'batch': 'batched_all_to_all'}[path]] = 'ok' if ok else 'MISMATCH'
         report['sample_events'] = n_ev
         ok_all &= ok
     report['parity_vs_oracle'] = 'ok' if ok_all else 'MISMATCH'

@@ -322,9 +322,14 @@ class Comm:
             check(lib.oa_split_quantiles(ptr(gen.gpos), ptr(res.d_sel),
                                          ptr(res.d_small), n_seg, W, ptr(prop),
                                          st))
-            prop_all = splitters if splitters is not None else self._splitters
+            persistent = getattr(res, 'persistent', False)
+            prop_all = splitters if splitters is not None else (
+                None if persistent else self._splitters)
             if prop_all is None:
-                # first exchange: nothing to lag behind
+                # first exchange: nothing to lag behind.  A batch always splits by
+                # its own quantiles: batches differ in length (the last one, the
+                # one flushed at a checkpoint), and one more small all-gather per
+                # K snapshots costs nothing
                 prop_all = torch.empty(W * n_prop, **i64)
                 dist.all_gather_into_tensor(prop_all, prop.contiguous())
             h.splitters = prop_all
@@ -344,7 +349,8 @@ class Comm:
             meta_all = torch.empty(W * meta.numel(), **i64)
             dist.all_gather_into_tensor(meta_all, meta)
             # the proposals of all ranks, [W][W - 1], for the next exchange
-            self._splitters = meta_all.view(W, -1)[:, 2 + n_cnt:].contiguous()
+            if not persistent:
+                self._splitters = meta_all.view(W, -1)[:, 2 + n_cnt:].contiguous()
             tracker.launches += 5
             done = self._event()
             done.record(self.stream)
@@ -481,15 +487,51 @@ class Comm:
         if h.to_host:
             gen = res.prev_gen
             self._results += 1
+            # (a batch: K snapshots' events in buffers of their own, reserved once
+            # by _reserve_batch; a single snapshot: room for the send capacity)
+            batch = getattr(res, 'persistent', False)
             h_ids, h_ang, ready = h.tracker.to_host_async(
                 res.d_ids, res.d_ang, stream=self.stream,
-                names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap),
+                names=('xb_ids', 'xb_ang') if batch else ('x_ids', 'x_ang'),
+                reserve=int(1.25 * (hi - lo)) if batch else max(hi - lo, self._cap),
                 step=self._results)
             res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
             res.apsis_angles = h_ang.numpy().view(np.float16)
             res.host_ready = ready
         h.keep = None
         return res
+
+    def _reserve_batch(self, tracker, n_local, n_seg):
+        """Called with the first snapshot staged on `tracker`: allocate what a
+        full batch will need -- staging sets, send / receive / merge buffers (left
+        in torch's caching allocator) and the pinned result buffers -- so that no
+        exchange pays for cudaMalloc / page pinning later (pinning ~0.5 GB costs
+        tenths of a second).  Every rank calls it at the same snapshot."""
+        K, W = self.batch_size, self.world
+        t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per_snapshot = max(int(t.item()), 1024)
+        self._cap = max(self._cap or 0, self._round_cap(K * per_snapshot))
+        n_ev = int(1.3 * K * per_snapshot)
+        keep_open = self._open
+        for slot in range(3):
+            self._open = _Exchange()
+            self._open.n_local = self._open.n_seg = 0
+            self._staging(slot, n_ev, K * (n_seg + 1) + 1)
+        self._open = keep_open
+        if self.device.type == 'cuda':
+            cap = self._block_cap()
+            blk = lib.oa_exchange_bytes(0, cap)
+            with self._on_stream():
+                warm = [torch.empty(W * blk, dtype=torch.uint8, device=self.device)
+                        for _ in range(2)]
+                warm.append(torch.empty(W * cap, dtype=torch.int64, device=self.device))
+                warm.append(torch.empty(W * cap, dtype=torch.int16, device=self.device))
+            del warm
+        if hasattr(tracker, '_hbuf'):         # (the CPU stand-in has no pinned rings)
+            for k in range(tracker.HOST_RING):
+                tracker._hbuf('xb_ids', n_ev, torch.int64, k)
+                tracker._hbuf('xb_ang', n_ev, torch.int16, k)
 
     # -- events: several snapshots per exchange -----------------------------------
     # The tracking of later snapshots does not need the merged events, so the
@@ -512,12 +554,15 @@ class Comm:
             self.stream = _HostStream() if self.device.type != 'cuda' \
                 else torch.cuda.Stream(self.device)
         b = self._open
+        n_local, n_seg = int(res.n_events), len(res.apsis_offsets) - 1
+        if getattr(self, '_reserved_for', None) is not tracker:
+            self._reserved_for = tracker
+            self._reserve_batch(tracker, n_local, n_seg)
         if b is None:
             b = self._open = _Exchange()
             b.items, b.n_local, b.n_seg, b.h = [], 0, 0, None
             b.slot = self._batches % 3          # staging set (2 batches alive)
             self._batches += 1
-        n_local, n_seg = int(res.n_events), len(res.apsis_offsets) - 1
         st_set = self._staging(b.slot, b.n_local + n_local, b.n_seg + n_seg + 1)
         if res.compacted is not None:
             self.stream.wait_event(res.compacted)

@@ -2,10 +2,24 @@
 
 Same signature, callback protocol and result-file layout as the reference
 ``orbitanalysis/track_orbits.py:9-11``; the per-halo
-numpy loop (``:147-217``) is replaced by ``OrbitTracker.step`` -- one fused CUDA
-kernel per snapshot plus an ordered event compaction.  Host code here only does
-what the reference's driver does outside ``track(j)``: argument validation,
-snapshot ordering, resume bookkeeping and writing the HDF5 layout.
+numpy loop (``:147-217``) is replaced by ``OrbitTracker.submit/collect`` -- one
+fused CUDA kernel per snapshot plus an ordered event compaction.  Host code here
+only does what the reference's driver does outside ``track(j)``: argument
+validation, snapshot ordering, resume bookkeeping and writing the HDF5 layout.
+
+The driver is a software pipeline: while snapshot s is on the GPU, the user's
+``regions`` / ``load_snapshot_data`` callbacks run for s+1 and the result group
+of s-1 is written, so callbacks, host->device copies, kernels and file writes
+overlap (the reference is strictly serial, ``track_orbits.py:104-240``).
+
+Multi-GPU (one process per GPU, ``torch.distributed`` initialised by the
+launcher, e.g. ``torchrun``): particles are sharded by ``id mod world``
+(SURVEY.md section 8(e)); rank 0's catalogue is broadcast, every rank tracks its
+shard, the event lists are merged in the reference's order
+(``track_orbits.py:199-217, 315-316``) and rank 0 writes the file.  The loader
+may return the whole snapshot (it is sharded here) or this rank's shard
+together with ``snapshot['_gpos']`` = each particle's position in the unsharded
+arrays (loader-side sharding: no rank ever holds the whole snapshot).
 
 Deliberate, documented deviations (DESIGN.md "Quirks"):
 * ``npool`` is accepted and ignored (it only changes scheduling);
@@ -13,20 +27,25 @@ Deliberate, documented deviations (DESIGN.md "Quirks"):
   only when row 0 is processed (the reference crashes on ``'r+'`` otherwise,
   ``track_orbits.py:140,375``);
 * a derived bulk velocity (``regions`` returned ``None``) is accumulated in
-  float64 (reference: sequential accumulation in the input dtype).
+  float64 (reference: sequential accumulation in the input dtype); sharded runs
+  need catalogue bulk velocities;
+* the ``ValueError`` of a snapshot without matched halos (``:216``) is raised
+  when that snapshot's results are collected, one loop iteration later.
 """
 import time
+from collections import deque
 
 import numpy as np
 
 from . import storage
+from .sharded import shard_snapshot
 from .tracker import OrbitTracker, require_cuda
 from .utils import hubble_parameter
 
 
 def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
                  savefile, mode='pericentric', checkpoint=False, resume=False,
-                 npool=1, verbose=True, device=None):
+                 npool=1, verbose=True, device=None, comm=None):
     """Track the orbits of particles in gravitating systems (GPU path).
 
     Parameters are those of the reference (``track_orbits.py:13-71``):
@@ -44,6 +63,9 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
     checkpoint, resume : as in the reference (``:93-101, 229-232, 390-394``)
     npool : ignored
     device : optional torch device (extension; default current CUDA device)
+    comm : extension.  None (default): shard over the ranks of an initialised
+        ``torch.distributed`` process group, single GPU otherwise; False: never
+        shard; a ``sharded.Comm``: use it
     """
     if len(main_branches) != len(snapshot_numbers):
         raise ValueError(
@@ -75,9 +97,71 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
         main_branches = main_branches[first:]
 
     tracker = OrbitTracker(mode=mode, device=device)
+    comm = _communicator(comm)
+    sharded_run = comm is not None
+    rank = comm.rank if sharded_run else 0
+    writer = rank == 0
+    verbose = verbose and writer
+    if sharded_run:
+        tracker.events_on_device = True
+    ckpt_name = savefile + '.checkpoint' + ('.%d' % rank if sharded_run else '')
     tag = mode[:-3] + 'er'
     istart, started, initialised = 0, False, bool(resume)
     prev_halo_exists = None
+    last_snap = snapshot_numbers[-1]
+
+    def write(e, res):
+        """Result group of one snapshot (``track_orbits.py:366-397``)."""
+        if res.apsis_ids is None or len(res.hinds) == 0:
+            # reference: np.concatenate([]) of an empty list (:216)
+            raise ValueError("need at least one array to concatenate")
+        if res.host_ready is not None:
+            res.host_ready.synchronize()
+        if checkpoint:
+            with storage.File(ckpt_name, 'w') as hf:
+                hf.create_dataset('angles', data=e.angles)
+        if not writer:
+            return
+        t0 = time.time()
+        hinds = res.hinds
+        with storage.File(savefile, 'r+') as hf:
+            g = hf.create_group('snapshot_%03d' % e.snap_no)
+            g.create_dataset('region_offsets', data=res.apsis_offsets)
+            g.create_dataset(tag + '_IDs', data=res.apsis_ids)
+            g.create_dataset('angles', data=res.apsis_angles)
+            g.create_dataset('halo_IDs', data=e.halo_ids[hinds])
+            if e.snap_no != last_snap:
+                g.create_dataset('final_descendant_IDs',
+                                 data=main_branches[-1][e.prev_halo_exists])
+            g.create_dataset('region_radii', data=e.radii[hinds])
+            g.create_dataset('region_positions', data=e.positions[hinds])
+            g.create_dataset('bulk_velocities', data=res.bulk_velocities[hinds])
+        if verbose:
+            print('Saved snapshot {} to file ({} s)\n'.format(
+                '%03d' % e.snap_no, time.time() - t0))
+
+    pending = deque()      # submitted, not collected
+    merging = deque()      # collected, event exchange in flight (multi-GPU)
+
+    def finish(e):
+        res = tracker.collect(e.p)
+        e.p = None
+        e.angles = res.angles
+        if verbose:
+            print('Finished {} detection for snapshot {} ({} s after its '
+                  'submission)\n'.format(tag, '%03d' % e.snap_no,
+                                         time.time() - e.t0))
+        if not e.has_events:
+            return
+        if not sharded_run:
+            write(e, res)
+            return
+        if res.apsis_offsets is None or len(res.hinds) == 0:
+            raise ValueError("need at least one array to concatenate")
+        merging.append((e, comm.start_merge(tracker, res, to_host=True)))
+        while len(merging) > 1:
+            e0, h = merging.popleft()
+            write(e0, comm.finish_merge(h))
 
     for i, (halo_ids, snap_no) in enumerate(
             zip(main_branches, snapshot_numbers)):
@@ -91,10 +175,30 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
                 istart = i + 1
             continue
         halo_ids_ = halo_ids[halo_exists]
-        region_positions, region_radii, region_bulk_vels = regions(
-            snap_no, halo_ids_)
+        if sharded_run:
+            # the catalogue comes from rank 0; the other ranks do
+            # not call `regions`
+            cat = regions(snap_no, halo_ids_) if writer else (None, None, None)
+            region_positions, region_radii, region_bulk_vels = \
+                _broadcast_catalogue(comm, cat, len(halo_ids_))
+            if region_bulk_vels is None:
+                raise ValueError(
+                    "sharded tracking needs catalogue bulk velocities "
+                    "(regions() returned None for them)")
+        else:
+            region_positions, region_radii, region_bulk_vels = regions(
+                snap_no, halo_ids_)
         snapshot = load_snapshot_data(snap_no, region_positions, region_radii)
-        if len(snapshot['coordinates']) == 0:
+        gpos = None
+        if sharded_run:
+            if '_gpos' in snapshot:
+                gpos = np.ascontiguousarray(snapshot['_gpos'], dtype=np.int64)
+            else:
+                snapshot, gpos = shard_snapshot(snapshot, rank, comm.world)
+            empty = _all_empty(comm, len(snapshot['coordinates']))
+        else:
+            empty = len(snapshot['coordinates']) == 0
+        if empty:
             if not started:
                 istart = i + 1
             continue
@@ -105,57 +209,99 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
             snapshot['Omega_L'], snapshot.get('Omega_k', 0))
 
         if not initialised:
-            with storage.File(savefile, 'w') as hf:
-                hf.attrs['mode'] = mode
-                if 'box_size' in snapshot:
-                    hf.attrs['box_size'] = snapshot['box_size']
+            if writer:
+                with storage.File(savefile, 'w') as hf:
+                    hf.attrs['mode'] = mode
+                    if 'box_size' in snapshot:
+                        hf.attrs['box_size'] = snapshot['box_size']
             initialised = True
             if verbose:
                 print('Savefile initialized\n')
 
-        t0 = time.time()
         if i <= istart:
             tracker.prev = None       # first processed snapshot: no matching
-        res = tracker.step(
-            snapshot, halo_exists, np.asarray(region_positions),
-            region_bulk_vels, H, want_angles=checkpoint)
-        if verbose:
-            print('Finished {} detection for snapshot {} in {} s\n'.format(
-                tag, '%03d' % snap_no, time.time() - t0))
-
-        if i > istart:
-            if res.apsis_ids is None or len(res.hinds) == 0:
-                # reference: np.concatenate([]) of an empty list (:216)
-                raise ValueError("need at least one array to concatenate")
-            t0 = time.time()
-            hinds = res.hinds
-            with storage.File(savefile, 'r+') as hf:
-                g = hf.create_group('snapshot_%03d' % snap_no)
-                g.create_dataset('region_offsets', data=res.apsis_offsets)
-                g.create_dataset(tag + '_IDs', data=res.apsis_ids)
-                g.create_dataset('angles', data=res.apsis_angles)
-                g.create_dataset('halo_IDs', data=halo_ids_[hinds])
-                if snap_no != snapshot_numbers[-1]:
-                    g.create_dataset(
-                        'final_descendant_IDs',
-                        data=main_branches[-1][prev_halo_exists])
-                g.create_dataset(
-                    'region_radii', data=np.asarray(region_radii)[hinds])
-                g.create_dataset(
-                    'region_positions',
-                    data=np.asarray(region_positions)[hinds])
-                g.create_dataset(
-                    'bulk_velocities', data=res.bulk_velocities[hinds])
-            if checkpoint:
-                with storage.File(savefile + '.checkpoint', 'w') as hf:
-                    hf.create_dataset('angles', data=res.angles)
-            if verbose:
-                print('Saved to file ({} s)\n'.format(time.time() - t0))
-        elif resume:
-            with storage.File(savefile + '.checkpoint', 'r') as hf:
+        e = _Entry()
+        e.snap_no, e.halo_ids, e.t0 = snap_no, halo_ids_, time.time()
+        e.positions, e.radii = np.asarray(region_positions), \
+            np.asarray(region_radii)
+        e.prev_halo_exists, e.has_events = prev_halo_exists, i > istart
+        e.p = tracker.submit(
+            snapshot, halo_exists, e.positions, region_bulk_vels, H,
+            want_angles=checkpoint, gpos=gpos)
+        if resume and i <= istart:
+            with storage.File(ckpt_name, 'r') as hf:
                 tracker.load_angles(hf['angles'][:])
+        pending.append(e)
+        # results of the PREVIOUS snapshot: collected and written while this one
+        # is on the GPU
+        while len(pending) > 1:
+            finish(pending.popleft())
         prev_halo_exists = halo_exists
+
+    while pending:
+        finish(pending.popleft())
+    while merging:
+        e0, h = merging.popleft()
+        write(e0, comm.finish_merge(h))
 
     if verbose:
         print('Finished {} detection for all snapshots in {} s\n'.format(
             tag, time.time() - t_start))
+
+
+class _Entry:
+    """A submitted snapshot: what its result group needs besides the events."""
+    pass
+
+
+def _communicator(comm):
+    """``comm`` argument -> ``sharded.Comm`` or None (single GPU).  Default:
+    shard when ``torch.distributed`` is initialised with more than one rank."""
+    if comm is False:
+        return None
+    if comm is None or comm is True:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1):
+            return None
+        from .sharded import Comm
+        return Comm()
+    return comm
+
+
+def _broadcast_catalogue(comm, cat, n_h):
+    """Rank 0's ``regions()`` output on every rank, dtypes included."""
+    import torch
+    import torch.distributed as dist
+    pos, rad, bulk = cat
+    meta = torch.zeros(4, dtype=torch.int64, device=comm.device)
+    if comm.rank == 0:
+        pos, rad = np.asarray(pos), np.asarray(rad)
+        code = {np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+        meta[0] = code.get(pos.dtype, 2)
+        meta[1] = code.get(rad.dtype, 2)
+        meta[2] = 0 if bulk is None else code.get(np.asarray(bulk).dtype, 2)
+        meta[3] = len(rad)
+    dist.broadcast(meta, src=0)
+    m = meta.cpu().numpy()
+    dt = {1: np.float32, 2: np.float64}
+    if comm.rank != 0:
+        n = int(m[3])
+        pos = np.zeros((n, 3), dtype=dt[int(m[0])])
+        rad = np.zeros(n, dtype=dt[int(m[1])])
+        bulk = np.zeros((n, 3), dtype=dt[int(m[2])]) if m[2] else None
+    else:
+        pos = pos.astype(dt[int(m[0])], copy=False)
+        rad = rad.astype(dt[int(m[1])], copy=False)
+        bulk = None if bulk is None else \
+            np.asarray(bulk).astype(dt[int(m[2])], copy=False)
+    return comm.broadcast_catalogue(pos, rad, bulk)
+
+
+def _all_empty(comm, n_local):
+    """True when no rank holds a particle of this snapshot."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([n_local], dtype=torch.int64, device=comm.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item()) == 0

@@ -281,6 +281,7 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch
         par = multi['parity_multi_gpu']
         assert par['parity_vs_oracle'] == 'ok' and par['sample_events'] > 0
         assert par['all_gather'] == par['all_to_all'] == 'ok'
+        assert par['batched_all_to_all'] == 'ok'
     if world == 2:
         assert multi['e2e']['value'] > 0
         assert multi['e2e']['events_per_step'] == multi['events_per_step']
@@ -378,3 +379,68 @@ def test_pjoin_empty_block_and_vanishing_halo(emul, pjoin_env, monkeypatch, tmp_
     oracle.track_orbits(sim.snapshot_numbers, mb, sim.regions, load, f_cpu,
                         storage=storage)
     compare_track_trees(storage.tree(f_dev), storage.tree(f_cpu), data_f64=False)
+
+
+# ---------------------------------------------------------------------------
+# the drop-in entry point, sharded over 2 ranks (gloo), against the oracle
+# ---------------------------------------------------------------------------
+def _entry_rank(rank, world, port, emul_path, out_dir, loader_side):
+    import ctypes as C
+    import sys
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      OA_TRACK_IMPL='pjoin', OA_FAKE_CTAS='1')
+    import exchange_emul
+    import fake_cuda as fc
+    from nbody_orbit_analysis_b200 import pjoin as pj, sharded, track_orbits
+    emul_lib = C.CDLL(emul_path)
+    emul_lib.pj_emul_step.argtypes = [C.POINTER(pj.PJoinArgs), C.c_int]
+    pj.TARGET, pj.LAG_PARTICLES = 400, 1 << 12
+    exchange_emul.install(sharded)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sim = SynthSim(24000, 7, 5, dtype=np.float32, catalogue_dtype=np.float32,
+                   late_halos=0.3)
+    calls = {'regions': 0}
+
+    def regions(sn, halo_ids):
+        calls['regions'] += 1
+        return sim.regions(sn, halo_ids)
+
+    def loader(sn, pos, rad):
+        snap = sim.load_snapshot_data(sn, pos, rad)
+        if loader_side:                 # this rank's shard + global positions
+            snap, gpos = sharded.shard_snapshot(snap, rank, world)
+            snap['_gpos'] = gpos
+        return snap
+    out = os.path.join(out_dir, 'sharded.h5')
+    with fc.install(emul_lib):
+        track_orbits.track_orbits(sim.snapshot_numbers, sim.main_branches,
+                                  regions, loader, out, verbose=False,
+                                  device='cpu')
+    # the catalogue is read on rank 0 only and broadcast
+    assert (calls['regions'] > 0) == (rank == 0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('loader_side', [False, True])
+def test_track_orbits_sharded_entry_point(emul, tmp_path, loader_side):
+    """``track_orbits`` under a 2-rank process group: catalogue broadcast from
+    rank 0, particles sharded by ID (by the driver, or by the loader with
+    ``_gpos``), events merged in the reference order, rank 0 writes the file --
+    which must equal the oracle's single-process file."""
+    import torch.multiprocessing as mp
+    from test_sharded_gloo import _free_port
+    mp.spawn(_entry_rank, args=(2, _free_port(), emul._name, str(tmp_path),
+                                loader_side), nprocs=2, join=True)
+    sim = SynthSim(24000, 7, 5, dtype=np.float32, catalogue_dtype=np.float32,
+                   late_halos=0.3)
+    f_cpu = str(tmp_path / 'cpu.h5')
+    oracle.track_orbits(sim.snapshot_numbers, sim.main_branches, sim.regions,
+                        sim.load_snapshot_data, f_cpu, storage=storage)
+    got, exp = storage.tree(str(tmp_path / 'sharded.h5')), storage.tree(f_cpu)
+    assert sum(len(v) for k, v in exp.items() if k.endswith('er_IDs')) > 0
+    compare_track_trees(got, exp, data_f64=False, derived_bulk=False)
