@@ -409,15 +409,34 @@ def run_b200(args):
         phases[name] = phases.get(name, 0.0) + time.perf_counter() - t0
         return out
 
+    CAT_BLOCK = int(os.environ.get('OA_CAT_BLOCK', '16'))
+    cat_done = {}
+
+    def cat_block(b):
+        """Broadcast the catalogues of snapshots [b CAT_BLOCK, (b+1) CAT_BLOCK)
+        as ONE catalogue (the rows of the snapshots back to back)."""
+        ts = range(b * CAT_BLOCK, min((b + 1) * CAT_BLOCK, n_snap))
+        return comm.start_broadcast(*[np.concatenate([cats[t][k] for t in ts])
+                                      for k in range(3)])
+
     def catalogue(t):
-        """This snapshot's catalogue; multi-GPU: broadcast from rank 0, started
-        one snapshot ahead so that it never stalls the submission."""
+        """This snapshot's catalogue; multi-GPU: broadcast from rank 0 (SURVEY
+        8(e)), a block of snapshots per collective, one block ahead, so that it
+        neither stalls the submission nor costs a collective per snapshot."""
         if comm is None:
             return cats[t]
-        h = cat_ahead.pop(t, None) or comm.start_broadcast(*cats[t])
-        if t + 1 < n_snap:
-            cat_ahead[t + 1] = comm.start_broadcast(*cats[t + 1])
-        return comm.finish_broadcast(h)
+        b = t // CAT_BLOCK
+        if b not in cat_done:
+            h = cat_ahead.pop(b, None) or cat_block(b)
+            if (b + 1) * CAT_BLOCK < n_snap:
+                cat_ahead[b + 1] = cat_block(b + 1)
+            pos, rad, bulk = comm.finish_broadcast(h)
+            cat_done.clear()
+            cat_done[b] = (pos, rad, bulk)
+        pos, rad, bulk = cat_done[b]
+        lo = (t - b * CAT_BLOCK) * args.halos
+        hi = lo + args.halos
+        return pos[lo:hi], rad[lo:hi], bulk[lo:hi]
 
     def submit_step(trk, t, host=None):
         pos, rad, bulk = timed('catalogue', catalogue, t)
@@ -784,6 +803,8 @@ def multi_rank_parity(args, snaps, cats, gen, comm, world, rank, torch, dist):
 
     def whole(res):
         """This rank's slice of a merged result -> the global lists (rank 0)."""
+        if res.host_ready is not None:
+            res.host_ready.synchronize()
         lo, hi = res.host_slice
         pieces = [None] * world
         dist.all_gather_object(pieces, (lo, np.array(res.apsis_ids[:hi - lo]),

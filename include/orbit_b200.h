@@ -70,6 +70,12 @@ typedef struct oa_region {
     int64_t reserved;
 } oa_region;             /* 128 bytes; the table must be 16-byte aligned      */
 
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: the small
+ * read-backs of a snapshot (reference: the numpy arrays `track` returns,
+ * track_orbits.py:186-187, live on the host) without a stream switch in the
+ * host framework.  Pinned host memory for a truly asynchronous copy. */
+int oa_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* The region table on the HOST (host pointers, no CUDA call): what the Python
  * driver otherwise assembles with ~20 numpy calls per snapshot.  For region j:
  * centre / bulk from the catalogue arrays (float32 or float64, `bulk` may be NULL
@@ -692,6 +698,43 @@ int oa_vote_reduce(const uint64_t* sorted_keys, int64_t m, int n_desc,
 /* marks[i] = float16(angles[i]) > cut  (postprocessing.py:124-127). */
 int oa_angle_cut(const uint16_t* angles, int64_t n, double cut, uint16_t* marks,
                  void* stream);
+/* Region extraction, the loader step in front of the tracking path
+ * (example_script.py:36-67: per halo, np.argwhere(|recenter(x - c)| < R) over all
+ * particles).  A uniform grid (grid_lo / grid_inv_cell / grid_dim; cell index =
+ * floor((x - lo) inv_cell), wrapped when periodic) holds per cell the regions
+ * whose sphere touches it (CSR cell_start / cell_regions, built on the host);
+ * one thread per particle tests the regions of its cell with numpy's arithmetic
+ * (frame_dtype = promoted dtype of `coordinates - position`; utils.py:13-33) and
+ * emits key = region << 32 | particle.  keys == NULL counts only; *counter
+ * (device) receives the number of pairs.  Sorting the keys (oa_sort_pairs_u64)
+ * gives the reference layout; oa_gather_by_key gathers rows of 3 (`rows3`) or
+ * scalars of elem_bytes in {4, 8} by the particle index in the low 32 bits. */
+int oa_region_pairs(const void* pos, int data_dtype, int64_t n, const double* centres,
+                    const float* centres_f, const double* radii, int frame_dtype,
+                    const int32_t* cell_start, const int32_t* cell_regions,
+                    const double* grid_lo, const double* grid_inv_cell,
+                    const int32_t* grid_dim, const double* box, int periodic,
+                    uint64_t* keys, int64_t capacity, uint64_t* counter, void* stream);
+int oa_gather_by_key(const void* src, int elem_bytes, int rows3, const uint64_t* keys,
+                     int64_t n, void* out, void* stream);
+
+/* Incremental collation (postprocessing.py:121-141: the reference re-runs
+ * np.unique over a halo's WHOLE event history at every snapshot).  The collated
+ * state is a table (pool, ID, count) ascending in (pool, ID); a snapshot's new
+ * events, sorted and run-length encoded the same way, are merged into it:
+ *   oa_merge_find : lb[k] = lower bound of new key k in the table; an equal key
+ *                   adds new_cnt[k] to tab_cnt[lb[k]] (miss[k] = 0), else miss[k] = 1;
+ *   oa_merge_place: with miss_sel = ascending positions of the misses, writes the
+ *                   merged table of n_tab + n_miss rows. */
+int oa_merge_find(const int64_t* tab_seg, const int64_t* tab_ids, int64_t* tab_cnt,
+                  int64_t n_tab, const int64_t* new_seg, const int64_t* new_ids,
+                  const int64_t* new_cnt, int64_t n_new, int64_t* lb, uint16_t* miss,
+                  void* stream);
+int oa_merge_place(const int64_t* tab_seg, const int64_t* tab_ids, const int64_t* tab_cnt,
+                   int64_t n_tab, const int64_t* new_seg, const int64_t* new_ids,
+                   const int64_t* new_cnt, const int64_t* lb, const int64_t* miss_sel,
+                   int64_t n_miss, int64_t* out_seg, int64_t* out_ids, int64_t* out_cnt,
+                   void* stream);
 /* seg_out[i] = table[segment of i] (segment index itself if table is NULL). */
 int oa_expand_segments(const int64_t* seg_off, int n_seg, const int32_t* table,
                        int64_t n, int32_t* seg_out, void* stream);

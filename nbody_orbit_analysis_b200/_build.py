@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liborbit_b200.so')
 SOURCES = ['oa_api.cu', 'oa_track.cu', 'oa_select.cu', 'oa_bulk.cu',
            'oa_sort.cu', 'oa_synth.cu', 'oa_segment.cu', 'oa_join.cu',
-           'oa_pjoin.cu', 'oa_pj2.cu']
+           'oa_pjoin.cu', 'oa_pj2.cu', 'oa_regions.cu']
 HEADERS = [os.path.join(CSRC, 'oa_common.cuh'),
            os.path.join(CSRC, 'oa_pjoin_core.cuh'),
            os.path.join(os.path.dirname(HERE), 'include', 'orbit_b200.h')]

@@ -29,6 +29,16 @@ extern "C" int oa_device_info(int* sm_count, int* cc_major, int* cc_minor,
     return OA_OK;
 }
 
+// plain asynchronous copy on an explicit stream (host code: a small device->host
+// or host->device copy without switching the framework's current stream)
+extern "C" int oa_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return OA_OK;
+    OA_REQUIRE(dst && src, "oa_copy_async: NULL pointer");
+    OA_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault,
+                                  static_cast<cudaStream_t>(stream)));
+    return OA_OK;
+}
+
 extern "C" size_t oa_track_args_size(void) { return sizeof(oa_track_args); }
 extern "C" size_t oa_synth_params_size(void) { return sizeof(oa_synth_params); }
 

@@ -299,3 +299,96 @@ extern "C" int oa_expand_segments(const int64_t* seg_off, int n_seg, const int32
     OA_LAUNCH_CHECK();
     return OA_OK;
 }
+
+// ---- incremental collation (postprocessing.py:121-141) --------------------------------------
+// The collated state of all snapshots so far is a table of (pool, ID, count),
+// ascending in (pool, ID) -- per pool exactly np.unique(..., return_counts=True)
+// of that pool's event IDs.  A new snapshot's events, sorted and run-length
+// encoded the same way, are MERGED into it instead of re-sorting the whole
+// history: (1) every new key finds its lower bound in the table; an equal key
+// adds its count, the others are "misses"; (2) the table and the misses are
+// written to the merged table: a table row moves up by the number of misses in
+// front of it, miss m lands at lower_bound + m.
+namespace {
+__device__ __forceinline__ bool key_less(int64_t sa, int64_t ia, int64_t sb, int64_t ib) {
+    return sa < sb || (sa == sb && ia < ib);
+}
+
+__global__ void merge_find_kernel(const int64_t* __restrict__ t_seg,
+                                  const int64_t* __restrict__ t_ids, int64_t* t_cnt, int64_t n_tab,
+                                  const int64_t* __restrict__ n_seg, const int64_t* __restrict__ n_ids,
+                                  const int64_t* __restrict__ n_cnt, int64_t n_new,
+                                  int64_t* __restrict__ lb, uint16_t* __restrict__ miss) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_new) return;
+    const int64_t s = n_seg[k], id = n_ids[k];
+    int64_t lo = 0, hi = n_tab;                      // first row with key >= (s, id)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (key_less(t_seg[mid], t_ids[mid], s, id)) lo = mid + 1; else hi = mid;
+    }
+    lb[k] = lo;
+    const bool hit = lo < n_tab && t_seg[lo] == s && t_ids[lo] == id;
+    miss[k] = hit ? 0 : 1;
+    if (hit) t_cnt[lo] += n_cnt[k];                  // new keys are unique: no conflict
+}
+
+__global__ void merge_place_kernel(const int64_t* __restrict__ t_seg,
+                                   const int64_t* __restrict__ t_ids,
+                                   const int64_t* __restrict__ t_cnt, int64_t n_tab,
+                                   const int64_t* __restrict__ n_seg, const int64_t* __restrict__ n_ids,
+                                   const int64_t* __restrict__ n_cnt,
+                                   const int64_t* __restrict__ lb, const int64_t* __restrict__ msel,
+                                   int64_t n_miss, int64_t* __restrict__ o_seg,
+                                   int64_t* __restrict__ o_ids, int64_t* __restrict__ o_cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tab) {
+        int64_t lo = 0, hi = n_miss;                 // misses with lower bound <= i
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (lb[msel[mid]] <= i) lo = mid + 1; else hi = mid;
+        }
+        o_seg[i + lo] = t_seg[i];
+        o_ids[i + lo] = t_ids[i];
+        o_cnt[i + lo] = t_cnt[i];
+    } else if (i < n_tab + n_miss) {
+        const int64_t m = i - n_tab, k = msel[m], at = lb[k] + m;
+        o_seg[at] = n_seg[k];
+        o_ids[at] = n_ids[k];
+        o_cnt[at] = n_cnt[k];
+    }
+}
+}  // namespace
+
+extern "C" int oa_merge_find(const int64_t* tab_seg, const int64_t* tab_ids, int64_t* tab_cnt,
+                             int64_t n_tab, const int64_t* new_seg, const int64_t* new_ids,
+                             const int64_t* new_cnt, int64_t n_new, int64_t* lb, uint16_t* miss,
+                             void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_new <= 0) return OA_OK;
+    OA_REQUIRE(n_tab >= 0 && new_seg && new_ids && new_cnt && lb && miss &&
+               (n_tab == 0 || (tab_seg && tab_ids && tab_cnt)), "oa_merge_find: bad arguments");
+    merge_find_kernel<<<blocks_for(n_new, 256), 256, 0, st>>>(tab_seg, tab_ids, tab_cnt, n_tab,
+                                                              new_seg, new_ids, new_cnt, n_new, lb,
+                                                              miss);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
+extern "C" int oa_merge_place(const int64_t* tab_seg, const int64_t* tab_ids,
+                              const int64_t* tab_cnt, int64_t n_tab, const int64_t* new_seg,
+                              const int64_t* new_ids, const int64_t* new_cnt, const int64_t* lb,
+                              const int64_t* miss_sel, int64_t n_miss, int64_t* out_seg,
+                              int64_t* out_ids, int64_t* out_cnt, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_tab + n_miss <= 0) return OA_OK;
+    OA_REQUIRE(n_tab >= 0 && n_miss >= 0 && out_seg && out_ids && out_cnt &&
+               (n_tab == 0 || (tab_seg && tab_ids && tab_cnt)) &&
+               (n_miss == 0 || (new_seg && new_ids && new_cnt && lb && miss_sel)),
+               "oa_merge_place: bad arguments");
+    merge_place_kernel<<<blocks_for(n_tab + n_miss, 256), 256, 0, st>>>(
+        tab_seg, tab_ids, tab_cnt, n_tab, new_seg, new_ids, new_cnt, lb, miss_sel, n_miss, out_seg,
+        out_ids, out_cnt);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}

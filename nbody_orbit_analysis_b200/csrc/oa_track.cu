@@ -261,6 +261,7 @@ struct ChunkMeta {
 // ---- derived launch constants (host -> kernel) ----------------------------------------------
 struct TrackConst {
     const int2* chunk_regions;    // (n_chunks,) first / last region of every chunk
+    unsigned int* ticket;         // TICKETS counters, 32 words apart
     const uint32_t* cnt_prev;     // bucket fill counters of the previous table
     const uint32_t* slot_prev;    // its slot buckets
     uint32_t* cnt_cur;
@@ -314,10 +315,20 @@ __device__ __noinline__ void insert_slow(uint32_t* __restrict__ cnt,
     }
 }
 
+// Chunks beyond a warp's static first rounds are handed out by ticket.  One
+// counter would serialise in L2 (~2 ns per same-address atomic: 0.4 M tickets per
+// launch doubled the kernel time); TICKETS counters on separate 128-byte lines,
+// counter c serving the chunks == c (mod TICKETS), are each hit 64 times less.
+constexpr int TICKETS = 64;
+
 // first / last region of every chunk (one thread per chunk)
 __global__ void track_chunks_kernel(const int64_t* __restrict__ off, int n_regions,
                                     int64_t n, int n_chunks, int2* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // chunk tickets of the tracking kernel: TICKETS counters, one per 128-byte line
+    if (t < TICKETS * 16) out[n_chunks + t] = make_int2(0, 0);
+    if (t == 0 && n_chunks < TICKETS * 16)
+        for (int q = n_chunks; q < TICKETS * 16; ++q) out[n_chunks + q] = make_int2(0, 0);
     if (t >= n_chunks) return;
     const int64_t first = (int64_t)t * CHUNK;
     const int64_t last = min(first + (int64_t)CHUNK, n) - 1;
@@ -637,15 +648,33 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
         }                                                                                  \
     } while (0)
 
+    // Chunk schedule.  The first D + 2 chunks of a warp are static (chunk c ->
+    // warp c mod stride: the whole GPU sweeps the snapshot as one compact front);
+    // every later chunk is taken by TICKET, so that a warp on an SM it shares with
+    // another kernel (the NCCL channels of the multi-GPU exchange) simply takes
+    // fewer chunks instead of holding the whole launch back.  Position p of the
+    // warp's sequence lives in wq[p & 7]; lane 0 requests the ticket of position
+    // p + D + 3 during iteration p and stores it one iteration later (the atomic's
+    // round trip never stalls the warp).
+    __shared__ int wq_all[TRACK_WARPS * 8];
+    int* const wq = wq_all + warp * 8;
+    if (lane < D + 2) wq[lane] = first + lane * stride;
+    __syncwarp();
+    const unsigned int static_chunks = (unsigned int)(D + 2) * (unsigned int)stride;
+    unsigned int t_pend = 0;
+    int my_c = first % TICKETS;               // this warp's ticket counter
+    bool drained = false;                     // every counter is past the last chunk
+    if (lane == 0) t_pend = atomicAdd(k.ticket + 32 * my_c, 1u);
+
     // ---- prologue: D chunks in flight, table traffic of the first one issued ------
     if (lane == 0) {
         for (int s = 0; s < D; ++s) {
-            const int ch = first + s * stride;
+            const int ch = wq[s];
             if (ch < k.n_chunks) issue(ch, s, __ldg(k.chunk_regions + ch));
         }
     }
     int2 jr_next = make_int2(0, 0);           // regions of the chunk D steps ahead
-    if (first + D * stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + first + D * stride);
+    if (wq[D] < k.n_chunks) jr_next = __ldg(k.chunk_regions + wq[D]);
 
     int s = 0;
     uint32_t phase = 0;
@@ -653,7 +682,9 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
     int64_t id = 0;
     if (first < k.n_chunks) OA_HASH_CHUNK(first, wsm, &full[0], 0u, H, id);
 
-    for (int ch = first; ch < k.n_chunks; ch += stride) {
+    for (int p = 0;; ++p) {
+        const int ch = wq[p & 7];
+        if (ch >= k.n_chunks) break;
         unsigned char* st = wsm + s * L::BYTES;
         const int sn = (s + 1 == D) ? 0 : s + 1;
         const uint32_t phase_n = (s + 1 == D) ? (phase ^ 1u) : phase;
@@ -664,8 +695,9 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
         //      flight during everything below ---------------------------------------
         Probe Hn = empty_probe();
         int64_t id_n = 0;
-        if (ch + stride < k.n_chunks)
-            OA_HASH_CHUNK(ch + stride, wsm + sn * L::BYTES, &full[sn], phase_n, Hn, id_n);
+        const int ch_n = wq[(p + 1) & 7];
+        if (ch_n < k.n_chunks)
+            OA_HASH_CHUNK(ch_n, wsm + sn * L::BYTES, &full[sn], phase_n, Hn, id_n);
 
         // ---- stage B: candidate of THIS chunk (its bucket arrived an iteration ago)
         uint32_t cand = 0xFFFFFFFFu, fill = 0;
@@ -697,10 +729,30 @@ oa_track_kernel(const __grid_constant__ oa_track_args a, const __grid_constant__
         }
         // the slot has been consumed: refill it with the chunk D steps ahead
         __syncwarp();
-        const int ahead = ch + D * stride;
+        const int ahead = wq[(p + D) & 7];
         if (ahead < k.n_chunks) {
             if (lane == 0) issue(ahead, s, jr_next);
-            if (ahead + stride < k.n_chunks) jr_next = __ldg(k.chunk_regions + ahead + stride);
+            const int ahead2 = wq[(p + D + 1) & 7];
+            if (ahead2 < k.n_chunks) jr_next = __ldg(k.chunk_regions + ahead2);
+        }
+        // the ticket requested an iteration ago is position p + D + 2; request the next
+        if (lane == 0) {
+            int chunk = k.n_chunks;
+            if (!drained) {
+                unsigned int t = t_pend;
+                for (int tries = 0;; ++tries) {
+                    const unsigned long long c =
+                        (unsigned long long)static_chunks + (unsigned long long)t * TICKETS + my_c;
+                    if (c < (unsigned long long)k.n_chunks) { chunk = (int)c; break; }
+                    // this counter is exhausted (the tail of the launch): take
+                    // chunks of the next one
+                    if (tries == TICKETS) { drained = true; break; }
+                    my_c = (my_c + 1 == TICKETS) ? 0 : my_c + 1;
+                    t = atomicAdd(k.ticket + 32 * my_c, 1u);
+                }
+            }
+            wq[(p + D + 2) & 7] = chunk;
+            if (!drained) t_pend = atomicAdd(k.ticket + 32 * my_c, 1u);
         }
 
         // ---- stage D ------------------------------------------------------------------
@@ -731,10 +783,12 @@ int launch_track_impl(const oa_track_args& a, cudaStream_t st) {
 
     TrackConst k;
     k.n_chunks = (int)((a.n_cur + CHUNK - 1) / CHUNK);
-    OA_REQUIRE(a.workspace && a.workspace_bytes >= sizeof(int2) * (size_t)k.n_chunks,
+    OA_REQUIRE(a.workspace &&
+                   a.workspace_bytes >= sizeof(int2) * ((size_t)k.n_chunks + 1 + TICKETS * 16),
                "oa_track_fused: workspace too small (need oa_track_workspace_bytes)");
     int2* chunks = static_cast<int2*>(a.workspace);
     k.chunk_regions = chunks;
+    k.ticket = reinterpret_cast<unsigned int*>(chunks + k.n_chunks);
     k.cnt_prev = a.tab_prev;
     k.slot_prev = a.tab_prev ? a.tab_prev + table_count_words(a.tab_prev_buckets) : nullptr;
     k.cnt_cur = a.tab_cur;
@@ -797,7 +851,7 @@ extern "C" int oa_index_bits(int64_t max_block_len) {
 }
 
 extern "C" size_t oa_track_workspace_bytes(int64_t n_cur) {
-    return sizeof(int2) * (size_t)((n_cur + CHUNK - 1) / CHUNK + 1);
+    return sizeof(int2) * (size_t)((n_cur + CHUNK - 1) / CHUNK + 1 + TICKETS * 16);
 }
 
 // Only the fill counters are cleared; slot buckets are validated by the counters

@@ -4,11 +4,13 @@ Same class, methods, arguments, ``ValueError``s and collated-file layout as the
 reference ``postprocessing.py:8-240``.  File reading/writing stays on the host
 (``storage.py``); the reductions move to the GPU:
 
-* ``collate_apsides``: the event IDs that pass ``angles > angle_cut`` are kept
-  in one device pool tagged with their halo; per snapshot the pool is sorted by
-  (halo, ID) with two radix sorts and run-length encoded -- that is the
-  reference's per-halo ``np.unique(..., return_counts=True)`` over the whole
-  history (``:133-141``) in one pass for all halos;
+* ``collate_apsides``: the collated state -- per halo the unique event IDs that
+  passed ``angles > angle_cut`` so far and their counts, i.e. the reference's
+  ``np.unique(..., return_counts=True)`` over a halo's whole history
+  (``:133-141``) -- is ONE device table ascending in (halo, ID).  Per snapshot
+  only the new events are sorted (two radix sorts) and run-length encoded, then
+  merged into the table (``oa_merge_find`` / ``oa_merge_place``): the history is
+  never re-sorted, O(E_total) instead of the reference's O(n_snap x E_total);
 * ``save_final_apsis_counts``: the per-halo ``myin1d`` look-ups (``:222-232``)
   become one segmented binary-search join.
 
@@ -74,7 +76,9 @@ class Apsides:
         ctx = DeviceContext(self._device)
         st = ctx.stream()
         n_pool = len(halo_ids)
-        pool_ids = pool_seg = None          # device int64: ID, pool index
+        # collated state: (pool index, ID, count) device int64 arrays, ascending
+        # in (pool, ID); a snapshot's events are MERGED into it (section f-3)
+        table_state = None
         idtype = None
 
         for s in self.snapshot_numbers[:last + 1]:
@@ -122,40 +126,26 @@ class Apsides:
                                          n_sel)[:n_sel]
                 keep = new_seg < n_pool           # halos that are collated
                 new_ids, new_seg = new_ids[keep], new_seg[keep]
-                pool_ids = new_ids if pool_ids is None else \
-                    torch.cat((pool_ids, new_ids))
-                pool_seg = new_seg if pool_seg is None else \
-                    torch.cat((pool_seg, new_seg))
+                n_new = int(new_ids.numel())
+                if n_new:
+                    table_state = self._merge_new(
+                        ctx, table_state, new_ids, new_seg, n_new, n_pool)
             ctx.launches += 2
 
             # ---- unique IDs + counts of every pool ------------------------------
-            P = 0 if pool_ids is None else int(pool_ids.numel())
-            if P:
-                _, order, _ = ctx.argsort_values(pool_ids, P)
-                seg_sorted = ctx.gather_i64(pool_seg, order, P)
-                seg_sorted, order = ctx.sort_pairs(
-                    seg_sorted, order, P, max(n_pool - 1, 1).bit_length())
-                ids_sorted = ctx.gather_i64(pool_ids, order, P)
-                head = ctx.empty(P + 8, torch.int16)
-                check(lib.oa_run_heads(ptr(seg_sorted), ptr(ids_sorted), P,
-                                       ptr(head), st))
-                starts, n_runs = ctx.select(head, P, _lib.OA_SEL_EQ, 1)
-                counts = ctx.empty(n_runs, torch.int64)
-                check(lib.oa_run_lengths(ptr(starts), n_runs, P, ptr(counts),
-                                         st))
-                u_ids = ctx.gather_i64(ids_sorted, starts, n_runs)
-                u_seg = ctx.gather_i64(seg_sorted, starts, n_runs)
+            if table_state is not None:
+                t_seg, t_ids, t_cnt = table_state
+                n_runs = int(t_ids.numel())
                 # number of unique IDs in the pools before pool h
                 d_keys = ctx.upload(np.arange(n_pool + 1, dtype=np.int64))
                 d_poff = ctx.empty(n_pool + 1, torch.int64)
-                check(lib.oa_segment_offsets(ptr(u_seg), n_runs, None,
+                check(lib.oa_segment_offsets(ptr(t_seg), n_runs, None,
                                              ptr(d_keys), n_pool + 1,
                                              ptr(d_poff), st))
-                ctx.launches += 3
+                ctx.launches += 1
                 pool_off = d_poff[:n_pool + 1].cpu().numpy()
-                particle_ids = u_ids[:n_runs].cpu().numpy().astype(
-                    idtype, copy=False)
-                particle_counts = counts[:n_runs].cpu().numpy()
+                particle_ids = t_ids.cpu().numpy().astype(idtype, copy=False)
+                particle_counts = t_cnt.cpu().numpy()
             else:
                 pool_off = np.zeros(n_pool + 1, dtype=np.int64)
                 particle_ids = np.zeros(0, dtype=idtype)
@@ -185,6 +175,53 @@ class Apsides:
             self.save_final_apsis_counts(savefile, verbose=verbose)
         if verbose:
             print('Collated apsides in {} s\n'.format(time.time() - t_start))
+
+    # ------------------------------------------------------------------------
+    @staticmethod
+    def _merge_new(ctx, table, new_ids, new_seg, n_new, n_pool):
+        """Merge one snapshot's cut-passing events ``(new_seg, new_ids)`` into
+        the collated table: the reference's per-halo ``np.unique(...,
+        return_counts=True)`` over the whole history (``postprocessing.py:
+        133-141``) without touching the history -- only the new events are
+        sorted, the table is merged (``oa_merge_find`` / ``oa_merge_place``)."""
+        st = ctx.stream()
+        # (pool, ID)-sorted new events, run-length encoded
+        _, order, _ = ctx.argsort_values(new_ids, n_new)
+        seg_sorted = ctx.gather_i64(new_seg, order, n_new)
+        seg_sorted, order = ctx.sort_pairs(
+            seg_sorted, order, n_new, max(n_pool - 1, 1).bit_length())
+        ids_sorted = ctx.gather_i64(new_ids, order, n_new)
+        head = ctx.empty(n_new + 8, torch.int16)
+        check(lib.oa_run_heads(ptr(seg_sorted), ptr(ids_sorted), n_new,
+                               ptr(head), st))
+        starts, n_runs = ctx.select(head, n_new, _lib.OA_SEL_EQ, 1)
+        counts = ctx.empty(n_runs, torch.int64)
+        check(lib.oa_run_lengths(ptr(starts), n_runs, n_new, ptr(counts), st))
+        u_ids = ctx.gather_i64(ids_sorted, starts, n_runs)[:n_runs]
+        u_seg = ctx.gather_i64(seg_sorted, starts, n_runs)[:n_runs]
+        counts = counts[:n_runs]
+        ctx.launches += 2
+        if table is None:
+            return u_seg, u_ids, counts
+        t_seg, t_ids, t_cnt = table
+        n_tab = int(t_ids.numel())
+        lb = ctx.empty(n_runs, torch.int64)
+        miss = ctx.empty(n_runs + 8, torch.int16)
+        check(lib.oa_merge_find(ptr(t_seg), ptr(t_ids), ptr(t_cnt), n_tab,
+                                ptr(u_seg), ptr(u_ids), ptr(counts), n_runs,
+                                ptr(lb), ptr(miss), st))
+        msel, n_miss = ctx.select(miss, n_runs, _lib.OA_SEL_EQ, 1)
+        ctx.launches += 1
+        if n_miss == 0:
+            return table
+        out = [ctx.empty(n_tab + n_miss, torch.int64)[:n_tab + n_miss]
+               for _ in range(3)]
+        check(lib.oa_merge_place(ptr(t_seg), ptr(t_ids), ptr(t_cnt), n_tab,
+                                 ptr(u_seg), ptr(u_ids), ptr(counts), ptr(lb),
+                                 ptr(msel), n_miss, ptr(out[0]), ptr(out[1]),
+                                 ptr(out[2]), st))
+        ctx.launches += 1
+        return tuple(out)
 
     # ------------------------------------------------------------------------
     def save_final_apsis_counts(self, collated_file, snapshot_numbers=None,

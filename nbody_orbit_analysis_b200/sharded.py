@@ -647,10 +647,12 @@ class Comm:
     def finish_batch(self, b):
         """Global results of the snapshots of a launched batch, in order: like
         ``finish_merge(to_host='slice')`` per snapshot (``host_slice`` is this
-        rank's part of that snapshot's list, possibly empty)."""
+        rank's part of that snapshot's list, possibly empty; wait for
+        ``host_ready`` before reading ``apsis_ids`` / ``apsis_angles`` -- they
+        stay valid until HOST_RING further batches have been finished)."""
         big = self.finish_merge(b.h)
-        if big.host_ready is not None:
-            big.host_ready.synchronize()
+        # (the copy of the batch's lists to the host is in flight: the results
+        # carry its event, nothing waits here)
         lo, hi = big.host_slice
         off = big.apsis_offsets
         out = []
@@ -663,7 +665,7 @@ class Comm:
             res.d_ids, res.d_ang = big.d_ids[a - lo:z - lo], big.d_ang[a - lo:z - lo]
             res.apsis_ids = big.apsis_ids[a - lo:z - lo]
             res.apsis_angles = big.apsis_angles[a - lo:z - lo]
-            res.host_ready = None
+            res.host_ready = big.host_ready
             out.append(res)
         if b in self._launched:
             self._launched.remove(b)

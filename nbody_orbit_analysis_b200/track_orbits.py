@@ -60,7 +60,12 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
         ``Omega_m``, ``Omega_L``, optional ``Omega_k``
     savefile : str -- HDF5 result file (layout of ``track_orbits.py:366-397``)
     mode : 'pericentric' | 'apocentric'
-    checkpoint, resume : as in the reference (``:93-101, 229-232, 390-394``)
+    checkpoint, resume : as in the reference (``:93-101, 229-232, 390-394``).
+        Extension: ``checkpoint='state'`` also saves the carried device state
+        (records + ID table) next to the reference's
+        ``angles`` dataset; ``resume=True`` then continues at the snapshot AFTER
+        the last saved one without reloading it (with a plain checkpoint the
+        last saved snapshot is re-processed, like in the reference)
     npool : ignored
     device : optional torch device (extension; default current CUDA device)
     comm : extension.  None (default): shard over the ranks of an initialised
@@ -87,12 +92,16 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
     snapshot_numbers = snapshot_numbers[order]
     main_branches = main_branches[order]
 
+    restored = None
     if resume:
         if verbose:
             print('Resuming from file...\n')
         with storage.File(savefile, 'r') as hf:
             last = int(list(hf.keys())[-1].split('_')[1])
         first = int(np.flatnonzero(snapshot_numbers == last)[0])
+        restored = _read_state(savefile + '.checkpoint', last)
+        if restored is not None:
+            first += 1                # the carried state of `last` is restored
         snapshot_numbers = snapshot_numbers[first:]
         main_branches = main_branches[first:]
 
@@ -108,7 +117,13 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
     tag = mode[:-3] + 'er'
     istart, started, initialised = 0, False, bool(resume)
     prev_halo_exists = None
-    last_snap = snapshot_numbers[-1]
+    last_snap = snapshot_numbers[-1] if len(snapshot_numbers) else None
+    if restored is not None:
+        if sharded_run:
+            raise ValueError("device-state checkpoints are single-GPU")
+        tracker.load_state(restored)
+        prev_halo_exists = np.asarray(restored['halo_exists'])
+        istart, started = -1, True
 
     def write(e, res):
         """Result group of one snapshot (``track_orbits.py:366-397``)."""
@@ -120,6 +135,11 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
         if checkpoint:
             with storage.File(ckpt_name, 'w') as hf:
                 hf.create_dataset('angles', data=e.angles)
+                if e.state is not None:
+                    g = hf.create_group('b200_state')
+                    g.attrs['snapshot'] = int(e.snap_no)
+                    for k, v in e.state.items():
+                        g.create_dataset(k, data=v)
         if not writer:
             return
         t0 = time.time()
@@ -231,6 +251,7 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
         if resume and i <= istart:
             with storage.File(ckpt_name, 'r') as hf:
                 tracker.load_angles(hf['angles'][:])
+        e.state = tracker.save_state() if checkpoint == 'state' else None
         pending.append(e)
         # results of the PREVIOUS snapshot: collected and written while this one
         # is on the GPU
@@ -247,6 +268,21 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
     if verbose:
         print('Finished {} detection for all snapshots in {} s\n'.format(
             tag, time.time() - t_start))
+
+
+def _read_state(path, snapshot):
+    """The device state saved by ``checkpoint='state'`` for ``snapshot``, or
+    None (plain checkpoint, other snapshot, no file)."""
+    import os
+    if not os.path.exists(path):
+        return None
+    with storage.File(path, 'r') as hf:
+        if 'b200_state' not in list(hf.keys()):
+            return None
+        g = hf['b200_state']
+        if int(g.attrs['snapshot']) != int(snapshot):
+            return None
+        return {k: g[k][:] for k in g.keys()}
 
 
 class _Entry:

@@ -120,6 +120,8 @@ class OrbitTracker:
         self.events_on_device = False
         self.wait_before_submit = None   # event the next submit must wait for
         self.sm_reserve = 0        # SMs the fused kernel leaves to other streams
+        self._cur_main = None
+        self._copy_st = C.c_void_p(self.copy_stream.cuda_stream)
 
     # -- buffers -------------------------------------------------------------
     RING = 3      # generations / in-flight steps a buffer name cycles through
@@ -156,7 +158,10 @@ class OrbitTracker:
         return raw[:int(n) * item].view(dtype)
 
     def _main(self):
-        return torch.cuda.current_stream(self.device)
+        # (inside submit_device the current stream is looked up once: the
+        # torch.cuda.current_stream call costs ~10 us, a submit used it 8 times)
+        cur = self._cur_main
+        return cur if cur is not None else torch.cuda.current_stream(self.device)
 
     def _stream(self):
         return C.c_void_p(self._main().cuda_stream)
@@ -221,8 +226,10 @@ class OrbitTracker:
         else:
             h = self._hbuf(name, n, t.dtype, step, reserve)
         if n:
-            with torch.cuda.stream(self.copy_stream):
-                h.copy_(t[:n], non_blocking=True)
+            # (cudaMemcpyAsync on the copy stream through the C ABI: no stream
+            # switch of the host framework per copy)
+            check(lib.oa_copy_async(h.data_ptr(), t.data_ptr(),
+                                    n * _ITEMSIZE[t.dtype], self._copy_st))
         return h
 
     def to_host(self, *tensors, stream=None):
@@ -312,6 +319,19 @@ class OrbitTracker:
         """Same as ``submit`` with the particle arrays already in HBM
         (``dev`` = dict of flat torch tensors ``pos``, ``vel``, ``ids``,
         optional ``mass``)."""
+        self._cur_main = torch.cuda.current_stream(self.device)
+        try:
+            return self._submit_device(
+                dev, n, data_dtype, ids_dtype, offsets, halo_exists,
+                region_positions, region_bulk_vels, H, box_size, redshift,
+                mass_dtype, want_angles, diagnostics, gpos)
+        finally:
+            self._cur_main = None
+
+    def _submit_device(self, dev, n, data_dtype, ids_dtype, offsets,
+                       halo_exists, region_positions, region_bulk_vels, H,
+                       box_size, redshift, mass_dtype, want_angles, diagnostics,
+                       gpos):
         st = self._stream()
         if self.wait_before_submit is not None:
             # e.g. the multi-GPU exchange still reading the ring's event buffers
@@ -787,6 +807,72 @@ class OrbitTracker:
         if release:
             p.keep = None
         return res
+
+    # -- checkpoint of the carried device state ----------------
+    def save_state(self):
+        """The carried state of the last submitted snapshot as host arrays:
+        everything ``track(j)`` needs from the previous snapshot (reference
+        ``track_orbits.py:234-240``: ids, unit vectors, radial velocities, angle
+        accumulators) in this library's record layout, plus the ID table.  A run
+        restored with ``load_state`` continues at the NEXT snapshot without
+        reloading this one (the reference re-processes the last saved snapshot
+        and restores only the angles, ``:93-101, 229-232``).  Synchronous."""
+        gen = self.prev
+        if gen is None:
+            raise _lib.OrbitB200Error("no snapshot has been processed yet")
+        if gen.pjoin:
+            raise _lib.OrbitB200Error(
+                "device-state checkpoints need impl='hash'")
+        torch.cuda.current_stream(self.device).synchronize()
+        meta = np.array([gen.n, gen.index_bits, gen.n_buckets,
+                         int(gen.frame_f64), len(gen.halo_exists)],
+                        dtype=np.int64)
+        state = {'meta': meta, 'rec': gen.rec.cpu().numpy(),
+                 'tab': gen.tab.cpu().numpy(),
+                 'offsets': np.asarray(gen.offsets, dtype=np.int64),
+                 'halo_exists': np.asarray(gen.halo_exists, dtype=np.int64),
+                 'buckets': np.asarray(gen.buckets, dtype=np.int64),
+                 'ids_dtype': np.frombuffer(
+                     gen.ids_dtype.str.encode().ljust(8), dtype=np.uint8).copy()}
+        if gen.gpos is not None:
+            state['gpos'] = gen.gpos.cpu().numpy()
+        return state
+
+    def load_state(self, state):
+        """Inverse of ``save_state`` on a fresh tracker."""
+        meta = np.asarray(state['meta'], dtype=np.int64)
+        n, index_bits, n_buckets, frame_f64, n_h = (int(v) for v in meta)
+        slot = (self._step - 1) % self.RING      # the slot of "the previous step"
+        gen = Generation()
+        gen.n, gen.index_bits, gen.n_buckets = n, index_bits, n_buckets
+        gen.frame_f64 = bool(frame_f64)
+        gen.offsets = np.ascontiguousarray(state['offsets'], dtype=np.int64)
+        gen.halo_exists = np.asarray(state['halo_exists'], dtype=np.int64)
+        gen.halo_ids64 = np.ascontiguousarray(gen.halo_exists, dtype=np.int64)
+        gen.buckets = np.ascontiguousarray(state['buckets'], dtype=np.int64)
+        gen.ids_dtype = np.dtype(bytes(np.asarray(
+            state['ids_dtype'], dtype=np.uint8)).decode().strip())
+        gen.pjoin = gen.pj2 = False
+        gen.ids = None
+        rec = np.ascontiguousarray(state['rec'], dtype=np.uint8)
+        tab = np.ascontiguousarray(state['tab'], dtype=np.int32)
+        if len(rec) != max(n, 1) * lib.oa_record_bytes(int(gen.frame_f64)) or \
+                len(tab) != lib.oa_table_slots(n, n_h) or \
+                len(gen.offsets) != n_h + 1:
+            raise ValueError("device-state checkpoint is inconsistent")
+        gen.rec = self._buf('rec', len(rec), torch.uint8, slot)
+        gen.rec.copy_(torch.from_numpy(rec))
+        gen.tab = self._buf('tab', len(tab), torch.int32, slot)
+        gen.tab.copy_(torch.from_numpy(tab))
+        gen.mark = self._buf('mark', max(n, 1) + 8, torch.int16, slot)
+        check(lib.oa_fill_u16(ptr(gen.mark), max(n, 1) + 8, _lib.OA_NO_EVENT,
+                              self._stream()))
+        gen.gpos = None
+        if 'gpos' in state:
+            gen.gpos = torch.from_numpy(np.ascontiguousarray(
+                state['gpos'], dtype=np.int64)).to(self.device)
+        self.launches += 1
+        self.prev = gen
 
     def load_angles(self, angles):
         """Replace the angle accumulators of the current generation with a

@@ -636,3 +636,33 @@ class Apsides:
                     k = ordered_match(ids_final[flo:fhi], ids[lo:hi])
                     retro[lo:hi] = counts_final[flo:fhi][k]
                 g.create_dataset(tag + '_counts_final', data=retro)
+
+
+# ---------------------------------------------------------------------------
+# region extraction (the example loader, example_script.py:36-67)
+# ---------------------------------------------------------------------------
+def extract_regions(coordinates, region_positions, region_radii, box_size=None):
+    """Particle indices within each region and ``region_offsets``: restates the
+    selection loop of the reference's example loader (``example_script.py:
+    50-58``) with the reference's helpers (``utils.py:13-33``): for every
+    region, ``np.argwhere(vector_norm(recenter_coordinates(coordinates -
+    position, box_size)) < radius).flatten()``.  O(N x n_regions): test sizes
+    only."""
+    region_inds = []
+    for position, radius in zip(np.atleast_2d(region_positions),
+                                np.atleast_1d(region_radii)):
+        d = coordinates - position
+        if box_size is not None:
+            boxsize = box_size
+            if isinstance(boxsize, (float, np.floating, int, np.integer)):
+                boxsize = boxsize * np.ones(3)
+            for dim, bs in enumerate(boxsize):
+                d[np.argwhere((d[:, dim] > bs / 2)), dim] -= bs
+                d[np.argwhere((d[:, dim] < -bs / 2)), dim] += bs
+        r = np.sqrt(np.einsum('...i,...i', d, d))
+        region_inds.append(np.argwhere(r < radius).flatten())
+    region_lens = [len(inds) for inds in region_inds]
+    region_offsets = np.cumsum([0] + region_lens)[:-1]
+    region_inds = np.hstack(region_inds).astype(int) if region_inds else \
+        np.zeros(0, dtype=int)
+    return region_inds, region_offsets

@@ -71,6 +71,10 @@ class FakeLib:
     def __getattr__(self, name):
         return getattr(self._real, name)
 
+    def oa_copy_async(self, dst, src, nbytes, stream):
+        C.memmove(dst, src, int(nbytes))
+        return 0
+
     # ---- no-op kernels of the hash-table branch --------------------------------
     def oa_table_clear(self, *a):
         self.calls.append('oa_table_clear')

@@ -215,6 +215,42 @@ def run_kernels(name, dtype, cdtype, seed):
         os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+def run_regions(name, dtype, cdtype, periodic, seed):
+    """The selection loop of the reference's example loader
+    (``example_script.py:50-58``), executed with the REFERENCE's own
+    ``utils.vector_norm`` / ``utils.recenter_coordinates``."""
+    rng = np.random.default_rng(seed)
+    L = 40.0
+    n, n_h = 6000, 9
+    centres = (rng.uniform(0, L, (n_h, 3))).astype(cdtype)
+    centres[0] = [0.3, 39.8, 20.0]                 # on a box face
+    centres[1] = centres[0] + np.array([1.0, -0.5, 0.7], dtype=cdtype)  # overlap
+    radii = rng.uniform(1.0, 6.0, n_h).astype(cdtype)
+    radii[2] = 0.01                                # an empty region
+    host = rng.integers(0, n_h, n)
+    x = (centres[host].astype(np.float64) +
+         rng.normal(0, 2.5, (n, 3))) % L
+    x[:50] = centres[3].astype(np.float64) + radii[3] * np.array([1.0, 0, 0]) \
+        * (1 + rng.normal(0, 1e-7, (50, 1)))       # on the edge of a region
+    coordinates = x.astype(dtype)
+    box_size = L if periodic else None
+    region_inds = []
+    for position, radius in zip(np.atleast_2d(centres), np.atleast_1d(radii)):
+        d = coordinates - position
+        if periodic:
+            d = ref.utils.recenter_coordinates(d, box_size)
+        r = ref.utils.vector_norm(d)
+        region_inds.append(np.argwhere(r < radius).flatten())
+    region_lens = [len(inds) for inds in region_inds]
+    out = {'/region_offsets': np.cumsum([0] + region_lens)[:-1],
+           '/region_inds': np.hstack(region_inds).astype(int)}
+    inputs = {'in/coordinates': coordinates, 'in/centres': centres,
+              'in/radii': radii, 'in/box_size': np.asarray(L if periodic else -1.0)}
+    path = save_fixture('regions_' + name, dict(kind='regions'), inputs, out)
+    print('%-28s %8.1f KB' % (
+        os.path.basename(path), os.path.getsize(path) / 1024))
+
+
 def _jsonable(d):
     out = {}
     for k, v in d.items():
@@ -226,8 +262,13 @@ def _jsonable(d):
     return out
 
 
-def main():
+def main(only=None):
     f32, f64 = np.float32, np.float64
+    if only == 'regions':
+        run_regions('f32_c64', f32, f64, True, 11)
+        run_regions('f32_c32', f32, f32, True, 12)
+        run_regions('f64_c64_open', f64, f64, False, 13)
+        return
     base = dict(n_particles=1600, n_halos=5, n_snap=7)
     sf, _ = run_track('peri_f32_cat64',
                       dict(base, late_halos=0.6, dtype=f32,
@@ -273,7 +314,11 @@ def main():
     run_kernels('f32_c64', f32, f64, 1)
     run_kernels('f32_c32', f32, f32, 2)
     run_kernels('f64_c64', f64, f64, 3)
+    run_regions('f32_c64', f32, f64, True, 11)
+    run_regions('f32_c32', f32, f32, True, 12)
+    run_regions('f64_c64_open', f64, f64, False, 13)
 
 
 if __name__ == '__main__':
-    main()
+    # python tests/golden/make_golden.py [regions]: everything, or one family
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -357,3 +357,39 @@ def test_id_sharding_emulated_on_one_gpu(world, tmp_path):
             np.concatenate(([0], np.cumsum(sum(c.cpu().numpy() for c in cnts)))),
             exp['apsis_offsets'])
     assert n_events > 0
+
+
+@pytest.mark.parametrize('mode', ['pericentric', 'apocentric'])
+def test_device_state_checkpoint_resume(mode, tmp_path):
+    """``checkpoint='state'`` saves the carried device state
+    (records + ID table) next to the reference's ``angles`` dataset; a resumed
+    run continues at the NEXT snapshot -- its loader is never asked for the
+    snapshots already saved -- and writes the same file as an uninterrupted
+    run.  A plain ``checkpoint=True`` file still resumes the reference way."""
+    _, storage, track_orbits, _, SynthSim, _ = _imports()
+    sim = SynthSim(30000, 6, 7, dtype=np.float32, catalogue_dtype=np.float64,
+                   late_halos=0.3)
+    f_a, f_b = str(tmp_path / 'a.h5'), str(tmp_path / 'b.h5')
+    args = (sim.regions, sim.load_snapshot_data)
+    track_orbits.track_orbits(sim.snapshot_numbers, sim.main_branches, *args,
+                              f_a, mode=mode, verbose=False)
+    k = 4
+    track_orbits.track_orbits(sim.snapshot_numbers[:k], sim.main_branches[:k],
+                              *args, f_b, mode=mode, checkpoint='state',
+                              verbose=False)
+    ck = storage.tree(f_b + '.checkpoint')
+    assert '/angles' in ck and '/b200_state/rec' in ck
+    asked = []
+
+    def loader(sn, pos, rad):
+        asked.append(int(sn))
+        return sim.load_snapshot_data(sn, pos, rad)
+    track_orbits.track_orbits(sim.snapshot_numbers, sim.main_branches,
+                              sim.regions, loader, f_b, mode=mode,
+                              checkpoint='state', resume=True, verbose=False)
+    assert asked == [int(s) for s in sim.snapshot_numbers[k:]]
+    got, exp = storage.tree(f_b), storage.tree(f_a)
+    assert set(got) == set(exp)
+    for key in exp:
+        assert np.array_equal(np.asarray(got[key]), np.asarray(exp[key]),
+                              equal_nan=np.asarray(exp[key]).dtype.kind == 'f'), key

@@ -146,3 +146,47 @@ def test_hubble_parameter():
     assert oracle.hubble_parameter(0.0, 70.0, 0.3, 0.7) == 70.0
     h = oracle.hubble_parameter(1.0, 70.0, 0.3, 0.7, 0.0)
     assert h == 70.0 * np.sqrt(0.3 * 8 + 0.7)
+
+
+@pytest.mark.parametrize('name', list_fixtures('regions_'))
+def test_region_extraction_matches_reference(name):
+    """oracle.extract_regions against the selection loop of the reference's
+    example loader run with the reference's own utils (make_golden.py
+    run_regions; example_script.py:50-58)."""
+    fx = load_fixture(name)
+    box = float(fx['in/box_size'])
+    inds, offs = oracle.extract_regions(
+        fx['in/coordinates'], fx['in/centres'], fx['in/radii'],
+        box if box > 0 else None)
+    assert len(fx['out/region_inds']) > 100
+    assert_same_array('region_inds', inds, fx['out/region_inds'])
+    assert_same_array('region_offsets', offs, fx['out/region_offsets'])
+
+
+@pytest.mark.parametrize('name', list_fixtures('regions_'))
+def test_region_cell_lists_cover_every_member(name):
+    """Host side of the GPU region extraction: every (particle, region) pair of
+    the reference selection has the region in the list of the particle's cell
+    (several grid resolutions, periodic wrap included)."""
+    from nbody_orbit_analysis_b200 import regions
+    fx = load_fixture(name)
+    box = float(fx['in/box_size'])
+    periodic = box > 0
+    x = fx['in/coordinates'].astype(np.float64)
+    c64 = fx['in/centres'].astype(np.float64)
+    r64 = fx['in/radii'].astype(np.float64)
+    inds = fx['out/region_inds']
+    offs = np.append(fx['out/region_offsets'], len(inds))
+    reg = np.repeat(np.arange(len(r64)), np.diff(offs))
+    for cells in (None, 1, 7, 64):
+        lo, inv, dim = regions._grid(c64, r64, np.full(3, box) if periodic else None,
+                                     cells)
+        start, lists = regions._cell_lists(c64, r64, lo, inv, dim, periodic)
+        k = np.floor((x[inds] - lo) * inv).astype(np.int64)
+        if periodic:
+            k %= dim
+        else:
+            assert (k >= 0).all() and (k < dim).all()
+        cell = (k[:, 2] * dim[1] + k[:, 1]) * dim[0] + k[:, 0]
+        for i in range(0, len(inds), 7):
+            assert reg[i] in lists[start[cell[i]]:start[cell[i] + 1]]
