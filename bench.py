@@ -48,6 +48,10 @@ def parse():
                     help='snapshots submitted ahead of the one being collected')
     ap.add_argument('--profile', action='store_true',
                     help='cProfile of the timed host loop (to stderr)')
+    ap.add_argument('--config', type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help='index into BASELINE.json configs (1 = the headline, '
+                         'default; 2 = its 100k-halo shape per GPU; 0, 3, 4: '
+                         'tools/bench_configs.py)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-particles', type=int, default=400000,
@@ -456,6 +460,11 @@ def run_b200(args):
         returns (local result, finished global result or None)."""
         res = timed('collect', trk.collect, pending)
         done = []
+        if comm is not None and os.environ.get('OA_BENCH_NO_EXCHANGE') == '1':
+            # diagnostic: tracking only, no event exchange (local event counts)
+            if res.apsis_offsets is not None:
+                done.append(res)
+            return res, done
         if comm is not None and res.apsis_offsets is not None:
             if comm.batch_size > 1:
                 # OA_EXCHANGE_BATCH=K: K snapshots per exchange, finished one
@@ -499,7 +508,8 @@ def run_b200(args):
         # nvidia-smi is started before the warm-up: its NVML initialisation
         # stalls CUDA calls for tens of ms and must not fall in the timed region
         sampler = ClockSampler(local)
-        if rank == 0:
+        per_rank_clocks = world > 1 and os.environ.get('OA_BENCH_RANK_CLOCKS') == '1'
+        if rank == 0 or per_rank_clocks:
             sampler.start()
         from collections import deque
         depth = max(1, args.depth)     # snapshots in flight (tracker ring = 3)
@@ -562,7 +572,7 @@ def run_b200(args):
         barrier()
         wall1 = time.time()
         ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+        clocks = sampler.stop(wall0, wall1) if (rank == 0 or per_rank_clocks) else None
         stats_on = stats_fn(pj_stats, 0)
         kern_ms = [a.elapsed_time(b) for a, b, _ in trk.timing]
         kern_n = [n for _, _, n in trk.timing]
@@ -575,7 +585,14 @@ def run_b200(args):
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             ms, n_part = float(mx[0]), float(sm[1])
             n_events = float(stats[2])      # already global after the merge
-        return {'ms': ms, 'wall_ms': 1e3 * (wall1 - wall0),
+        per_rank = None
+        if world > 1:
+            mine = {'rank': rank, 'kernel_ms': float(np.mean(kern_ms)) if kern_ms else None,
+                    'step_ms': float(stats[0]), 'clocks': clocks}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            per_rank = gathered
+        return {'ms': ms, 'wall_ms': 1e3 * (wall1 - wall0), 'per_rank': per_rank,
                 'host_phases_ms_per_step': {k: round(1e3 * v / K, 4)
                                             for k, v in phases.items()},
                 'particles': n_part, 'events': n_events,
@@ -647,6 +664,15 @@ def run_b200(args):
         e2e['events_equal_device_run'] = bool(
             e2e_run['events'] == dev_run['events'])
 
+    # ---- end to end through the drop-in ENTRY POINT --------------------------------
+    # track_orbits() itself: pageable numpy arrays from the loader callback (the
+    # staging memcpy into pinned memory included), the pipelined driver, and the
+    # result file written per snapshot.  Wall clock from the loader call of the
+    # third snapshot (allocation / pinning warm-up before it) to the return.
+    e2e_entry = None
+    if world == 1 and not args.no_e2e:
+        e2e_entry = entry_point_e2e(args, snaps, cats, gen, min(K, 12) + 2)
+
     # ---- roofline of the fused kernel ------------------------------------------
     peak, peak_kind = measured_peak()
     k_ms = float(np.mean(dev_run['kern_ms']))
@@ -703,6 +729,8 @@ def run_b200(args):
             'host_phases_ms_per_step': dev_run['host_phases_ms_per_step'],
             'roofline': roofline,
         }
+        if dev_run.get('per_rank'):
+            line['per_rank'] = dev_run['per_rank']
         if dev_run.get('pj_stats') and impl == 'pj2':
             st = dev_run['pj_stats']
             tot = float(st[12]) or 1.0      # cycles of thread 0 of every CTA
@@ -730,6 +758,8 @@ def run_b200(args):
             line['e2e'] = e2e
         elif not args.no_e2e:
             line['e2e_skipped'] = e2e_skipped
+        if e2e_entry is not None:
+            line['e2e_entry_point'] = e2e_entry
         if cpu is not None:
             line['cpu_baseline'] = cpu
         if multi_parity is not None:
@@ -859,6 +889,55 @@ def multi_rank_parity(args, snaps, cats, gen, comm, world, rank, torch, dist):
     return report
 
 
+def entry_point_e2e(args, snaps, cats, gen, n_e):
+    """Time ``track_orbits()`` (the call a user of the reference makes,
+    ``track_orbits.py:9-11``) over ``n_e`` snapshots of this run's data."""
+    import shutil
+    import tempfile
+    from nbody_orbit_analysis_b200 import track_orbits
+    n_e = min(n_e, len(snaps))
+    host = []
+    for t in range(n_e):
+        dev, n, offsets = snaps[t]
+        host.append({
+            'ids': dev['ids'].cpu().numpy(),                   # pageable
+            'coordinates': dev['pos'].cpu().numpy().reshape(-1, 3),
+            'velocities': dev['vel'].cpu().numpy().reshape(-1, 3),
+            'masses': 1.0, 'region_offsets': offsets[:-1].copy(),
+            'box_size': gen.host.box, 'redshift': 0.0, 'H0': 0.0,
+            'Omega_m': 0.3, 'Omega_L': 0.7})
+    marks = {}
+
+    def regions(sn, halo_ids):
+        return cats[int(sn)]
+
+    def loader(sn, pos, rad):
+        marks.setdefault(int(sn), time.perf_counter())
+        return host[int(sn)]
+    tmp = tempfile.mkdtemp(prefix='oa_entry_')
+    out = os.path.join(tmp, 'entry.h5')
+    mb = np.tile(np.arange(args.halos, dtype=np.int64), (n_e, 1))
+    track_orbits.track_orbits(np.arange(n_e), mb, regions, loader, out,
+                              mode=args.mode, verbose=False)
+    t1 = time.perf_counter()
+    first = 2
+    secs = t1 - marks[first]
+    count = sum(len(host[t]['ids']) for t in range(first, n_e))
+    file_bytes = os.path.getsize(out)
+    shutil.rmtree(tmp, ignore_errors=True)
+    steps = n_e - first
+    return {'value': count / secs, 'unit': 'particle-snapshots/s',
+            'ms_per_step': 1e3 * secs / steps, 'snapshots': steps,
+            'h2d_bytes_per_step': int(count / steps * 32 + args.halos * 72),
+            'file_bytes_per_step': int(file_bytes / max(n_e - 1, 1)),
+            'h2d_gb_per_s': count / steps * 32 / (secs / steps) / 1e9,
+            'what': 'nbody_orbit_analysis_b200.track_orbits.track_orbits(...) '
+                    'with loader callbacks returning PAGEABLE numpy arrays, '
+                    'result groups written per snapshot (storage backend: '
+                    'h5py if importable, else the in-repo container); wall '
+                    'clock'}
+
+
 def cpu_baseline(args, snaps, cats, gen, torch):
     """Oracle on the first halos of the first snapshots of THIS run's data,
     timed on one host core, and compared with the GPU path on the same data."""
@@ -929,5 +1008,11 @@ if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.config in (0, 3, 4):
+        sys.path.insert(0, os.path.join(HERE, 'tools'))
+        import bench_configs
+        bench_configs.run(a)
     else:
+        if a.config == 2:
+            a.halos = 100000
         run_b200(a)

@@ -70,6 +70,11 @@ typedef struct oa_region {
     int64_t reserved;
 } oa_region;             /* 128 bytes; the table must be 16-byte aligned      */
 
+/* Host twin of the device routine that restates numpy's pairwise summation
+ * (np.sum of a contiguous 1-D float array; used for the mass sum of the derived
+ * bulk velocity, track_orbits.py:270-274): HOST pointer, result in *out. */
+int oa_pairwise_sum_host(const void* a, int dtype, int64_t n, double* out);
+
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: the small
  * read-backs of a snapshot (reference: the numpy arrays `track` returns,
  * track_orbits.py:186-187, live on the host) without a stream switch in the

@@ -62,7 +62,7 @@ extern "C" int oa_region_rows_host(int n_regions, const int64_t* offsets,
                "oa_region_rows_host: bad dtype");
     OA_REQUIRE(n_prev_regions == 0 || (prev_halo_ids && prev_offsets && prev_buckets),
                "oa_region_rows_host: previous generation incomplete");
-    int m = 0;
+    int m = 0, hint = 0;
     for (int j = 0; j < n_regions; ++j) {
         oa_region& r = rows[j];
         memset(&r, 0, sizeof(r));
@@ -93,14 +93,22 @@ extern "C" int oa_region_rows_host(int n_regions, const int64_t* offsets,
         r.cur_bucket = oa_table_bucket_begin(offsets[j], j);
         buckets_out[j] = r.cur_bucket;
         r.prev_begin = -1;
-        // position of this halo in the previous (ascending) list
-        int lo = 0, hi = n_prev_regions;
+        // position of this halo in the previous (ascending) list.  Catalogues
+        // keep their order from snapshot to snapshot: the entry after the last
+        // hit is tried first (a binary search per halo is 17 cache misses at
+        // 100 k halos: 6 ms per snapshot)
         const int64_t id = halo_ids[j];
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (prev_halo_ids[mid] < id) lo = mid + 1; else hi = mid;
+        int lo = hint;
+        if (!(lo < n_prev_regions && prev_halo_ids[lo] == id)) {
+            int hi = n_prev_regions;
+            lo = 0;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (prev_halo_ids[mid] < id) lo = mid + 1; else hi = mid;
+            }
         }
         const bool hit = lo < n_prev_regions && prev_halo_ids[lo] == id;
+        if (hit) hint = lo + 1;
         matched_out[j] = hit ? 1 : 0;
         prev_index_out[j] = hit ? lo : -1;
         if (hit) {

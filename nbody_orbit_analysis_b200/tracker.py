@@ -84,8 +84,20 @@ class OrbitTracker:
     """
 
     def __init__(self, mode='pericentric', device=None, onthefly=False,
-                 impl=None):
+                 impl=None, ring=None):
         require_cuda()
+        # ring: slots every device buffer cycles through.  3 (default) lets two
+        # snapshots be in flight (submit s+1 before collecting s); 2 is the
+        # minimum (previous + current generation) and is the memory plan for
+        # snapshots that fill HBM: ~79 B per region-particle and slot (32 inputs +
+        # 32 record + ~13 table + 2 mark), i.e. 158 B/particle instead of 237
+        import os
+        if ring is None and os.environ.get('OA_TRACKER_RING'):
+            ring = int(os.environ['OA_TRACKER_RING'])
+        if ring is not None:
+            if int(ring) < 2:
+                raise ValueError("ring must be at least 2")
+            self.RING = int(ring)
         # 'hash' : oa_track_fused (global hash table, every option)
         # 'pjoin': oa_pjoin_step (partitioned shared-memory join; float32 data
         #          and catalogue, plain tracking without per-particle outputs)

@@ -90,13 +90,11 @@ class FakeLib:
 
     def oa_bulk_velocity(self, vel, vel_dtype, mass, mass_dtype, cur_off, n_h, n,
                          round_f32, rows, bulk_out, ws, ws_bytes, st):
-        """csrc/oa_bulk.cu in numpy: (mass-weighted) mean velocity of every
-        block, float64 accumulation, written to the rows and to bulk_out."""
+        """csrc/oa_bulk.cu reproduces numpy's summation order: here numpy
+        itself, written to the rows and to bulk_out."""
         self.calls.append('oa_bulk_velocity')
-        v = _arr(vel, 3 * n, C.c_double if vel_dtype else C.c_float)
-        v = v.reshape(-1, 3).astype(np.float64)
-        m = _arr(mass, n, C.c_double if mass_dtype else C.c_float).astype(
-            np.float64) if mass else np.ones(n)
+        v = _arr(vel, 3 * n, C.c_double if vel_dtype else C.c_float).reshape(-1, 3)
+        m = _arr(mass, n, C.c_double if mass_dtype else C.c_float) if mass else None
         off = _arr(cur_off, n_h + 1, C.c_int64)
         from nbody_orbit_analysis_b200._lib import REGION_DTYPE
         rec = _arr(rows, n_h * 128, C.c_uint8).view(REGION_DTYPE)
@@ -104,9 +102,13 @@ class FakeLib:
         with np.errstate(all='ignore'):
             for j in range(n_h):
                 lo, hi = off[j], off[j + 1]
-                b = (v[lo:hi] * m[lo:hi, None]).sum(axis=0) / m[lo:hi].sum()
-                if round_f32:
-                    b = b.astype(np.float32).astype(np.float64)
+                # the reference's own expressions (track_orbits.py:270-280)
+                if m is not None:
+                    b = np.sum(m[lo:hi][:, np.newaxis] * v[lo:hi], axis=0) / \
+                        np.sum(m[lo:hi])
+                else:
+                    b = np.mean(v[lo:hi], axis=0)
+                b = b.astype(np.float64)
                 rec['bulk'][j] = b
                 rec['bulk_f'][j] = b
                 if out is not None:

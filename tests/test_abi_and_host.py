@@ -203,3 +203,39 @@ def test_region_rows_host_equals_numpy_assembly():
         if n_h and n_p:
             exp_prev[matched] = pos_c[matched]
         assert np.array_equal(g_prev, exp_prev)
+
+
+def test_pairwise_sum_equals_numpy():
+    """The mass sum of the derived bulk velocity (``np.sum`` of a contiguous
+    1-D slice, ``track_orbits.py:270-274``) is numpy's pairwise sum: the routine
+    the device kernel uses (csrc/oa_bulk.cu, compiled for the host too) must
+    return numpy's value bit for bit at every length class of the algorithm."""
+    import ctypes as C
+    from nbody_orbit_analysis_b200 import _lib
+    rng = np.random.default_rng(3)
+    sizes = list(range(0, 280)) + [1000, 1023, 1024, 1025, 4095, 8191, 8192,
+                                   8193, 16385, 70001, 200000, 1234567]
+    for dt in (np.float32, np.float64):
+        for n in sizes:
+            a = (rng.uniform(0.5, 1.5, n) * rng.choice([-1, 1], n)).astype(dt)
+            out = C.c_double()
+            _lib.check(_lib.lib.oa_pairwise_sum_host(
+                a.ctypes.data, _lib.dtype_code(dt), n, C.byref(out)))
+            ref = np.sum(a) if n else dt(0)
+            assert dt(out.value) == ref, (dt, n)
+
+
+def test_axis0_reduction_is_sequential():
+    """The other half of the derived bulk velocity: numpy reduces axis 0 of an
+    (n, 3) array row after row in the array's dtype (what the device kernel's
+    three chains do) -- pinned here so that a numpy that changes its order is
+    noticed."""
+    rng = np.random.default_rng(4)
+    for dt in (np.float32, np.float64):
+        for n in (1, 9, 129, 8193, 50000):
+            v = (rng.normal(0, 100, (n + 3, 3)) + 30).astype(dt)[3:]
+            acc = v[0].copy()
+            for row in v[1:]:
+                acc = acc + row
+            assert np.array_equal(np.add.reduce(v, axis=0), acc)
+            assert np.array_equal(np.mean(v, axis=0), acc / dt(n))

@@ -155,6 +155,9 @@ def test_bench_end_to_end_on_fake_cuda(emul, pjoin_env, monkeypatch, capsys):
     assert line['events_per_step'] > 0
     assert line['e2e']['value'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
     assert line['e2e']['events_per_step'] == line['events_per_step']
+    # the same data through the drop-in entry point (pageable arrays, file write)
+    ep = line['e2e_entry_point']
+    assert ep['value'] > 0 and ep['snapshots'] == 3 and ep['file_bytes_per_step'] > 0
     r = line['roofline']
     assert r['bound'] == 'hbm' and r['achieved'] > 0 and 'oa_pjoin' in r['kernel']
     assert line['cpu_baseline']['parity_vs_gpu_on_sample'] == 'ok'
