@@ -165,6 +165,7 @@ def cpu_track(snapshots, catalog, mode):
     from oracle import orbit_oracle as oracle
     prev, outs = None, []
     seconds, count = 0.0, 0
+    near_zero = []
     for s, (snap, (pos, rad, bulk)) in enumerate(zip(snapshots, catalog)):
         exists = np.arange(len(pos))
         t0 = time.perf_counter()
@@ -176,6 +177,16 @@ def cpu_track(snapshots, catalog, mode):
             count += len(snap['ids'])
         outs.append(out)
         prev = state
+        # particles whose |v_r| lies within float eps of zero (north_star:
+        # "listed separately"): relative to their speed in the halo frame
+        lens = np.diff(np.append(snap['region_offsets'], len(snap['ids'])))
+        vrel = np.linalg.norm(
+            snap['velocities'].astype(np.float64) - np.repeat(
+                np.asarray(bulk, dtype=np.float64), lens, axis=0), axis=1)
+        hit = np.flatnonzero(np.abs(state.radial_vels) <=
+                             8 * np.finfo(np.float32).eps * vrel)
+        near_zero += [(s, int(snap['ids'][i])) for i in hit]
+    cpu_track.near_zero = near_zero
     return seconds, count, outs
 
 
@@ -985,6 +996,13 @@ def cpu_baseline(args, snaps, cats, gen, torch):
         'seconds': secs,
         'parity_vs_gpu_on_sample': 'ok' if ok else 'MISMATCH',
         'sample_events': n_ev,
+        # |v_r| <= 8 float32 eps x |v - v_bulk|: the sign of such a v_r could
+        # differ between two correct float evaluations; the CUDA path rounds
+        # where numpy rounds, so these particles still agree with the reference
+        'vr_within_eps_of_zero': {
+            'count': len(cpu_track.near_zero),
+            'first': [list(x) for x in cpu_track.near_zero[:8]],
+            'what': '(snapshot of the sample, particle ID)'},
     }
     if reference_available():
         # the UNMODIFIED reference on the same sample, one core (npool=None is

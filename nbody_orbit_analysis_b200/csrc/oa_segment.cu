@@ -331,16 +331,40 @@ __global__ void merge_blocks_kernel(const unsigned char* __restrict__ recv, int 
         info[0] = tot;
         info[1] = largest;
     }
-    if (i >= size) return;
-    const int64_t key = reinterpret_cast<const int64_t*>(mine + L.keys)[i];
-    int64_t pos = i;
-    for (int q = 0; q < world; ++q) {
-        if (q == r) continue;
-        const unsigned char* other = recv + (size_t)q * L.bytes;
+    // The keys of this CTA's elements are ascending, so their lower bounds in
+    // another list lie between the lower bounds of the CTA's first and last key:
+    // one full binary search per (CTA, list) and end, then every element searches
+    // a window of about blockDim.x entries (a few cache lines) instead of the
+    // whole list -- (world - 1) x 17 dependent, scattered loads per event were
+    // slowing the tracking kernel the exchange overlaps with.
+    __shared__ int64_t s_lo[64], s_hi[64];
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    if (first >= size) return;                       // (uniform for the CTA)
+    const int64_t last = min(first + (int64_t)blockDim.x, size) - 1;
+    const int64_t* my_keys = reinterpret_cast<const int64_t*>(mine + L.keys);
+    for (int q = threadIdx.x; q < 2 * world; q += blockDim.x) {
+        const int list = q >> 1;
+        const int64_t key = (q & 1) ? my_keys[last] : my_keys[first];
+        const unsigned char* other = recv + (size_t)list * L.bytes;
         int64_t hi = reinterpret_cast<const int64_t*>(other)[0];
         if (hi > cap) hi = cap;
         const int64_t* keys = reinterpret_cast<const int64_t*>(other + L.keys);
         int64_t lo = 0;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        if (q & 1) s_hi[list] = lo; else s_lo[list] = lo;
+    }
+    __syncthreads();
+    if (i >= size) return;
+    const int64_t key = my_keys[i];
+    int64_t pos = i;
+    for (int q = 0; q < world; ++q) {
+        if (q == r) continue;
+        const int64_t* keys =
+            reinterpret_cast<const int64_t*>(recv + (size_t)q * L.bytes + L.keys);
+        int64_t lo = s_lo[q], hi = s_hi[q];
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
             if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
@@ -478,8 +502,8 @@ extern "C" int oa_stage_events(const int64_t* gpos, const int64_t* sel, const in
 extern "C" int oa_merge_blocks(const void* recv, int world, int64_t cap, int64_t* ids_out,
                                uint16_t* angles_out, int64_t* info, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    OA_REQUIRE(recv && ids_out && angles_out && info && world >= 1 && cap >= 1,
-               "oa_merge_blocks: bad arguments");
+    OA_REQUIRE(recv && ids_out && angles_out && info && world >= 1 && world <= 64 && cap >= 1,
+               "oa_merge_blocks: bad arguments (at most 64 ranks)");
     dim3 grid(blocks_for(cap, 256), (unsigned)world);
     merge_blocks_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(recv), world,
                                               cap, ids_out, angles_out, info);

@@ -81,17 +81,24 @@ def test_ordered_select(n, density):
             offs, np.searchsorted(np.flatnonzero(~hit), begins, side='left'))
 
 
-@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('dtype,mdtype', [(np.float32, np.float32),
+                                          (np.float64, np.float64),
+                                          (np.float32, np.float64),
+                                          (np.float64, np.float32)])
 @pytest.mark.parametrize('weighted', [False, True])
-def test_bulk_velocity(dtype, weighted):
+def test_bulk_velocity(dtype, mdtype, weighted):
+    """Derived bulk velocity = the reference's own numpy expressions
+    (track_orbits.py:270-280), BIT for bit: the kernel adds in numpy's order
+    (axis-0 reduction row after row, mass sum pairwise)."""
     torch, _lib, lib, ptr, check = _env()
     rng = np.random.default_rng(11)
-    lens = np.concatenate([[0, 1, 2, 5000, 0, 33, 9000, 4096, 4097, 1, 0],
+    lens = np.concatenate([[0, 1, 2, 5000, 0, 33, 9000, 4096, 4097, 1, 0, 7, 8,
+                            9, 127, 128, 129, 300000],
                            rng.integers(0, 50, 400)])
     off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
     n, nh = int(off[-1]), len(lens)
-    vel = rng.normal(0, 200, (n, 3)).astype(dtype)
-    mass = rng.uniform(0.5, 2, n).astype(dtype) if weighted else None
+    vel = (rng.normal(0, 200, (n, 3)) + 40).astype(dtype)
+    mass = rng.uniform(0.5, 2, n).astype(mdtype) if weighted else None
     rows = np.zeros(nh, dtype=_lib.REGION_DTYPE)
     d_rows = _dev(torch, rows.view(np.uint8))
     d_out = torch.empty(3 * nh, dtype=torch.float64, device='cuda')
@@ -100,25 +107,26 @@ def test_bulk_velocity(dtype, weighted):
     d_vel, d_off = _dev(torch, vel.reshape(-1)), _dev(torch, off)
     d_mass = _dev(torch, mass) if weighted else None
     code = 1 if dtype == np.float64 else 0
-    check(lib.oa_bulk_velocity(ptr(d_vel), code, ptr(d_mass), code, ptr(d_off),
+    mcode = 1 if mdtype == np.float64 else 0
+    check(lib.oa_bulk_velocity(ptr(d_vel), code, ptr(d_mass), mcode, ptr(d_off),
                                nh, n, 0, ptr(d_rows), ptr(d_out), ptr(ws),
                                ws_bytes, None))
     got = d_out.cpu().numpy().reshape(nh, 3)
     rows_back = d_rows.cpu().numpy().view(_lib.REGION_DTYPE)
     with np.errstate(all='ignore'):
         for j in range(nh):
-            v = vel[off[j]:off[j + 1]].astype(np.float64)
+            v = vel[off[j]:off[j + 1]]
             if weighted:
-                m = mass[off[j]:off[j + 1]].astype(np.float64)
-                exp = (m[:, None] * v).sum(0) / m.sum()
+                m = mass[off[j]:off[j + 1]]
+                exp = np.sum(m[:, np.newaxis] * v, axis=0) / np.sum(m)
             else:
-                exp = v.mean(0) if len(v) else np.full(3, np.nan)
-            assert np.allclose(got[j], exp, rtol=1e-12, atol=1e-9,
-                               equal_nan=True), j
+                exp = np.mean(v, axis=0)
+            assert np.array_equal(got[j], exp.astype(np.float64),
+                                  equal_nan=True), (j, got[j], exp)
             assert np.array_equal(rows_back['bulk'][j], got[j], equal_nan=True)
     # deterministic: a second run gives the same bits
     d_out2 = torch.empty_like(d_out)
-    check(lib.oa_bulk_velocity(ptr(d_vel), code, ptr(d_mass), code, ptr(d_off),
+    check(lib.oa_bulk_velocity(ptr(d_vel), code, ptr(d_mass), mcode, ptr(d_off),
                                nh, n, 0, ptr(d_rows), ptr(d_out2), ptr(ws),
                                ws_bytes, None))
     assert np.array_equal(d_out2.cpu().numpy(), d_out.cpu().numpy(),

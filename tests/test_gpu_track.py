@@ -386,7 +386,7 @@ def test_device_state_checkpoint_resume(mode, tmp_path):
         track_orbits.track_orbits(sim.snapshot_numbers, sim.main_branches,
                                   sim.regions, crashing, f_b, mode=mode,
                                   checkpoint='state', verbose=False)
-    saved = [int(key.split('_')[1]) for key in storage.tree(f_b)
+    saved = [int(key.split('/')[1].split('_')[1]) for key in storage.tree(f_b)
              if key.endswith('/halo_IDs')]
     last = max(saved)
     assert last < int(sim.snapshot_numbers[k])

@@ -28,23 +28,39 @@ def _line(metric, unit, value, steps, ms, config, extra):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'data': 'synthetic', 'config': config}
     line.update(extra)
+    if MISMATCHES:
+        line['parity_detail'] = MISMATCHES[:8]
     print(json.dumps(line))
     return line
 
 
+MISMATCHES = []          # first differences found, reported in the JSON line
+
+
 def _trees_equal(got, exp):
+    """Integer datasets identical, float datasets within the float16-angle
+    tolerance of the GPU tests; differences are noted in MISMATCHES."""
     if sorted(got) != sorted(exp):
+        MISMATCHES.append('keys: %s' % sorted(set(got) ^ set(exp))[:4])
         return False
-    for k in exp:
+    ok = True
+    for k in sorted(exp):
         a, b = np.asarray(got[k]), np.asarray(exp[k])
-        if a.dtype.kind == 'f' or b.dtype.kind == 'f':
-            if a.shape != b.shape or not np.allclose(
-                    a.astype(np.float64), b.astype(np.float64), rtol=2e-3,
-                    atol=2e-3, equal_nan=True):
-                return False
+        if a.shape != b.shape:
+            MISMATCHES.append('%s: shape %s vs %s' % (k, a.shape, b.shape))
+            ok = False
+        elif a.dtype.kind == 'f' or b.dtype.kind == 'f':
+            close = np.isclose(a.astype(np.float64), b.astype(np.float64),
+                               rtol=2e-3, atol=2e-3, equal_nan=True)
+            if not close.all():
+                MISMATCHES.append('%s: %d of %d floats differ' % (
+                    k, int((~close).sum()), close.size))
+                ok = False
         elif not np.array_equal(a, b):
-            return False
-    return True
+            MISMATCHES.append('%s: %d of %d integers differ' % (
+                k, int((a != b).sum()), a.size))
+            ok = False
+    return ok
 
 
 # ---------------------------------------------------------------------------
