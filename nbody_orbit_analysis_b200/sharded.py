@@ -341,6 +341,16 @@ class Comm:
                 ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
                 ptr(res.d_ang_buf), ptr(res.d_small), n_seg, ptr(prop_all), W,
                 cap, ptr(bnd), ptr(send), ptr(counts), st))
+            # The tracker's ring buffers (gpos, selection, event lists) have now
+            # been read: the NEXT snapshot may be submitted once the pack kernel
+            # is done.  (Round 1 recorded this event after the collectives, so
+            # every submit waited for the all-to-all of the previous snapshot --
+            # i.e. for the slowest rank -- before its tracking kernel could start.)
+            # A batch reads staging buffers of its own: nothing to wait for.
+            if not persistent:
+                packed = self._event()
+                packed.record(self.stream)
+                tracker.wait_before_submit = packed
             dist.all_to_all_single(recv, send)
             h.ids = torch.empty(W * cap, **i64)
             h.ang = torch.empty(W * cap, dtype=torch.int16, device=self.device)
@@ -352,9 +362,6 @@ class Comm:
             if not persistent:
                 self._splitters = meta_all.view(W, -1)[:, 2 + n_cnt:].contiguous()
             tracker.launches += 5
-            done = self._event()
-            done.record(self.stream)
-            tracker.wait_before_submit = done
             # (meta_all is read by the copy stream below: it must stay allocated
             # until the handle is finished, or the caching allocator hands its
             # block to the next exchange while the copy is still queued)
@@ -365,8 +372,11 @@ class Comm:
         h.h_meta, h.ready = tracker.to_host_async(meta_all, stream=self.stream)
         return h
 
-    def _round_cap(self, largest):
-        return -(-int(self.HEADROOM * max(largest, 1024)) // 4096) * 4096
+    BATCH_HEADROOM = 1.3  # batches split by their own quantiles: blocks are balanced
+
+    def _round_cap(self, largest, headroom=None):
+        headroom = self.HEADROOM if headroom is None else headroom
+        return -(-int(headroom * max(largest, 1024)) // 4096) * 4096
 
     def _launch_merge(self, tracker, res, cap, to_host):
         gen = res.prev_gen
@@ -383,6 +393,10 @@ class Comm:
                 ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
                 ptr(res.d_ang_buf), ptr(res.d_small), n_seg, cap, ptr(send),
                 st))
+            # the tracker's ring buffers have been read (see _launch_split)
+            packed = self._event()
+            packed.record(self.stream)
+            tracker.wait_before_submit = packed
             recv = torch.empty(self.world * nbytes, dtype=torch.uint8,
                                device=self.device)
             dist.all_gather_into_tensor(recv, send)
@@ -395,10 +409,6 @@ class Comm:
             check(lib.oa_merge_gathered(ptr(recv), self.world, n_seg, cap,
                                         ptr(h.ids), ptr(h.ang), ptr(info), st))
             tracker.launches += 3
-            # the tracker's ring buffers read above may be rewritten after this
-            done = self._event()
-            done.record(self.stream)
-            tracker.wait_before_submit = done
             h.keep = (send, recv, info)
         # small read-back (total, global offsets, sizes, overflow flag) into a
         # pinned buffer owned by the handle (see _launch_split)
@@ -447,7 +457,7 @@ class Comm:
             h_ids, h_ang, ready = h.tracker.to_host_async(
                 res.d_ids[lo:hi], res.d_ang[lo:hi], stream=self.stream,
                 names=('x_ids', 'x_ang'), reserve=max(hi - lo, self._cap),
-                step=self._results)
+                step=self._results, bulk=True)
             res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
             res.apsis_angles = h_ang.numpy().view(np.float16)
             res.host_slice, res.host_ready = (lo, hi), ready
@@ -471,7 +481,9 @@ class Comm:
                 h.tracker, h.res, self._block_cap(), h.to_host,
                 splitters=h.splitters))
         self._repeats = 0
-        self._cap = max(self._cap, self._round_cap(int(sizes.max())))
+        batch = getattr(h.res, 'persistent', False)
+        self._cap = max(self._cap, self._round_cap(
+            int(sizes.max()), self.BATCH_HEADROOM if batch else None))
         res = h.res
         total = int(sizes.sum())
         lo = int(sizes[:self.rank].sum())
@@ -494,7 +506,7 @@ class Comm:
                 res.d_ids, res.d_ang, stream=self.stream,
                 names=('xb_ids', 'xb_ang') if batch else ('x_ids', 'x_ang'),
                 reserve=int(1.25 * (hi - lo)) if batch else max(hi - lo, self._cap),
-                step=self._results)
+                step=self._results, bulk=True)
             res.apsis_ids = h_ids.numpy().astype(gen.ids_dtype, copy=False)
             res.apsis_angles = h_ang.numpy().view(np.float16)
             res.host_ready = ready
@@ -511,7 +523,8 @@ class Comm:
         t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         per_snapshot = max(int(t.item()), 1024)
-        self._cap = max(self._cap or 0, self._round_cap(K * per_snapshot))
+        self._cap = max(self._cap or 0, self._round_cap(K * per_snapshot,
+                                                        self.BATCH_HEADROOM))
         n_ev = int(1.3 * K * per_snapshot)
         keep_open = self._open
         for slot in range(3):
@@ -553,6 +566,12 @@ class Comm:
         if self.stream is None:
             self.stream = _HostStream() if self.device.type != 'cuda' \
                 else torch.cuda.Stream(self.device)
+        if getattr(self, 'stage_stream', None) is None:
+            # staging has a stream of its own: on the exchange stream a snapshot's
+            # stage kernel would queue behind the previous batch's all-to-all, and
+            # the next submit (which waits for the stage kernel) with it
+            self.stage_stream = _HostStream() if self.device.type != 'cuda' \
+                else torch.cuda.Stream(self.device)
         b = self._open
         n_local, n_seg = int(res.n_events), len(res.apsis_offsets) - 1
         if getattr(self, '_reserved_for', None) is not tracker:
@@ -565,18 +584,20 @@ class Comm:
             self._batches += 1
         st_set = self._staging(b.slot, b.n_local + n_local, b.n_seg + n_seg + 1)
         if res.compacted is not None:
-            self.stream.wait_event(res.compacted)
-        with self._on_stream():
-            check(lib.oa_stage_events(
-                ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
-                ptr(res.d_ang_buf), ptr(res.d_small), n_seg, n_local,
-                len(b.items) << self.TAG_SHIFT, b.n_local, ptr(st_set['keys']),
-                ptr(st_set['ids']), ptr(st_set['ang']),
-                ptr(st_set['small'][b.n_seg:]), C.c_void_p(self.stream.cuda_stream)))
-            tracker.launches += 1
-            done = self._event()
-            done.record(self.stream)
-            tracker.wait_before_submit = done   # the ring buffers were read
+            self.stage_stream.wait_event(res.compacted)
+        # (the kernel takes its stream as an argument: no stream context)
+        check(lib.oa_stage_events(
+            ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+            ptr(res.d_ang_buf), ptr(res.d_small), n_seg, n_local,
+            len(b.items) << self.TAG_SHIFT, b.n_local, ptr(st_set['keys']),
+            ptr(st_set['ids']), ptr(st_set['ang']),
+            ptr(st_set['small'][b.n_seg:]),
+            C.c_void_p(self.stage_stream.cuda_stream)))
+        tracker.launches += 1
+        done = self._event()
+        done.record(self.stage_stream)
+        tracker.wait_before_submit = done       # the ring buffers were read
+        b.staged = done                         # the exchange waits for the last one
         b.items.append((res, n_seg, b.n_seg, n_local))
         b.n_local += n_local
         b.n_seg += n_seg
@@ -588,11 +609,17 @@ class Comm:
     def _staging(self, slot, n_events, n_small):
         """Staging arrays of a batch (kept and grown geometrically).  Everything
         here -- allocation, the grow-copy, the identity selection -- is issued on
-        the EXCHANGE stream, the only stream that touches these arrays; a
+        the STAGING stream, which also runs the stage kernels; the exchange
+        stream waits for the batch's last stage kernel before it reads them.  A
         replaced array stays referenced by the open batch until the batch is
         finished, so its block cannot be recycled under a pending copy."""
         st_set = self._stage_sets.setdefault(slot, {})
         b = self._open
+        keys = st_set.get('keys')
+        if keys is not None and keys.numel() >= n_events and \
+                st_set['small'].numel() >= n_small and \
+                st_set['iota'].numel() >= keys.numel():
+            return st_set                   # steady state: nothing to allocate
         retired = b.__dict__.setdefault('retired', [])
 
         def grow(name, n, dtype, keep):
@@ -606,7 +633,8 @@ class Comm:
                     retired.append(old)
                 st_set[name] = new
 
-        with self._on_stream():
+        with (torch.cuda.stream(self.stage_stream) if self.device.type == 'cuda'
+              else self.stage_stream):
             grow('keys', n_events, torch.int64, b.n_local)
             grow('ids', n_events, torch.int64, b.n_local)
             grow('ang', n_events, torch.int16, b.n_local)
@@ -626,6 +654,7 @@ class Comm:
         if b is None or not b.items:
             return None
         st_set = self._stage_sets[b.slot]
+        self.stream.wait_event(b.staged)        # every snapshot of the batch is staged
         if self._cap is None:
             t = torch.tensor([b.n_local], dtype=torch.int64, device=self.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -134,6 +134,7 @@ class OrbitTracker:
         self.sm_reserve = 0        # SMs the fused kernel leaves to other streams
         self._cur_main = None
         self._copy_st = C.c_void_p(self.copy_stream.cuda_stream)
+        self._bulk_stream = None
 
     # -- buffers -------------------------------------------------------------
     RING = 3      # generations / in-flight steps a buffer name cycles through
@@ -228,7 +229,8 @@ class OrbitTracker:
             raw = self._hpool[key]
         return raw[:int(n) * item].view(dtype)
 
-    def _to_host_async(self, t, n=None, name=None, step=None, reserve=0):
+    def _to_host_async(self, t, n=None, name=None, step=None, reserve=0,
+                       via=None):
         """Device tensor -> pinned host tensor on the copy stream (the caller
         synchronises before reading).  With ``name`` the destination is the
         tracker's pinned ring buffer of that name."""
@@ -241,7 +243,8 @@ class OrbitTracker:
             # (cudaMemcpyAsync on the copy stream through the C ABI: no stream
             # switch of the host framework per copy)
             check(lib.oa_copy_async(h.data_ptr(), t.data_ptr(),
-                                    n * _ITEMSIZE[t.dtype], self._copy_st))
+                                    n * _ITEMSIZE[t.dtype],
+                                    self._copy_st if via is None else via))
         return h
 
     def to_host(self, *tensors, stream=None):
@@ -255,19 +258,28 @@ class OrbitTracker:
         return out
 
     def to_host_async(self, *tensors, stream=None, names=None, reserve=0,
-                      step=None):
+                      step=None, bulk=False):
         """Like ``to_host`` without the synchronisation: returns the pinned
         tensors and the event that marks their completion.  With ``names`` the
         destinations are the tracker's pinned ring buffers of those names, slot
-        ``step`` mod HOST_RING (default: the number of submitted snapshots)."""
+        ``step`` mod HOST_RING (default: the number of submitted snapshots).
+        ``bulk``: a large copy (the merged event lists of the multi-GPU
+        exchange) goes on a stream of its own, so that the few-kilobyte
+        read-backs every ``collect`` waits for do not queue behind it."""
+        cs = self.copy_stream
+        if bulk:
+            if self._bulk_stream is None:
+                self._bulk_stream = torch.cuda.Stream(self.device)
+            cs = self._bulk_stream
         done = torch.cuda.Event()
         done.record(stream if stream is not None else self._main())
-        self.copy_stream.wait_event(done)
+        cs.wait_event(done)
+        via = C.c_void_p(cs.cuda_stream) if bulk else None
         names = names or [None] * len(tensors)
-        out = [self._to_host_async(t, name=nm, reserve=reserve, step=step)
+        out = [self._to_host_async(t, name=nm, reserve=reserve, step=step, via=via)
                for t, nm in zip(tensors, names)]
         ready = torch.cuda.Event()
-        ready.record(self.copy_stream)
+        ready.record(cs)
         return out + [ready]
 
     # -- one snapshot ----------------------------------------------------------

@@ -188,7 +188,7 @@ class EmulTracker:
         self._ring = {}
 
     def to_host_async(self, *tensors, stream=None, names=None, reserve=0,
-                      step=None):
+                      step=None, bulk=False):
         step = self._step if step is None else step
         if names is None:                  # buffers owned by the caller
             return [t.clone() for t in tensors] + [_Done()]
