@@ -487,7 +487,9 @@ def run_b200(args):
                 return res, done
             # every rank hands its 1/world share of the merged lists to the
             # host (parallel write of the result datasets)
-            h = timed('start_merge', comm.start_merge, trk, res, to_host='slice')
+            h = timed('start_merge', comm.start_merge, trk, res,
+                      to_host=False if os.environ.get('OA_BENCH_TO_HOST') == '0'
+                      else 'slice')
             prev, exchange['inflight'] = exchange['inflight'], h
             if prev is not None:
                 done.append(timed('finish_merge', comm.finish_merge, prev))
@@ -742,6 +744,11 @@ def run_b200(args):
         }
         if dev_run.get('per_rank'):
             line['per_rank'] = dev_run['per_rank']
+        if comm is not None and getattr(comm, 'phase_ms', None):
+            n_x = max(comm.phase_ms.get('exchanges', 1), 1)
+            line['exchange_phases_ms'] = {
+                k: round(v / n_x, 4) for k, v in comm.phase_ms.items()
+                if k != 'exchanges'}
         if dev_run.get('pj_stats') and impl == 'pj2':
             st = dev_run['pj_stats']
             tot = float(st[12]) or 1.0      # cycles of thread 0 of every CTA
@@ -974,11 +981,17 @@ def cpu_baseline(args, snaps, cats, gen, torch):
     # same sample through the CUDA path
     trk = OrbitTracker(mode=args.mode)
     ok, n_ev = True, 0
+    ulp_hist = np.zeros(4, dtype=np.int64)     # float16 event angles: 0, 1, 2, >2 ulp
     for t in range(n_s):
         res = trk.step(host[t], np.arange(ncols), cat[t][0], cat[t][2], 0.0)
         if t > 0:
             exp = outs[t]
             n_ev += len(exp['apsis_ids'])
+            ga = np.asarray(res.apsis_angles, dtype=np.float16).view(np.int16)
+            ea = np.asarray(exp['apsis_angles'], dtype=np.float16).view(np.int16)
+            if ga.shape == ea.shape:
+                du = np.abs(ga.astype(np.int64) - ea.astype(np.int64))
+                ulp_hist += np.bincount(np.minimum(du, 3), minlength=4)[:4]
             ok &= np.array_equal(res.apsis_ids, exp['apsis_ids'])
             ok &= np.array_equal(res.apsis_offsets, exp['apsis_offsets'])
             a, b = res.apsis_angles.astype(np.float32), \
@@ -996,6 +1009,11 @@ def cpu_baseline(args, snaps, cats, gen, torch):
         'seconds': secs,
         'parity_vs_gpu_on_sample': 'ok' if ok else 'MISMATCH',
         'sample_events': n_ev,
+        # float16 accumulated angles of the events, GPU vs oracle (arccos is not
+        # correctly rounded in either libm; a 1-ulp difference of a float16
+        # accumulator carries forward)
+        'angle_ulp_histogram': {'0': int(ulp_hist[0]), '1': int(ulp_hist[1]),
+                                '2': int(ulp_hist[2]), '>2': int(ulp_hist[3])},
         # |v_r| <= 8 float32 eps x |v - v_bulk|: the sign of such a v_r could
         # differ between two correct float evaluations; the CUDA path rounds
         # where numpy rounds, so these particles still agree with the reference

@@ -80,6 +80,11 @@ int oa_pairwise_sum_host(const void* a, int dtype, int64_t n, double* out);
  * track_orbits.py:186-187, live on the host) without a stream switch in the
  * host framework.  Pinned host memory for a truly asynchronous copy. */
 int oa_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+/* The same for a few kilobytes, done by a kernel (SM stores into pinned,
+ * UVA-mapped host memory) instead of a copy engine: a small read-back that the
+ * host waits for must not queue behind the event lists in flight on the DMA
+ * engine.  `dst` / `src` / `bytes` multiples of 4. */
+int oa_copy_small(void* dst, const void* src, size_t bytes, void* stream);
 
 /* The region table on the HOST (host pointers, no CUDA call): what the Python
  * driver otherwise assembles with ~20 numpy calls per snapshot.  For region j:

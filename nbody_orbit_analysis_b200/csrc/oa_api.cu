@@ -29,6 +29,34 @@ extern "C" int oa_device_info(int* sm_count, int* cc_major, int* cc_minor,
     return OA_OK;
 }
 
+// Copy by a kernel instead of a copy engine: for the few-kilobyte read-backs the
+// host waits for every snapshot (event counts, exchange sizes).  The DMA engine of
+// a direction serves the copies of ALL streams in issue order, so such a copy
+// would sit behind megabytes of event lists that are in flight to the host; SM
+// stores into (UVA-mapped) pinned host memory are independent of that queue.
+namespace {
+__global__ void copy_small_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                  size_t words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+         i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace
+
+extern "C" int oa_copy_small(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return OA_OK;
+    OA_REQUIRE(dst && src && bytes % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3u) == 0,
+               "oa_copy_small: pointers and size must be multiples of 4 bytes");
+    const size_t words = bytes / 4;
+    const unsigned blocks = (unsigned)((words + 255) / 256 < 64 ? (words + 255) / 256 : 64);
+    copy_small_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src), words);
+    OA_LAUNCH_CHECK();
+    return OA_OK;
+}
+
 // plain asynchronous copy on an explicit stream (host code: a small device->host
 // or host->device copy without switching the framework's current stream)
 extern "C" int oa_copy_async(void* dst, const void* src, size_t bytes, void* stream) {

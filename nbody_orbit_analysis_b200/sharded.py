@@ -308,8 +308,10 @@ class Comm:
         h.step0 = getattr(res, 'step', tracker._step)
         if res.compacted is not None:
             self.stream.wait_event(res.compacted)
+        prof = self._profile_events()
         with self._on_stream():
             st = C.c_void_p(self.stream.cuda_stream)
+            self._mark(prof, 'start')
             i64 = dict(dtype=torch.int64, device=self.device)
             u8 = dict(dtype=torch.uint8, device=self.device)
             n_prop = max(W - 1, 1)
@@ -351,13 +353,18 @@ class Comm:
                 packed = self._event()
                 packed.record(self.stream)
                 tracker.wait_before_submit = packed
+            self._mark(prof, 'packed')
             dist.all_to_all_single(recv, send)
+            self._mark(prof, 'all_to_all')
             h.ids = torch.empty(W * cap, **i64)
             h.ang = torch.empty(W * cap, dtype=torch.int16, device=self.device)
             check(lib.oa_merge_blocks(ptr(recv), W, cap, ptr(h.ids), ptr(h.ang),
                                       ptr(info), st))
+            self._mark(prof, 'merged')
             meta_all = torch.empty(W * meta.numel(), **i64)
             dist.all_gather_into_tensor(meta_all, meta)
+            self._mark(prof, 'all_gather')
+            h.prof = prof
             # the proposals of all ranks, [W][W - 1], for the next exchange
             if not persistent:
                 self._splitters = meta_all.view(W, -1)[:, 2 + n_cnt:].contiguous()
@@ -464,8 +471,31 @@ class Comm:
         h.keep = None
         return res
 
+    # -- optional profile of the exchange phases (OA_EXCHANGE_PROFILE=1) -------------
+    def _profile_events(self):
+        import os
+        if self.device.type != 'cuda' or os.environ.get('OA_EXCHANGE_PROFILE') != '1':
+            return None
+        return []
+
+    def _mark(self, prof, name):
+        if prof is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(self.stream)
+            prof.append((name, ev))
+
+    def _account(self, h):
+        prof = getattr(h, 'prof', None)
+        if not prof:
+            return
+        acc = self.__dict__.setdefault('phase_ms', {})
+        for (_, a), (name, b) in zip(prof[:-1], prof[1:]):
+            acc[name] = acc.get(name, 0.0) + a.elapsed_time(b)
+        acc['exchanges'] = acc.get('exchanges', 0) + 1
+
     def _finish_split(self, h):
         W = self.world
+        self._account(h)
         meta = h.h_meta.numpy().reshape(W, -1)
         info = meta[:, :2]
         sizes = info[:, 0]

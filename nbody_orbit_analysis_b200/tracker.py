@@ -208,6 +208,7 @@ class OrbitTracker:
         return dst
 
     HOST_RING = 4   # result buffers stay valid until two further submits
+    SMALL_COPY = 256 << 10   # read-backs up to this size are written by a kernel
 
     def _hbuf(self, name, n, dtype, step=None, reserve=0):
         """Persistent PINNED host buffer ``name`` of a ring slot (cudaHostAlloc
@@ -240,11 +241,16 @@ class OrbitTracker:
         else:
             h = self._hbuf(name, n, t.dtype, step, reserve)
         if n:
-            # (cudaMemcpyAsync on the copy stream through the C ABI: no stream
-            # switch of the host framework per copy)
-            check(lib.oa_copy_async(h.data_ptr(), t.data_ptr(),
-                                    n * _ITEMSIZE[t.dtype],
-                                    self._copy_st if via is None else via))
+            # (through the C ABI on the copy stream: no stream switch of the host
+            # framework per copy.  Small read-backs -- what collect() and the
+            # exchange wait for -- are written by a kernel: a DMA copy would
+            # queue behind the event lists in flight to the host)
+            nbytes = n * _ITEMSIZE[t.dtype]
+            small = nbytes <= self.SMALL_COPY and nbytes % 4 == 0 and \
+                t.data_ptr() % 4 == 0 and via is None
+            fn = lib.oa_copy_small if small else lib.oa_copy_async
+            check(fn(h.data_ptr(), t.data_ptr(), nbytes,
+                     self._copy_st if via is None else via))
         return h
 
     def to_host(self, *tensors, stream=None):

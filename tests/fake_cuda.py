@@ -75,6 +75,8 @@ class FakeLib:
         C.memmove(dst, src, int(nbytes))
         return 0
 
+    oa_copy_small = oa_copy_async
+
     # ---- no-op kernels of the hash-table branch --------------------------------
     def oa_table_clear(self, *a):
         self.calls.append('oa_table_clear')

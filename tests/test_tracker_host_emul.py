@@ -259,7 +259,7 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1):
         fh.write(buf.getvalue())
 
 
-@pytest.mark.parametrize('world,batch', [(2, 1), (3, 1), (2, 3)])
+@pytest.mark.parametrize('world,batch', [(2, 1), (2, 3)])
 def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch,
                                        capsys):
     """The multi-GPU arm of ``bench.py`` with `world` ranks on the CPU: sharded
