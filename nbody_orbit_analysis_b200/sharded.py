@@ -488,6 +488,10 @@ class Comm:
         prof = getattr(h, 'prof', None)
         if not prof:
             return
+        seen = self.__dict__.get('_profiled', 0)
+        self._profiled = seen + 1
+        if seen < 3:                  # communicator set-up, first allocations
+            return
         acc = self.__dict__.setdefault('phase_ms', {})
         for (_, a), (name, b) in zip(prof[:-1], prof[1:]):
             acc[name] = acc.get(name, 0.0) + a.elapsed_time(b)
