@@ -457,11 +457,16 @@ def run_b200(args):
         pos, rad, bulk = timed('catalogue', catalogue, t)
         if host is None:
             dev, n, offsets = snaps[t]
-            return timed('submit', trk.submit_device,
-                         dev, n, np.float32, np.int64, offsets, exists, pos, bulk,
-                         0.0, box_size=gen.host.box, gpos=dev.get('gpos'))
-        return timed('submit', trk.submit, host[t], exists, pos, bulk, 0.0,
-                     gpos=host[t].get('_gpos'))
+            pending = timed('submit', trk.submit_device,
+                            dev, n, np.float32, np.int64, offsets, exists, pos,
+                            bulk, 0.0, box_size=gen.host.box, gpos=dev.get('gpos'))
+        else:
+            pending = timed('submit', trk.submit, host[t], exists, pos, bulk, 0.0,
+                            gpos=host[t].get('_gpos'))
+        if comm is not None:
+            # the exchange's pack kernels right behind the snapshot's selection
+            timed('prepack', comm.prepack, trk, pending)
+        return pending
 
     exchange = {'inflight': None}
 

@@ -292,6 +292,54 @@ class Comm:
                 "finish_merge() no later than one snapshot after start_merge() "
                 "or raise Comm.HEADROOM")
 
+    def prepack(self, tracker, p):
+        """Call right after ``tracker.submit*()`` returned the pending snapshot
+        ``p``: enqueue the quantile and pack kernels of its events on the MAIN
+        stream, directly behind its selection kernels -- i.e. before the next
+        snapshot's persistent tracking kernel occupies the SMs (launched later,
+        from ``start_merge`` on the exchange stream, the same two kernels took
+        0.76 ms instead of 0.13 at 8 GPUs, profiles/r02_scaling.md).  The
+        splitters are those of the last FINISHED exchange (complete on the host,
+        so no stream has to wait for them).  ``start_merge`` then only runs the
+        collectives and the merge.  No-op whenever the plain path applies (first
+        exchanges, batches, no previous snapshot).  OPT-IN (OA_EXCHANGE_PREPACK=1):
+        on 2 GPUs it is correct (oracle parity on every path) but slower (1.08 vs
+        0.91 ms per step: the pack kernels lengthen the main stream's critical
+        path and the contention moves to the merge kernel, 0.09 -> 0.41 ms); it
+        has not been measured on 8 GPUs."""
+        import os
+        if os.environ.get('OA_EXCHANGE_PREPACK', '0') != '1':
+            return
+        prev = getattr(p, 'prev', None)
+        if self.batch_size > 1 or self._cap is None or prev is None or \
+                getattr(prev, 'gpos', None) is None or p.d_small is None or \
+                getattr(self, '_splitters_ready', None) is None or \
+                not tracker.events_on_device:
+            return
+        W = self.world
+        n_seg = p.n_m
+        cap = self._block_cap()
+        st = tracker._stream()
+        i64 = dict(dtype=torch.int64, device=self.device)
+        n_prop, n_cnt = max(W - 1, 1), max(n_seg, 1)
+        meta = torch.empty(2 + n_cnt + n_prop, **i64)
+        counts, prop = meta[2:2 + n_cnt], meta[2 + n_cnt:]
+        check(lib.oa_split_quantiles(ptr(prev.gpos), ptr(p.sel), ptr(p.d_small),
+                                     n_seg, W, ptr(prop), st))
+        prop_all = self._splitters_ready
+        send = torch.empty(W * lib.oa_exchange_bytes(0, cap), dtype=torch.uint8,
+                           device=self.device)
+        bnd = torch.empty(W + 1, **i64)
+        check(lib.oa_pack_split(
+            ptr(prev.gpos), ptr(p.sel), ptr(p.d_ids), ptr(p.d_ang),
+            ptr(p.d_small), n_seg, ptr(prop_all), W, cap, ptr(bnd), ptr(send),
+            ptr(counts), st))
+        packed = self._event()
+        packed.record(tracker._main())
+        tracker.launches += 2
+        p.prepack = dict(meta=meta, send=send, bnd=bnd, prop_all=prop_all, cap=cap,
+                         n_seg=n_seg, packed=packed)
+
     def _launch_split(self, tracker, res, cap, to_host, splitters=None):
         """``splitters``: the all-gathered quantile proposals to split by (a
         repeat uses those of the attempt it repeats).  Default: the proposals
@@ -306,7 +354,13 @@ class Comm:
         h.res, h.cap, h.n_seg, h.to_host, h.tracker = res, cap, n_seg, to_host, tracker
         h.split = True
         h.step0 = getattr(res, 'step', tracker._step)
-        if res.compacted is not None:
+        pre = getattr(res, 'prepack', None) if splitters is None else None
+        if pre is not None and (pre['cap'] != cap or pre['n_seg'] != n_seg):
+            pre = None
+        if pre is not None:
+            res.prepack = None                 # a repeat packs again, the plain way
+            self.stream.wait_event(pre['packed'])
+        elif res.compacted is not None:
             self.stream.wait_event(res.compacted)
         prof = self._profile_events()
         with self._on_stream():
@@ -319,14 +373,18 @@ class Comm:
             # rank's quantile proposals]: one buffer, so that ONE all-gather
             # carries the sizes, the counts and the next exchange's splitters
             n_cnt = max(n_seg, 1)
-            meta = torch.empty(2 + n_cnt + n_prop, **i64)
+            meta = pre['meta'] if pre is not None else \
+                torch.empty(2 + n_cnt + n_prop, **i64)
             info, counts, prop = meta[:2], meta[2:2 + n_cnt], meta[2 + n_cnt:]
-            check(lib.oa_split_quantiles(ptr(gen.gpos), ptr(res.d_sel),
-                                         ptr(res.d_small), n_seg, W, ptr(prop),
-                                         st))
+            if pre is None:
+                check(lib.oa_split_quantiles(ptr(gen.gpos), ptr(res.d_sel),
+                                             ptr(res.d_small), n_seg, W,
+                                             ptr(prop), st))
             persistent = getattr(res, 'persistent', False)
             prop_all = splitters if splitters is not None else (
                 None if persistent else self._splitters)
+            if pre is not None:
+                prop_all = pre['prop_all']
             if prop_all is None:
                 # first exchange: nothing to lag behind.  A batch always splits by
                 # its own quantiles: batches differ in length (the last one, the
@@ -336,20 +394,23 @@ class Comm:
                 dist.all_gather_into_tensor(prop_all, prop.contiguous())
             h.splitters = prop_all
             blk = lib.oa_exchange_bytes(0, cap)
-            send = torch.empty(W * blk, **u8)
             recv = torch.empty(W * blk, **u8)
-            bnd = torch.empty(W + 1, **i64)
-            check(lib.oa_pack_split(
-                ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
-                ptr(res.d_ang_buf), ptr(res.d_small), n_seg, ptr(prop_all), W,
-                cap, ptr(bnd), ptr(send), ptr(counts), st))
+            if pre is not None:
+                send, bnd = pre['send'], pre['bnd']
+            else:
+                send = torch.empty(W * blk, **u8)
+                bnd = torch.empty(W + 1, **i64)
+                check(lib.oa_pack_split(
+                    ptr(gen.gpos), ptr(res.d_sel), ptr(res.d_ids_buf),
+                    ptr(res.d_ang_buf), ptr(res.d_small), n_seg, ptr(prop_all), W,
+                    cap, ptr(bnd), ptr(send), ptr(counts), st))
             # The tracker's ring buffers (gpos, selection, event lists) have now
             # been read: the NEXT snapshot may be submitted once the pack kernel
             # is done.  (Round 1 recorded this event after the collectives, so
             # every submit waited for the all-to-all of the previous snapshot --
             # i.e. for the slowest rank -- before its tracking kernel could start.)
             # A batch reads staging buffers of its own: nothing to wait for.
-            if not persistent:
+            if not persistent and pre is None:
                 packed = self._event()
                 packed.record(self.stream)
                 tracker.wait_before_submit = packed
@@ -368,6 +429,7 @@ class Comm:
             # the proposals of all ranks, [W][W - 1], for the next exchange
             if not persistent:
                 self._splitters = meta_all.view(W, -1)[:, 2 + n_cnt:].contiguous()
+                h.next_splitters = self._splitters
             tracker.launches += 5
             # (meta_all is read by the copy stream below: it must stay allocated
             # until the handle is finished, or the caching allocator hands its
@@ -515,6 +577,8 @@ class Comm:
                 h.tracker, h.res, self._block_cap(), h.to_host,
                 splitters=h.splitters))
         self._repeats = 0
+        if getattr(h, 'next_splitters', None) is not None:
+            self._splitters_ready = h.next_splitters   # complete: safe on any stream
         batch = getattr(h.res, 'persistent', False)
         self._cap = max(self._cap, self._round_cap(
             int(sizes.max()), self.BATCH_HEADROOM if batch else None))

@@ -53,7 +53,7 @@ class StepResult:
     __slots__ = ('host_ready', 'host_slice', 'step', 'n', 'apsis_ids', 'apsis_angles', 'apsis_offsets', 'hinds',
                  'bulk_velocities', 'angles', 'diag', 'n_events',
                  'apsis_prev_index', 'prev_gen', 'd_ids', 'd_ang', 'compacted',
-                 'd_sel', 'd_ids_buf', 'd_ang_buf', 'd_small')
+                 'd_sel', 'd_ids_buf', 'd_ang_buf', 'd_small', 'prepack')
 
 
 class Pending:
@@ -796,6 +796,7 @@ class OrbitTracker:
         res.host_ready = res.host_slice = None
         res.compacted = p.compacted
         res.prev_gen = p.prev
+        res.prepack = getattr(p, 'prepack', None)
         p.small_done.synchronize()
         if p.h_overflow is not None and int(p.h_overflow[0]) != 0:
             raise _lib.OrbitB200Error(
