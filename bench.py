@@ -749,6 +749,8 @@ def run_b200(args):
         }
         if dev_run.get('per_rank'):
             line['per_rank'] = dev_run['per_rank']
+        if comm is not None and getattr(comm, 'n_prepacked', 0):
+            line['exchange_prepacked'] = comm.n_prepacked
         if comm is not None and getattr(comm, 'phase_ms', None):
             n_x = max(comm.phase_ms.get('exchanges', 1), 1)
             line['exchange_phases_ms'] = {

@@ -339,6 +339,7 @@ class Comm:
         tracker.launches += 2
         p.prepack = dict(meta=meta, send=send, bnd=bnd, prop_all=prop_all, cap=cap,
                          n_seg=n_seg, packed=packed)
+        self.n_prepacked = getattr(self, 'n_prepacked', 0) + 1
 
     def _launch_split(self, tracker, res, cap, to_host, splitters=None):
         """``splitters``: the all-gathered quantile proposals to split by (a

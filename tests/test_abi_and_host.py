@@ -239,3 +239,50 @@ def test_axis0_reduction_is_sequential():
                 acc = acc + row
             assert np.array_equal(np.add.reduce(v, axis=0), acc)
             assert np.array_equal(np.mean(v, axis=0), acc / dt(n))
+
+
+def test_pj2_plan_invariants():
+    """``oa_pj2_plan_host`` (host side of the second partitioned join): partition
+    counts are powers of two that never shrink for a halo, capacities cover the
+    mean fill with the Poisson head room, record slots / fill entries are laid
+    out back to back, one JOIN item per current partition of a halo that has a
+    previous block, and the ticket ranges hold every tile exactly once."""
+    from nbody_orbit_analysis_b200 import pj2, _lib
+    plan = pj2.Planner(_lib.lib)
+    rng = np.random.default_rng(2)
+    n_h = 300
+    lens = rng.integers(0, 40000, n_h)
+    lens[[3, 17]] = 0
+    lens[5] = 900000
+    prev = [np.zeros(n_h, dtype=np.uint32) for _ in range(4)]
+    for step in range(4):
+        off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        p = plan(off, *prev, group_particles=1 << 17)
+        P, cap = p.P.astype(np.int64), p.cap.astype(np.int64)
+        assert ((P & (P - 1)) == 0).all() and (P >= 1).all()
+        assert (P >= prev[0]).all()                               # never shrinks
+        mean = -(-lens // P)
+        assert (mean <= pj2.TARGET).all() or (P[mean > pj2.TARGET] ==
+                                              prev[0][mean > pj2.TARGET]).all()
+        assert (cap >= np.minimum(mean + 16, pj2.CAP)).all() and (cap <= pj2.CAP).all()
+        assert np.array_equal(p.pb, np.concatenate(([0], np.cumsum(P)))[:-1])
+        assert np.array_equal(p.base, np.concatenate(([0], np.cumsum(P * cap)))[:-1])
+        assert p.n_entries == P.sum() and p.n_slots == (P * cap).sum()
+        rows = p.rows
+        has_prev = prev[0] > 0
+        joins = np.where(has_prev & (lens > 0), P, 0)
+        assert np.array_equal(rows['join_first'],
+                              np.concatenate(([0], np.cumsum(joins))))
+        assert (rows['P_cur'][:n_h][has_prev] ==
+                prev[0][has_prev].astype(np.int64) << rows['shift'][:n_h][has_prev]).all()
+        # groups partition the regions; ticket ranges: tiles once, joins once
+        gf, go, rs = p.group_first, p.group_off, p.range_start
+        assert gf[0] == 0 and gf[-1] == n_h and (np.diff(gf.astype(np.int64)) > 0).all()
+        assert np.array_equal(go, off[gf])
+        n_tiles = -(-int(off[-1]) // pj2.TILE)
+        tiles = sum(int(rs[2 * s + 1]) - int(rs[2 * s]) for s in range(p.n_groups))
+        assert tiles == n_tiles
+        assert p.total == n_tiles + int(joins.sum())
+        assert p.n_ranges == 2 * (p.n_groups + pj2.LAG) and rs[-1] == p.total
+        prev = [p.P.copy(), p.cap.copy(), p.base.copy(), p.pb.copy()]
+        lens = (lens * rng.uniform(0.7, 1.6, n_h)).astype(np.int64)

@@ -352,7 +352,7 @@ def test_previous_partition_larger_than_the_table(emul):
 
 
 def test_many_ctas_and_one_cta(emul):
-    sim = SynthSim(40000, 7, 4, dtype=np.float32, catalogue_dtype=np.float32)
+    sim = SynthSim(20000, 7, 4, dtype=np.float32, catalogue_dtype=np.float32)
     run_case(emul, sim, targets=[500], n_ctas=1)
     run_case(emul, sim, targets=[500], n_ctas=6, lag=1 << 10)
 

@@ -221,7 +221,7 @@ class ShardedHostSynth(HostSynth):
         return dev, n, np.append(loc['region_offsets'], n).astype(np.int64)
 
 
-def _bench_rank(rank, world, port, emul_path, out_dir, batch=1):
+def _bench_rank(rank, world, port, emul_path, out_dir, batch=1, prepack=False):
     import argparse
     import contextlib
     import io
@@ -235,7 +235,8 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1):
                       RANK=str(rank), LOCAL_RANK=str(rank),
                       WORLD_SIZE=str(world), OA_TRACK_IMPL='pjoin',
                       OA_BENCH_CLOCK_PERIOD='0.05', OA_FAKE_CTAS='1',
-                      OA_EXCHANGE_BATCH=str(batch))
+                      OA_EXCHANGE_BATCH=str(batch),
+                      OA_EXCHANGE_PREPACK='1' if prepack else '0')
     import bench
     import exchange_emul
     import fake_cuda as fc
@@ -259,9 +260,10 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1):
         fh.write(buf.getvalue())
 
 
-@pytest.mark.parametrize('world,batch', [(2, 1), (2, 3)])
-def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch,
-                                       capsys):
+@pytest.mark.parametrize('world,batch,prepack', [(2, 1, False), (2, 3, False),
+                                                 (2, 1, True)])
+def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, tmp_path,
+                                       monkeypatch, capsys):
     """The multi-GPU arm of ``bench.py`` with `world` ranks on the CPU: sharded
     snapshots, catalogue broadcast one snapshot ahead, asynchronous all-to-all
     exchange (numpy restatements of its kernels, gloo) and per-rank slices --
@@ -271,7 +273,7 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch
     import torch.multiprocessing as mp
     from test_sharded_gloo import _free_port
     mp.spawn(_bench_rank, args=(world, _free_port(), emul._name, str(tmp_path),
-                                batch), nprocs=world, join=True)
+                                batch, prepack), nprocs=world, join=True)
     lines = [ln for ln in open(str(tmp_path / 'out_0')).read().splitlines()
              if ln.startswith('{')]
     multi = json.loads(lines[-1])
@@ -294,6 +296,9 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, tmp_path, monkeypatch
     for r in range(1, world):          # only rank 0 prints
         assert '{' not in open(str(tmp_path / ('out_%d' % r))).read()
 
+    if prepack:
+        # (OA_EXCHANGE_PREPACK=1: the pack kernels ran at submit time)
+        assert multi['exchange_prepacked'] >= 4
     if world != 2:
         return
     # one rank, whole universe
