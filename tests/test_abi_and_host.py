@@ -142,11 +142,14 @@ def test_region_rows_host_equals_numpy_assembly():
     from nbody_orbit_analysis_b200 import _lib
     rng = np.random.default_rng(9)
     lib = _lib.lib
-    for trial in range(60):
+    for trial in range(62):
         n_h = int(rng.integers(0, 50))
         n_p = int(rng.integers(0, 50))
-        ids_cur = np.sort(rng.choice(200, n_h, replace=False)).astype(np.int64)
-        ids_prev = np.sort(rng.choice(200, n_p, replace=False)).astype(np.int64)
+        pool = 200
+        if trial >= 60:               # large catalogues: the threaded row fill
+            n_h, n_p, pool = 40000 + trial, 39000, 60000
+        ids_cur = np.sort(rng.choice(pool, n_h, replace=False)).astype(np.int64)
+        ids_prev = np.sort(rng.choice(pool, n_p, replace=False)).astype(np.int64)
         offsets = np.concatenate(([0], np.cumsum(rng.integers(0, 5000, n_h)))
                                  ).astype(np.int64)
         p_off = np.concatenate(([0], np.cumsum(rng.integers(0, 5000, n_p)))
