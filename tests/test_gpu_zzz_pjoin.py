@@ -86,3 +86,51 @@ def test_pjoin_equals_hash_kernel_at_scale(n, halos, impl):
         n_events += a.n_events
     torch.cuda.synchronize()
     assert n_events > 0
+
+
+def test_full_size_properties_and_agreement():
+    """BASELINE config[1] at FULL size (256^3 particles, 1000 halos: the bench
+    workload), where the oracle does not reach: size-independent properties of
+    the result, and agreement of the two independent implementations.
+
+    * the event positions are strictly ascending over the previous snapshot
+      (the reference's event order, ``track_orbits.py:315-316``);
+    * every event ID is the ID of the previous-snapshot particle at that
+      position (membership, ``:316``), offsets are non-decreasing and end at
+      the event count (``:214-215``);
+    * the hash kernel and the second partitioned join -- different kernels,
+      different data layouts -- give identical IDs, offsets and float16 angles;
+    * a second run gives the same bits."""
+    import torch
+    from nbody_orbit_analysis_b200.synth import DeviceSynth
+    from nbody_orbit_analysis_b200.tracker import OrbitTracker
+    n, halos = 256 ** 3, 1000
+    gen = DeviceSynth(n, halos)
+    exists = np.arange(halos)
+
+    def run(impl):
+        trk = OrbitTracker(impl=impl)
+        out, prev_ids = [], None
+        for t in range(4):
+            dev, m, offsets = gen.snapshot(t)
+            pos, rad, bulk = gen.regions(t)
+            res = trk.step_device(dev, m, np.float32, np.int64, offsets, exists,
+                                  pos, bulk, 0.0, box_size=gen.host.box)
+            if t > 0:
+                sel = res.apsis_prev_index
+                assert res.n_events == sel.numel() > 100000
+                assert bool(torch.all(sel[1:] > sel[:-1]))
+                assert torch.equal(res.d_ids, prev_ids[sel])
+                off = res.apsis_offsets
+                assert off[0] == 0 and off[-1] == res.n_events
+                assert (np.diff(off) >= 0).all() and len(off) == halos + 1
+                out.append((res.apsis_ids.copy(), off.copy(),
+                            res.apsis_angles.view(np.int16).copy()))
+            prev_ids = dev['ids']
+        torch.cuda.synchronize()
+        return out
+    a, b, a2 = run('hash'), run('pj2'), run('hash')
+    for (ia, oa, ga), (ib, ob, gb), (ic, oc, gc) in zip(a, b, a2):
+        assert np.array_equal(ia, ib) and np.array_equal(oa, ob)
+        assert np.array_equal(ga, gb)
+        assert np.array_equal(ia, ic) and np.array_equal(ga, gc)
