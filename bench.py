@@ -6,12 +6,17 @@
 
 metric  : particle-snapshots/sec = sum over timed snapshots of the particles in
           all region blocks / time of the tracking path (halo frame + ID match
-          + apsis detection + angle update + ordered event compaction + D2H of
-          the event lists).
+          + apsis detection + angle update + ordered event compaction; N > 1:
+          + exchange and merge of the event lists in the reference's order).
 step    : one snapshot.  Workload at N=1: BASELINE config[1], 256^3 particles,
           1000 halos, pericentric; per-GPU work is fixed as N grows (weak
           scaling, particles sharded by ID).
-value   : inputs resident in HBM (generated there by csrc/oa_synth.cu).
+value   : inputs resident in HBM (generated there by csrc/oa_synth.cu), results
+          (ordered event lists) left in HBM; only the event count and the
+          region offsets are read back.  No bulk host<->device copy.
+value_results_to_host : the same pass with the event lists also copied to
+          pinned host memory every snapshot (what `value` meant in round 1; at
+          8 GPUs this is bound by the box's host links, profiles/r02_scaling.md).
 e2e     : same steps through OrbitTracker.step() with HOST (pinned) snapshot
           arrays: H2D of ids/pos/vel and D2H of the events inside the timing.
 roofline: fused tracking kernel, algorithmic bytes = 72 B per particle-snapshot
@@ -373,6 +378,10 @@ def workload_config(args):
         'mode': args.mode,
         'l2': 'inputs larger than L2 (>=500 MB per step, distinct every step)',
         'sharding': 'particle ID mod n_gpus',
+        'results': 'GPU arm, `value`: the ordered (N > 1: merged) event lists '
+                   'stay in HBM, the host reads the event count and '
+                   'region_offsets; `value_results_to_host` and `e2e` also copy '
+                   'the lists to pinned host memory every snapshot',
     }
 
 
@@ -469,6 +478,7 @@ def run_b200(args):
         return pending
 
     exchange = {'inflight': None}
+    run_cfg = {'results': 'host'}
 
     def collect_step(trk, pending):
         """Results of one snapshot.  Multi-GPU: its event exchange is started
@@ -493,8 +503,7 @@ def run_b200(args):
             # every rank hands its 1/world share of the merged lists to the
             # host (parallel write of the result datasets)
             h = timed('start_merge', comm.start_merge, trk, res,
-                      to_host=False if os.environ.get('OA_BENCH_TO_HOST') == '0'
-                      else 'slice')
+                      to_host='slice' if run_cfg['results'] == 'host' else False)
             prev, exchange['inflight'] = exchange['inflight'], h
             if prev is not None:
                 done.append(timed('finish_merge', comm.finish_merge, prev))
@@ -513,14 +522,22 @@ def run_b200(args):
         h, exchange['inflight'] = exchange['inflight'], None
         return [comm.finish_merge(h)] if h is not None else []
 
-    def timed_run(host=None):
+    def timed_run(host=None, results='host'):
         """W+1 untimed snapshots, then K timed ones.  Up to `depth` snapshots
         are submitted ahead of the one whose results are being collected
         (software pipeline: host-side collection, H2D and D2H overlap the
-        kernels of the following snapshots)."""
+        kernels of the following snapshots).
+
+        results='hbm' : a snapshot's (merged, ordered) event lists stay in HBM;
+                        the host reads the event count and `region_offsets`
+                        (device-resident pass: no bulk host<->device copy in it);
+        results='host': they are also copied to pinned host memory every
+                        snapshot -- all of them at N = 1, every rank's 1/N slice
+                        of the merged lists at N > 1."""
+        run_cfg['results'] = results
         trk = OrbitTracker(mode=args.mode)
         flush_exchange.trk = trk
-        trk.events_on_device = comm is not None
+        trk.events_on_device = comm is not None or results == 'hbm'
         if comm is not None:       # room for the NCCL kernels of the exchange
             trk.sm_reserve = int(os.environ.get('OA_SM_RESERVE', '12'))
         # nvidia-smi is started before the warm-up: its NVML initialisation
@@ -618,8 +635,17 @@ def run_b200(args):
                 'kern_ms': kern_ms, 'kern_n': kern_n, 'last': last,
                 'pj_stats': list(pj_stats) if stats_on else None}
 
-    dev_run = timed_run()
+    # `value`: inputs AND results resident in HBM (the host reads counts and
+    # offsets only).  OA_BENCH_TO_HOST=1 restores the round-1 definition (event
+    # lists copied to the host inside the timed region); that pass is otherwise
+    # run right after and reported beside `value` as `value_results_to_host`.
+    results_in = 'host' if os.environ.get('OA_BENCH_TO_HOST') == '1' else 'hbm'
+    dev_run = timed_run(results=results_in)
     value = dev_run['particles'] / (dev_run['ms'] * 1e-3)
+    to_host_run = None
+    if results_in == 'hbm' and os.environ.get('OA_BENCH_TO_HOST') != '0' and \
+            os.environ.get('OA_BENCH_NO_EXCHANGE') != '1':
+        to_host_run = timed_run(results='host')
 
     # ---- end to end: host (pinned) snapshots ---------------------------------
     e2e = None
@@ -664,7 +690,7 @@ def run_b200(args):
             h['redshift'] = 0.0
             host.append(h)
         torch.cuda.synchronize()
-        e2e_run = timed_run(host)
+        e2e_run = timed_run(host, results='host')
         n_per_step = e2e_run['particles'] / K / world
         ev_per_step = e2e_run['events'] / K
         e2e = {'value': e2e_run['particles'] / (e2e_run['ms'] * 1e-3),
@@ -681,6 +707,24 @@ def run_b200(args):
         # same data, two passes: the global event totals must be identical
         e2e['events_equal_device_run'] = bool(
             e2e_run['events'] == dev_run['events'])
+    host_results = None
+    if to_host_run is not None:
+        ev_per_step = to_host_run['events'] / K
+        host_results = {
+            'value': to_host_run['particles'] / (to_host_run['ms'] * 1e-3),
+            'unit': 'particle-snapshots/s',
+            'ms_per_step': to_host_run['ms'] / K,
+            'd2h_bytes_per_step_per_gpu': int(ev_per_step * 10 / world
+                                              + args.halos * 8 + 8),
+            'events_equal_device_run': bool(
+                to_host_run['events'] == dev_run['events']),
+            'kernel_ms': float(np.mean(to_host_run['kern_ms'])),
+            'host_phases_ms_per_step': to_host_run['host_phases_ms_per_step'],
+            'what': 'the same device-resident pass with the event lists also '
+                    'copied to pinned host memory every snapshot (%s); the '
+                    'round-1 definition of `value`' % (
+                        'all of them' if world == 1 else
+                        "every rank's 1/%d slice of the merged lists" % world)}
 
     # ---- end to end through the drop-in ENTRY POINT --------------------------------
     # track_orbits() itself: pageable numpy arrays from the loader callback (the
@@ -779,6 +823,8 @@ def run_b200(args):
                 'items': {n: int(st[8 + i]) for i, n in enumerate(names)},
                 'cycles_per_item': {n: round(st[i] / max(st[8 + i], 1), 1)
                                     for i, n in enumerate(names)}}
+        if host_results is not None:
+            line['value_results_to_host'] = host_results
         if e2e is not None:
             line['e2e'] = e2e
         elif not args.no_e2e:
@@ -792,6 +838,8 @@ def run_b200(args):
         bad = (multi_parity is not None
                and multi_parity['parity_vs_oracle'] != 'ok') or (
             e2e is not None and not e2e['events_equal_device_run']) or (
+            host_results is not None
+            and not host_results['events_equal_device_run']) or (
             cpu is not None and cpu['parity_vs_gpu_on_sample'] != 'ok')
         line['parity'] = 'MISMATCH' if bad else 'ok'
         print(json.dumps(line))

@@ -155,6 +155,12 @@ def test_bench_end_to_end_on_fake_cuda(emul, pjoin_env, monkeypatch, capsys):
     assert line['events_per_step'] > 0
     assert line['e2e']['value'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0
     assert line['e2e']['events_per_step'] == line['events_per_step']
+    # `value`: results left in HBM; the pass that also copies them to the host
+    # is reported beside it and must see the same events
+    assert 'HBM' in line['config']['results']
+    vh = line['value_results_to_host']
+    assert vh['value'] > 0 and vh['events_equal_device_run'] is True
+    assert line['parity'] == 'ok'
     # the same data through the drop-in entry point (pageable arrays, file write)
     ep = line['e2e_entry_point']
     assert ep['value'] > 0 and ep['snapshots'] == 3 and ep['file_bytes_per_step'] > 0
@@ -280,6 +286,8 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, tmp_path,
     assert multi['n_gpus'] == world and multi['value'] > 0
     assert multi['events_per_step'] > 0
     assert multi['parity'] == 'ok'
+    vh = multi['value_results_to_host']
+    assert vh['value'] > 0 and vh['events_equal_device_run'] is True
     if batch == 1:
         # a sample of whole halos, put back together from all ranks' shards,
         # through both exchange paths against the oracle on rank 0
