@@ -86,6 +86,18 @@ int oa_copy_async(void* dst, const void* src, size_t bytes, void* stream);
  * engine.  `dst` / `src` / `bytes` multiples of 4. */
 int oa_copy_small(void* dst, const void* src, size_t bytes, void* stream);
 
+/* Host-to-host copy by up to `n_threads` threads (HOST pointers, no CUDA call):
+ * the staging copy of a loader's PAGEABLE arrays into the pinned ingest ring.
+ * The reference hands the loader's arrays to numpy as they are
+ * (track_orbits.py:130-131, 234-237); a GPU path has to stage them through
+ * pinned memory before the DMA engine can take them, and one core's memcpy
+ * (~10 GB/s) is slower than the host-to-device link (~52 GB/s).  Each thread
+ * copies one contiguous, 4096-byte aligned part with the C library's memcpy
+ * (non-temporal stores for large sizes: no read-for-ownership of the
+ * destination).  n_threads <= 1, or fewer than 1 MiB per thread: plain memcpy
+ * on the calling thread.  Blocks until the copy is complete. */
+int oa_host_copy(void* dst, const void* src, size_t bytes, int n_threads);
+
 /* The region table on the HOST (host pointers, no CUDA call): what the Python
  * driver otherwise assembles with ~20 numpy calls per snapshot.  For region j:
  * centre / bulk from the catalogue arrays (float32 or float64, `bulk` may be NULL

@@ -184,6 +184,7 @@ _pjoin.configure(lib)
 _sig('oa_pjoin_stats', C.c_int, _vp, C.c_int)
 _sig('oa_copy_async', C.c_int, _vp, _vp, _sz, _vp)
 _sig('oa_copy_small', C.c_int, _vp, _vp, _sz, _vp)
+_sig('oa_host_copy', C.c_int, _vp, _vp, _sz, C.c_int)
 _sig('oa_pairwise_sum_host', C.c_int, _vp, C.c_int, _i64, C.POINTER(C.c_double))
 _sig('oa_region_pairs', C.c_int, _vp, C.c_int, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp,
      _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp)
@@ -227,7 +228,7 @@ EXPORTS = [
     'oa_pjoin_stats', 'oa_pj2_workspace_bytes', 'oa_pj2_args_size',
     'oa_pj2_plan_host', 'oa_pj2_step', 'oa_pj2_stats', 'oa_pj2_config',
     'oa_copy_async', 'oa_merge_find', 'oa_merge_place', 'oa_region_pairs',
-    'oa_gather_by_key', 'oa_pairwise_sum_host', 'oa_copy_small',
+    'oa_gather_by_key', 'oa_pairwise_sum_host', 'oa_copy_small', 'oa_host_copy',
 ]
 
 

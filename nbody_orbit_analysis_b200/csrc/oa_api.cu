@@ -73,6 +73,40 @@ extern "C" size_t oa_track_args_size(void) { return sizeof(oa_track_args); }
 extern "C" size_t oa_synth_params_size(void) { return sizeof(oa_synth_params); }
 
 // ---- host-side assembly of the region table (see include/orbit_b200.h) -------------
+extern "C" int oa_host_copy(void* dst, const void* src, size_t bytes, int n_threads) {
+    OA_REQUIRE(bytes == 0 || (dst && src), "oa_host_copy: null pointer");
+    const size_t min_part = (size_t)1 << 20;
+    size_t parts = n_threads > 1 ? (size_t)n_threads : 1;
+    if (parts > 64) parts = 64;
+    if (parts > bytes / min_part) parts = bytes / min_part;
+    if (parts <= 1) {
+        if (bytes) memcpy(dst, src, bytes);
+        return OA_OK;
+    }
+    // part boundaries on 4 KiB multiples of the byte offset (the last part takes
+    // the remainder)
+    const size_t step = ((bytes / parts) + 4095) & ~(size_t)4095;
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    std::vector<std::thread> pool;
+    try {
+        for (size_t t = 1; t < parts; ++t) {
+            const size_t lo = t * step;
+            if (lo >= bytes) break;
+            const size_t hi = (t + 1 == parts || lo + step > bytes) ? bytes : lo + step;
+            pool.emplace_back([=] { memcpy(d + lo, s + lo, hi - lo); });
+        }
+    } catch (...) {
+        // (thread creation failed: the parts not handed out are copied below)
+        for (auto& th : pool) th.join();
+        memcpy(dst, src, bytes);
+        return OA_OK;
+    }
+    memcpy(d, s, step < bytes ? step : bytes);
+    for (auto& th : pool) th.join();
+    return OA_OK;
+}
+
 extern "C" int oa_region_rows_host(int n_regions, const int64_t* offsets,
                                    const void* centres, int centre_dtype,
                                    const void* bulk, int bulk_dtype,

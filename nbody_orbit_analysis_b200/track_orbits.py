@@ -125,13 +125,22 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
         prev_halo_exists = np.asarray(restored['halo_exists'])
         istart, started = -1, True
 
+    writer_thread = _Writer()
+
     def write(e, res):
-        """Result group of one snapshot (``track_orbits.py:366-397``)."""
+        """Result group of one snapshot (``track_orbits.py:366-397``): checked
+        here, written by the writer thread while the next snapshot is staged
+        (its arrays stay valid: they live in the tracker's pinned result ring,
+        which comes round three submits later, and at most one write is in
+        flight)."""
         if res.apsis_ids is None or len(res.hinds) == 0:
             # reference: np.concatenate([]) of an empty list (:216)
             raise ValueError("need at least one array to concatenate")
         if res.host_ready is not None:
             res.host_ready.synchronize()
+        writer_thread.submit(write_files, e, res)
+
+    def write_files(e, res):
         if checkpoint:
             with storage.File(ckpt_name, 'w') as hf:
                 hf.create_dataset('angles', data=e.angles)
@@ -183,87 +192,98 @@ def track_orbits(snapshot_numbers, main_branches, regions, load_snapshot_data,
             e0, h = merging.popleft()
             write(e0, comm.finish_merge(h))
 
-    for i, (halo_ids, snap_no) in enumerate(
-            zip(main_branches, snapshot_numbers)):
-        if verbose:
-            print('-' * 30, '\n')
-            print('Snapshot {}\n'.format('%03d' % snap_no))
-
-        halo_exists = np.flatnonzero(halo_ids != -1)
-        if len(halo_exists) == 0:
-            if not started:
-                istart = i + 1
-            continue
-        halo_ids_ = halo_ids[halo_exists]
-        if sharded_run:
-            # the catalogue comes from rank 0; the other ranks do
-            # not call `regions`
-            cat = regions(snap_no, halo_ids_) if writer else (None, None, None)
-            region_positions, region_radii, region_bulk_vels = \
-                _broadcast_catalogue(comm, cat, len(halo_ids_))
-            if region_bulk_vels is None:
-                raise ValueError(
-                    "sharded tracking needs catalogue bulk velocities "
-                    "(regions() returned None for them)")
-        else:
-            region_positions, region_radii, region_bulk_vels = regions(
-                snap_no, halo_ids_)
-        snapshot = load_snapshot_data(snap_no, region_positions, region_radii)
-        gpos = None
-        if sharded_run:
-            if '_gpos' in snapshot:
-                gpos = np.ascontiguousarray(snapshot['_gpos'], dtype=np.int64)
-            else:
-                snapshot, gpos = shard_snapshot(snapshot, rank, comm.world)
-            empty = _all_empty(comm, len(snapshot['coordinates']))
-        else:
-            empty = len(snapshot['coordinates']) == 0
-        if empty:
-            if not started:
-                istart = i + 1
-            continue
-        started = True
-
-        H = hubble_parameter(
-            snapshot['redshift'], snapshot['H0'], snapshot['Omega_m'],
-            snapshot['Omega_L'], snapshot.get('Omega_k', 0))
-
-        if not initialised:
-            if writer:
-                with storage.File(savefile, 'w') as hf:
-                    hf.attrs['mode'] = mode
-                    if 'box_size' in snapshot:
-                        hf.attrs['box_size'] = snapshot['box_size']
-            initialised = True
+    try:
+        for i, (halo_ids, snap_no) in enumerate(
+                zip(main_branches, snapshot_numbers)):
             if verbose:
-                print('Savefile initialized\n')
+                print('-' * 30, '\n')
+                print('Snapshot {}\n'.format('%03d' % snap_no))
 
-        if i <= istart:
-            tracker.prev = None       # first processed snapshot: no matching
-        e = _Entry()
-        e.snap_no, e.halo_ids, e.t0 = snap_no, halo_ids_, time.time()
-        e.positions, e.radii = np.asarray(region_positions), \
-            np.asarray(region_radii)
-        e.prev_halo_exists, e.has_events = prev_halo_exists, i > istart
-        e.p = tracker.submit(
-            snapshot, halo_exists, e.positions, region_bulk_vels, H,
-            want_angles=checkpoint, gpos=gpos)
-        if resume and i <= istart:
-            with storage.File(ckpt_name, 'r') as hf:
-                tracker.load_angles(hf['angles'][:])
-        e.state = tracker.save_state() if checkpoint == 'state' else None
-        pending.append(e)
-        # results of the PREVIOUS snapshot: collected and written while this one
-        # is on the GPU
-        while len(pending) > 1:
+            halo_exists = np.flatnonzero(halo_ids != -1)
+            if len(halo_exists) == 0:
+                if not started:
+                    istart = i + 1
+                continue
+            halo_ids_ = halo_ids[halo_exists]
+            if sharded_run:
+                # the catalogue comes from rank 0; the other ranks do
+                # not call `regions`
+                cat = regions(snap_no, halo_ids_) if writer else (None, None, None)
+                region_positions, region_radii, region_bulk_vels = \
+                    _broadcast_catalogue(comm, cat, len(halo_ids_))
+                if region_bulk_vels is None:
+                    raise ValueError(
+                        "sharded tracking needs catalogue bulk velocities "
+                        "(regions() returned None for them)")
+            else:
+                region_positions, region_radii, region_bulk_vels = regions(
+                    snap_no, halo_ids_)
+            snapshot = load_snapshot_data(snap_no, region_positions, region_radii)
+            gpos = None
+            if sharded_run:
+                if '_gpos' in snapshot:
+                    gpos = np.ascontiguousarray(snapshot['_gpos'], dtype=np.int64)
+                else:
+                    snapshot, gpos = shard_snapshot(snapshot, rank, comm.world)
+                empty = _all_empty(comm, len(snapshot['coordinates']))
+            else:
+                empty = len(snapshot['coordinates']) == 0
+            if empty:
+                if not started:
+                    istart = i + 1
+                continue
+            started = True
+
+            H = hubble_parameter(
+                snapshot['redshift'], snapshot['H0'], snapshot['Omega_m'],
+                snapshot['Omega_L'], snapshot.get('Omega_k', 0))
+
+            if not initialised:
+                if writer:
+                    with storage.File(savefile, 'w') as hf:
+                        hf.attrs['mode'] = mode
+                        if 'box_size' in snapshot:
+                            hf.attrs['box_size'] = snapshot['box_size']
+                initialised = True
+                if verbose:
+                    print('Savefile initialized\n')
+
+            if i <= istart:
+                tracker.prev = None       # first processed snapshot: no matching
+            e = _Entry()
+            e.snap_no, e.halo_ids, e.t0 = snap_no, halo_ids_, time.time()
+            # (copies: the group is written after the next callbacks have run,
+            # and a catalogue reader may reuse its arrays)
+            e.positions, e.radii = np.array(region_positions), \
+                np.array(region_radii)
+            if region_bulk_vels is not None:
+                region_bulk_vels = np.array(region_bulk_vels)
+            e.prev_halo_exists, e.has_events = prev_halo_exists, i > istart
+            e.p = tracker.submit(
+                snapshot, halo_exists, e.positions, region_bulk_vels, H,
+                want_angles=checkpoint, gpos=gpos)
+            if resume and i <= istart:
+                with storage.File(ckpt_name, 'r') as hf:
+                    tracker.load_angles(hf['angles'][:])
+            e.state = tracker.save_state() if checkpoint == 'state' else None
+            pending.append(e)
+            # results of the PREVIOUS snapshot: collected and written while this one
+            # is on the GPU
+            while len(pending) > 1:
+                finish(pending.popleft())
+            prev_halo_exists = halo_exists
+
+        while pending:
             finish(pending.popleft())
-        prev_halo_exists = halo_exists
-
-    while pending:
-        finish(pending.popleft())
-    while merging:
-        e0, h = merging.popleft()
-        write(e0, comm.finish_merge(h))
+        while merging:
+            e0, h = merging.popleft()
+            write(e0, comm.finish_merge(h))
+    except BaseException:
+        # (the result file ends at a whole group; the error that stopped the run
+        # is the one the caller sees)
+        writer_thread.wait(swallow=True)
+        raise
+    writer_thread.wait()
 
     if verbose:
         print('Finished {} detection for all snapshots in {} s\n'.format(
@@ -283,6 +303,40 @@ def _read_state(path, snapshot):
         if int(g.attrs['snapshot']) != int(snapshot):
             return None
         return {k: g[k][:] for k in g.keys()}
+
+
+class _Writer:
+    """Runs the result-file writes of the driver on a background thread, one at a
+    time and in order: ``submit`` first waits for the previous write.  The file
+    layer releases the GIL inside its large ``write`` calls, and the staging
+    copy / CUDA calls of the main thread release it too, so writing snapshot
+    s-1 overlaps staging snapshot s+1.  An exception raised by a write surfaces
+    at the next ``submit`` / ``wait`` on the calling thread."""
+
+    def __init__(self):
+        self._thread = None
+        self._error = None
+
+    def _run(self, fn, args):
+        try:
+            fn(*args)
+        except BaseException as exc:          # re-raised on the driver's thread
+            self._error = exc
+
+    def submit(self, fn, *args):
+        import threading
+        self.wait()
+        self._thread = threading.Thread(target=self._run, args=(fn, args),
+                                        name='orbit-b200-writer')
+        self._thread.start()
+
+    def wait(self, swallow=False):
+        thread, self._thread = self._thread, None
+        if thread is not None:
+            thread.join()
+        error, self._error = self._error, None
+        if error is not None and not swallow:
+            raise error
 
 
 class _Entry:

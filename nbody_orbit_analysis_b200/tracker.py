@@ -72,6 +72,48 @@ def _as_f(arr, name):
     return arr
 
 
+STAGE_MIN_BYTES = 8 << 20     # smaller staging copies stay on the calling thread
+_stage_threads = None
+
+
+def stage_threads():
+    """Threads of a staging copy (``oa_host_copy``): the cores this process may
+    run on, shared between the ranks of the node, at most 16 (a copy is bound by
+    memory bandwidth before that); ``OA_STAGE_THREADS`` overrides."""
+    global _stage_threads
+    if _stage_threads is None:
+        import os
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        try:
+            local = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+        except ValueError:
+            local = 1
+        n = max(1, min(16, cores // local))
+        try:
+            n = max(1, int(os.environ.get('OA_STAGE_THREADS', n)))
+        except ValueError:
+            pass
+        _stage_threads = n
+    return _stage_threads
+
+
+def _stage_copy(dst, src):
+    """Pageable host tensor -> pinned staging tensor (same dtype and length,
+    both contiguous).  Large copies are split over a few threads by the C
+    library (non-temporal memcpy, the GIL released for its duration): one
+    core's copy is several times slower than the host-to-device link."""
+    nbytes = src.numel() * src.element_size()
+    if nbytes < STAGE_MIN_BYTES or dst.dtype != src.dtype or \
+            dst.numel() != src.numel():
+        dst.copy_(src)
+        return
+    check(lib.oa_host_copy(dst.data_ptr(), src.data_ptr(), nbytes,
+                           stage_threads()))
+
+
 class OrbitTracker:
     """Per-snapshot GPU tracker.
 
@@ -198,7 +240,7 @@ class OrbitTracker:
                 buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
             else:
                 buf = self._hbuf('stage_' + name, t.numel(), t.dtype)
-            buf.copy_(t)
+            _stage_copy(buf, t)
             t = buf
         if name is None:
             return t.to(self.device, non_blocking=True)

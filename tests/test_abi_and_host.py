@@ -289,3 +289,72 @@ def test_pj2_plan_invariants():
         assert p.n_ranges == 2 * (p.n_groups + pj2.LAG) and rs[-1] == p.total
         prev = [p.P.copy(), p.cap.copy(), p.base.copy(), p.pb.copy()]
         lens = (lens * rng.uniform(0.7, 1.6, n_h)).astype(np.int64)
+
+
+@pytest.mark.parametrize('nbytes', [0, 1, 4095, (1 << 20) - 1, (3 << 20) + 17,
+                                    (16 << 20) + 4097, (40 << 20) + 3])
+@pytest.mark.parametrize('threads', [0, 1, 3, 8, 100])
+def test_host_copy_is_a_memcpy(nbytes, threads):
+    """``oa_host_copy`` (the staging copy of pageable loader arrays into the
+    pinned ingest ring): every byte, for part sizes that do and do not divide
+    the length, unaligned ends, more threads than parts; bytes around the
+    destination untouched."""
+    from nbody_orbit_analysis_b200._lib import lib
+    rng = np.random.default_rng(nbytes + threads)
+    src = rng.integers(0, 256, nbytes + 64, dtype=np.uint8)
+    dst = np.full(nbytes + 128, 0xA5, dtype=np.uint8)
+    rc = lib.oa_host_copy(dst.ctypes.data + 32, src.ctypes.data + 5, nbytes, threads)
+    assert rc == 0
+    assert np.array_equal(dst[32:32 + nbytes], src[5:5 + nbytes])
+    assert (dst[:32] == 0xA5).all() and (dst[32 + nbytes:] == 0xA5).all()
+
+
+def test_stage_copy_paths(monkeypatch):
+    """tracker._stage_copy: small copies through torch, large ones through
+    ``oa_host_copy`` with the thread count of ``stage_threads()``."""
+    import torch
+    from nbody_orbit_analysis_b200 import tracker
+    monkeypatch.setattr(tracker, 'STAGE_MIN_BYTES', 1 << 16)
+    monkeypatch.setattr(tracker, '_stage_threads', None)
+    monkeypatch.setenv('OA_STAGE_THREADS', '3')
+    assert tracker.stage_threads() == 3
+    for n in (100, 1 << 14, (1 << 20) + 13):
+        src = torch.arange(n, dtype=torch.int64) * 7 - 3
+        dst = torch.zeros(n, dtype=torch.int64)
+        tracker._stage_copy(dst, src)
+        assert torch.equal(dst, src)
+    monkeypatch.setattr(tracker, '_stage_threads', None)
+    monkeypatch.delenv('OA_STAGE_THREADS')
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '1000')
+    assert tracker.stage_threads() == 1
+    monkeypatch.setattr(tracker, '_stage_threads', None)
+
+
+def test_writer_thread_order_and_errors():
+    """track_orbits._Writer: writes run one at a time in submission order; an
+    exception raised by a write surfaces on the caller's thread at the next
+    submit / wait; ``wait(swallow=True)`` (used while another error unwinds)
+    joins without raising."""
+    import threading
+    import time
+    from nbody_orbit_analysis_b200.track_orbits import _Writer
+    w, log = _Writer(), []
+
+    def job(k, delay):
+        assert threading.current_thread().name == 'orbit-b200-writer'
+        time.sleep(delay)
+        log.append(k)
+    for k, d in enumerate((0.05, 0.0, 0.02, 0.0)):
+        w.submit(job, k, d)
+    w.wait()
+    assert log == [0, 1, 2, 3]
+
+    def bad():
+        raise OSError('disk full')
+    w.submit(bad)
+    with pytest.raises(OSError, match='disk full'):
+        w.submit(job, 9, 0.0)            # surfaces before the next write starts
+    assert log == [0, 1, 2, 3]
+    w.submit(bad)
+    w.wait(swallow=True)
+    w.wait()                             # nothing left, nothing raised

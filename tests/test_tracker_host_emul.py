@@ -460,3 +460,34 @@ def test_track_orbits_sharded_entry_point(emul, tmp_path, loader_side):
     got, exp = storage.tree(str(tmp_path / 'sharded.h5')), storage.tree(f_cpu)
     assert sum(len(v) for k, v in exp.items() if k.endswith('er_IDs')) > 0
     compare_track_trees(got, exp, data_f64=False, derived_bulk=False)
+
+
+def test_loader_error_leaves_whole_groups(emul, pjoin_env, monkeypatch, tmp_path):
+    """The result groups are written by a background thread: when a callback
+    raises, the caller sees that error and the file holds exactly the groups
+    of the snapshots finished before it, complete and equal to the oracle's."""
+    from nbody_orbit_analysis_b200 import track_orbits
+    monkeypatch.setattr(pjoin, 'TARGET', 400)
+    monkeypatch.setattr(pjoin, 'LAG_PARTICLES', 1 << 12)
+    sim = SynthSim(20000, 6, 6, dtype=np.float32, catalogue_dtype=np.float32)
+
+    def load(snap_no, pos, rad):
+        if snap_no == sim.snapshot_numbers[4]:
+            raise RuntimeError('snapshot file missing')
+        return sim.load_snapshot_data(snap_no, pos, rad)
+    f_dev, f_cpu = str(tmp_path / 'd.h5'), str(tmp_path / 'c.h5')
+    with fake_cuda.install(emul):
+        with pytest.raises(RuntimeError, match='snapshot file missing'):
+            track_orbits.track_orbits(sim.snapshot_numbers, sim.main_branches,
+                                      sim.regions, load, f_dev, verbose=False,
+                                      device='cpu')
+    oracle.track_orbits(sim.snapshot_numbers, sim.main_branches, sim.regions,
+                        sim.load_snapshot_data, f_cpu, storage=storage)
+    got, exp = storage.tree(f_dev), storage.tree(f_cpu)
+    def group(k):
+        return k.strip('/').split('/')[0]
+    groups = sorted({group(k) for k in got if group(k).startswith('snapshot_')})
+    assert groups == ['snapshot_%03d' % sim.snapshot_numbers[t] for t in (1, 2)]
+    exp = {k: v for k, v in exp.items()
+           if not group(k).startswith('snapshot_') or group(k) in groups}
+    compare_track_trees(got, exp, data_f64=False)
