@@ -40,7 +40,7 @@ extern "C" {
 #define OA_MODE_APOCENTRIC 1  /* v_r: + -> - (track_orbits.py:313-314) */
 
 /* ABI version; bumped whenever a struct below changes. */
-#define OA_ABI_VERSION 17
+#define OA_ABI_VERSION 18
 
 int oa_abi_version(void);
 const char* oa_last_error(void);

@@ -14,7 +14,7 @@ OA_F32, OA_F64 = 0, 1
 OA_MODE = {'pericentric': 0, 'apocentric': 1}
 OA_SEL_NE, OA_SEL_EQ = 0, 1
 OA_NO_EVENT = 0x8000
-ABI_VERSION = 17
+ABI_VERSION = 18
 BUCKET_LOAD = 3          # OA_BUCKET_LOAD
 
 
