@@ -500,3 +500,73 @@ def test_loader_error_leaves_whole_groups(emul, pjoin_env, monkeypatch, tmp_path
     exp = {k: v for k, v in exp.items()
            if not group(k).startswith('snapshot_') or group(k) in groups}
     compare_track_trees(got, exp, data_f64=False)
+
+
+# ---------------------------------------------------------------------------
+# property test: the drop-in driver (host code + emulated kernel) vs the oracle
+# ---------------------------------------------------------------------------
+def _hyp():
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    cfg = st.fixed_dictionaries(dict(
+        n_particles=st.integers(500, 6000), n_halos=st.integers(1, 12),
+        n_snap=st.integers(2, 6), seed=st.integers(1, 2 ** 31),
+        nfw=st.booleans(), hubble=st.booleans(), catalogue_bulk=st.booleans(),
+        mass_array=st.booleans(), periodic=st.booleans(),
+        late_halos=st.sampled_from([0.0, 0.0, 0.4])))
+    return HealthCheck, given, settings, st, cfg
+
+
+_HC, _given, _settings, _st, _cfg = _hyp()
+
+
+@_settings(max_examples=30, deadline=None, derandomize=True, database=None,
+           suppress_health_check=list(_HC))
+@_given(kw=_cfg, mode=_st.sampled_from(['pericentric', 'apocentric']),
+        reverse=_st.booleans(), vanish=_st.integers(0, 40),
+        target=_st.sampled_from([64, 400, 4096]))
+def test_track_orbits_property_vs_oracle(emul, tmp_path_factory, kw, mode,
+                                         reverse, vanish, target):
+    """Drawn configurations through ``track_orbits`` (pipelined driver, region
+    table, partition plan, staging, writer thread; kernel = the g++ build of the
+    partitioned join) against the oracle: same file.  Includes input rows in
+    reverse order, halos that vanish for a snapshot, derived and mass-weighted
+    bulk velocities, open boxes."""
+    from nbody_orbit_analysis_b200 import track_orbits
+    tmp = tmp_path_factory.mktemp('prop')
+    sim = SynthSim(dtype=np.float32, catalogue_dtype=np.float32, **kw)
+    snaps, mb = sim.snapshot_numbers.copy(), sim.main_branches.copy()
+    if vanish and sim.n_snap > 2:        # one halo missing at one inner snapshot
+        mb[1 + vanish % (sim.n_snap - 2), vanish % sim.n_halos] = -1
+    if reverse:
+        snaps, mb = snaps[::-1].copy(), mb[::-1].copy()
+    f_dev, f_cpu = str(tmp / 'dev.h5'), str(tmp / 'cpu.h5')
+    saved = (pjoin.TARGET, pjoin.LAG_PARTICLES, os.environ.get('OA_TRACK_IMPL'))
+    pjoin.TARGET, pjoin.LAG_PARTICLES = target, 1 << 12
+    os.environ['OA_TRACK_IMPL'] = 'pjoin'
+    try:
+        with np.errstate(all='ignore'):
+            try:
+                oracle.track_orbits(snaps, mb, sim.regions,
+                                    sim.load_snapshot_data, f_cpu, mode=mode,
+                                    storage=storage)
+                failed = False
+            except ValueError:           # a snapshot without matched halos
+                failed = True
+            with fake_cuda.install(emul):
+                if failed:
+                    with pytest.raises(ValueError):
+                        track_orbits.track_orbits(
+                            snaps, mb, sim.regions, sim.load_snapshot_data,
+                            f_dev, mode=mode, verbose=False, device='cpu')
+                    return
+                track_orbits.track_orbits(snaps, mb, sim.regions,
+                                          sim.load_snapshot_data, f_dev,
+                                          mode=mode, verbose=False, device='cpu')
+    finally:
+        pjoin.TARGET, pjoin.LAG_PARTICLES = saved[:2]
+        if saved[2] is None:
+            os.environ.pop('OA_TRACK_IMPL', None)
+        else:
+            os.environ['OA_TRACK_IMPL'] = saved[2]
+    compare_track_trees(storage.tree(f_dev), storage.tree(f_cpu), data_f64=False,
+                        derived_bulk=not kw['catalogue_bulk'])
