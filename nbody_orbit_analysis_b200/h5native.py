@@ -346,7 +346,9 @@ class _Store:
         if arr.nbytes:
             address = _pad8(self.end)
             self.fh.seek(address)
-            self.fh.write(arr.tobytes())
+            # (the array's own buffer: no intermediate bytes object, and the
+            # large write releases the GIL)
+            self.fh.write(arr.reshape(-1).view(np.uint8))
             self.end = address + arr.nbytes
         self.datasets[path] = (arr.dtype, tuple(arr.shape), address, arr.nbytes)
         self.attrs.setdefault(path, {})
@@ -379,6 +381,18 @@ class _Store:
             stop = shape[0]
         row = dtype.itemsize * int(np.prod(shape[1:], dtype=np.int64))
         count = max(stop - start, 0)
+        if inline is None and count * row:
+            # straight into the result array (one copy out of the page cache)
+            out = np.empty((count,) + tuple(shape[1:]), dtype=dtype)
+            self.fh.seek(address + start * row)
+            view = out.reshape(-1).view(np.uint8)
+            got = 0
+            while got < view.size:
+                k = self.fh.readinto(view[got:])
+                if not k:
+                    raise OSError("truncated HDF5 file")
+                got += k
+            return out
         return np.frombuffer(raw(start * row, count * row), dtype=dtype).reshape(
             (count,) + tuple(shape[1:])).copy()
 
