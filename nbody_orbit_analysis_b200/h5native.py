@@ -122,6 +122,44 @@ def _object_header(messages):
 # ---------------------------------------------------------------------------
 # the store: same interface as h5shim._Store
 # ---------------------------------------------------------------------------
+class _LazyDict(dict):
+    """path -> value; a lookup first parses the object's header if the file has
+    it and it has not been read yet (objects are read on first access: opening a
+    file with hundreds of snapshot groups costs one symbol table, not the whole
+    tree)."""
+
+    def __init__(self, store, *a):
+        dict.__init__(self, *a)
+        self._store = store
+
+    def __contains__(self, path):
+        self._store._ensure(path)
+        return dict.__contains__(self, path)
+
+    def __getitem__(self, path):
+        self._store._ensure(path)
+        return dict.__getitem__(self, path)
+
+    def get(self, path, default=None):
+        self._store._ensure(path)
+        return dict.get(self, path, default)
+
+    def setdefault(self, path, default=None):
+        self._store._ensure(path)
+        return dict.setdefault(self, path, default)
+
+
+class _LazySet(set):
+
+    def __init__(self, store, *a):
+        set.__init__(self, *a)
+        self._store = store
+
+    def __contains__(self, path):
+        self._store._ensure(path)
+        return set.__contains__(self, path)
+
+
 class _Store:
 
     def __init__(self, filename, mode):
@@ -139,11 +177,14 @@ class _Store:
         fresh = mode in ('w', 'w-', 'x') or (mode == 'a' and not exists)
         self.fh = open(filename, 'w+b' if fresh else
                        ('rb' if mode == 'r' else 'r+b'))
-        self.groups = {'/'}
-        self.datasets = {}      # path -> (dtype, shape, address, nbytes)
-        self.attrs = {'/': {}}
+        self.groups = _LazySet(self, {'/'})
+        self.datasets = _LazyDict(self)   # path -> (dtype, shape, address, nbytes)
+        self.attrs = _LazyDict(self, {'/': {}})
         self.dirty = fresh
         self.addr = {}          # path -> object header address (objects on disk)
+        self.kids = {'/': set()}   # group -> names of its children
+        self._unread = set()    # objects on disk whose header has not been parsed
+        self._unlisted = {}     # group -> (B-tree, heap) of a symbol table not read yet
         self.changed = {'/'} if fresh else set()   # objects to (re)write at close
         if fresh:
             self.fh.write(b'\x00' * 96)         # superblock, written at close
@@ -200,23 +241,54 @@ class _Store:
                 out.append((mtype, data))
         return out
 
+    def _ensure(self, path):
+        """Parse what the file holds about `path` (no-op for paths already read,
+        created in this session, or absent): the symbol tables of its ancestors
+        and its own object header."""
+        if not self._unread and not self._unlisted:
+            return
+        if not isinstance(path, str) or not path.startswith('/'):
+            return
+        node = '/'
+        for part in [q for q in path.split('/') if q]:
+            self._list(node)
+            node = h5shim._join(node, part)
+            if node in self._unread:
+                self._unread.discard(node)
+                self._read_object(node, self.addr[node])
+            elif not set.__contains__(self.groups, node):
+                return                    # a dataset, or nothing: no deeper level
+
+    def _list(self, group):
+        """Read a group's symbol table: names and header addresses of its
+        children (their headers stay unread until someone asks for them)."""
+        where = self._unlisted.pop(group, None)
+        if where is None:
+            return
+        btree, heap = where
+        hd = self._heap(heap)
+        names = self.kids.setdefault(group, set())
+        for name_off, child in self._btree(btree):
+            name = hd[name_off:hd.index(b'\x00', name_off)].decode('utf-8')
+            cpath = h5shim._join(group, name)
+            names.add(name)
+            self.addr[cpath] = child
+            self._unread.add(cpath)
+
     def _read_object(self, path, addr):
         self.addr[path] = addr
         msgs = self._messages(addr)
         kinds = {m for m, _ in msgs}
-        self.attrs.setdefault(path, {})
+        attrs = dict.setdefault(self.attrs, path, {})
         for mtype, data in msgs:
             if mtype == 0x000C:
                 k, v = self._parse_attr(data)
-                self.attrs[path][k] = v
+                attrs[k] = v
         if 0x0011 in kinds:                               # group
-            self.groups.add(path)
+            set.add(self.groups, path)
             data = dict(msgs)[0x0011]
-            btree, heap = struct.unpack_from('<QQ', data, 0)
-            hd = self._heap(heap)
-            for name_off, child in self._btree(btree):
-                name = hd[name_off:hd.index(b'\x00', name_off)].decode('utf-8')
-                self._read_object(h5shim._join(path, name), child)
+            self.kids.setdefault(path, set())
+            self._unlisted[path] = struct.unpack_from('<QQ', data, 0)
         elif 0x0008 in kinds:                             # dataset
             d = dict(msgs)
             shape = _parse_dspace(d[0x0001])
@@ -232,7 +304,7 @@ class _Store:
                 address, inline = None, bytes(lay[4:4 + nbytes])
             else:
                 raise OSError("chunked datasets are not supported by this reader")
-            self.datasets[path] = (dtype, shape, address, nbytes)
+            dict.__setitem__(self.datasets, path, (dtype, shape, address, nbytes))
             if inline is not None:
                 self._inline = getattr(self, '_inline', {})
                 self._inline[path] = inline
@@ -302,12 +374,9 @@ class _Store:
         return path in self.groups or path in self.datasets
 
     def children(self, path):
-        prefix = path.rstrip('/') + '/'
-        names = set()
-        for p in list(self.groups) + list(self.datasets):
-            if p != path and p.startswith(prefix):
-                names.add(p[len(prefix):].split('/')[0])
-        return sorted(names)
+        self._ensure(path)
+        self._list(path)
+        return sorted(self.kids.get(path, ()))
 
     def _writable(self, path):
         """`path` changes: it and its ancestors get new object headers at close
@@ -326,6 +395,9 @@ class _Store:
         parent = h5shim._norm(os.path.dirname(path))
         if parent != '/' and parent not in self.groups:
             self.add_group(parent)
+        self._list(parent)
+        self.kids.setdefault(parent, set()).add(os.path.basename(path))
+        self.kids.setdefault(path, set())
         self.groups.add(path)
         self.attrs.setdefault(path, {})
 
@@ -350,6 +422,8 @@ class _Store:
             # large write releases the GIL)
             self.fh.write(arr.reshape(-1).view(np.uint8))
             self.end = address + arr.nbytes
+        self._list(parent)
+        self.kids.setdefault(parent, set()).add(os.path.basename(path))
         self.datasets[path] = (arr.dtype, tuple(arr.shape), address, arr.nbytes)
         self.attrs.setdefault(path, {})
 
@@ -450,7 +524,9 @@ class _Store:
         entries = []                        # (name, object header address, is group)
         for name in names:
             child = h5shim._join(path, name)
-            if child in self.groups:
+            if child not in self.changed and child in self.addr:
+                entries.append((name, self.addr[child]))    # as it is on disk
+            elif child in self.groups:
                 entries.append((name, self._write_group(child)))
             else:
                 entries.append((name, self._write_dataset(child)))

@@ -177,3 +177,90 @@ def test_storage_opens_either_container(tmp_path):
     with storage.File(b, 'r+') as hf:                 # appended by its own writer
         hf.create_dataset('y', data=np.arange(2))
     assert h5shim.is_shim_file(b) and '/y' in storage.tree(b)
+
+
+def test_objects_are_parsed_on_first_access(tmp_path):
+    """Opening a file reads the root symbol table only; an object's header is
+    parsed when it is first asked for.  Appends after such a partial read keep
+    every untouched object (header address unchanged, never parsed), also
+    nested groups with attributes, and edits of existing objects land."""
+    import numpy as np
+    from nbody_orbit_analysis_b200 import h5native, storage
+    f = str(tmp_path / 'lazy.h5')
+    rng = np.random.default_rng(3)
+    expect = {}
+    with h5native.File(f, 'w') as hf:
+        hf.attrs['mode'] = 'pericentric'
+        for s in range(60):
+            g = hf.create_group('snapshot_%03d' % s)
+            g.attrs['k'] = s
+            for name in ('a', 'b', 'c'):
+                arr = rng.integers(0, 99, rng.integers(0, 50)).astype(np.int64)
+                g.create_dataset(name, data=arr)
+                expect['/snapshot_%03d/%s' % (s, name)] = arr
+            sub = g.create_group('deep')
+            sub.attrs['note'] = 'n%d' % s
+            sub.create_dataset('x', data=np.float16([s, 1.5]))
+            expect['/snapshot_%03d/deep/x' % s] = np.float16([s, 1.5])
+
+    calls = []
+    real = h5native._Store._read_object
+
+    def counting(self, path, addr):
+        calls.append(path)
+        return real(self, path, addr)
+    h5native._Store._read_object = counting
+    try:
+        with h5native.File(f, 'r') as hf:
+            assert calls == ['/']
+            assert len(hf.keys()) == 60 and list(hf.keys())[-1] == 'snapshot_059'
+            assert calls == ['/']                      # names need no headers
+            assert 'snapshot_007' in hf and 'snapshot_999' not in hf
+            assert np.array_equal(hf['snapshot_007']['b'][:],
+                                  expect['/snapshot_007/b'])
+            assert hf['snapshot_007/deep'].attrs['note'] == 'n7'
+            assert sorted(calls) == ['/', '/snapshot_007', '/snapshot_007/b',
+                                     '/snapshot_007/deep']
+        # append: one new group, one dataset into an existing (unread) group, one
+        # attribute on an existing (unread) nested group
+        del calls[:]
+        with h5native.File(f, 'r+') as hf:
+            old_addr = dict(hf._s.addr) if hf._s.addr else {}
+            g = hf.create_group('snapshot_060')
+            g.create_dataset('a', data=np.arange(5))
+            expect['/snapshot_060/a'] = np.arange(5)
+            hf['snapshot_010'].create_dataset('extra', data=np.float32([1, 2]))
+            expect['/snapshot_010/extra'] = np.float32([1, 2])
+            hf['snapshot_020/deep'].attrs['more'] = 7
+            with pytest.raises(ValueError):
+                hf.create_group('snapshot_030')        # exists (found lazily)
+            with pytest.raises(ValueError):
+                hf['snapshot_010'].create_dataset('a', data=np.arange(2))
+            store = hf._s
+        touched = {'/', '/snapshot_010', '/snapshot_020', '/snapshot_020/deep',
+                   '/snapshot_030'}
+        assert set(calls) <= touched | {'/snapshot_010/a'}, sorted(set(calls) - touched)
+        # untouched groups keep the header they had
+        with h5native.File(f, 'r') as hf:
+            hf.keys()
+            for s in (0, 5, 30, 59):
+                assert hf._s.addr['/snapshot_%03d' % s] == \
+                    store.addr['/snapshot_%03d' % s]
+    finally:
+        h5native._Store._read_object = real
+    got = storage.tree(f)
+    data = {k: v for k, v in got.items() if '__attr__' not in k}
+    assert sorted(data) == sorted(expect)
+    for k, v in expect.items():
+        assert data[k].dtype == v.dtype and np.array_equal(data[k], v), k
+    assert got['/__attr__/mode'] == 'pericentric'
+    assert int(got['/__attr__/snapshot_020/deep/more']) == 7
+    assert str(got['/__attr__/snapshot_020/deep/note']) == 'n20'
+    assert int(got['/__attr__/snapshot_059/k']) == 59
+    # reopening costs the same whatever the number of groups
+    import time
+    t0 = time.perf_counter()
+    for _ in range(20):
+        with h5native.File(f, 'r') as hf:
+            hf['snapshot_059/a'][:]
+    assert (time.perf_counter() - t0) / 20 < 0.01
