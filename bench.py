@@ -733,7 +733,12 @@ def run_b200(args):
     # third snapshot (allocation / pinning warm-up before it) to the return.
     e2e_entry = None
     if world == 1 and not args.no_e2e:
-        e2e_entry = entry_point_e2e(args, snaps, cats, gen, min(K, 12) + 2)
+        try:
+            e2e_entry = entry_point_e2e(args, snaps, cats, gen, min(K, 12) + 2)
+        except Exception as exc:      # a secondary figure must not cost the line
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            e2e_entry = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
     # ---- roofline of the fused kernel ------------------------------------------
     peak, peak_kind = measured_peak()
