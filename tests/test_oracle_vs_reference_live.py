@@ -112,6 +112,36 @@ def test_track_orbits_equals_reference(ref, tmp_path_factory, kw, mode,
                                 if k.endswith('er_IDs'))
 
 
+@settings(max_examples=20, **SETTINGS)
+@given(kw=sims, mode=st.sampled_from(['pericentric', 'apocentric']),
+       cut=st.integers(2, 4))
+def test_resume_equals_reference(ref, tmp_path_factory, kw, mode, cut):
+    """checkpoint=True up to snapshot `cut`, then resume=True over the whole
+    list (reference ``track_orbits.py:93-101, 229-232, 390-394``)."""
+    tmp = tmp_path_factory.mktemp('live_resume')
+    kw = dict(kw, n_snap=5, late_halos=0.0,
+              box_vector=kw['box_vector'] and kw['periodic'])
+    sim = SynthSim(**kw)
+    snaps, mb = sim.snapshot_numbers, sim.main_branches
+    backend = _storage_of_reference(ref)
+    files = []
+    with np.errstate(all='ignore'):
+        for run, extra in ((ref.track_orbits.track_orbits,
+                            dict(npool=None, verbose=False)),
+                           (oracle.track_orbits, dict(storage=backend))):
+            f = str(tmp / ('%d.h5' % len(files)))
+            run(snaps[:cut], mb[:cut], sim.regions, sim.load_snapshot_data, f,
+                mode=mode, checkpoint=True, **extra)
+            run(snaps, mb, sim.regions, sim.load_snapshot_data, f, mode=mode,
+                checkpoint=True, resume=True, **extra)
+            tree = storage.tree(f)
+            for k, v in storage.tree(f + '.checkpoint').items():
+                tree['/__checkpoint__' + k] = v
+            files.append(tree)
+    assert_same_tree(files[1], files[0])
+    SEEN['resumed'] = SEEN.get('resumed', 0) + 1
+
+
 @settings(max_examples=40, **SETTINGS)
 @given(kw=sims, mode=st.sampled_from(['pericentric', 'apocentric']),
        drop=st.lists(st.tuples(st.integers(0, 1), st.integers(0, 8)),
@@ -205,5 +235,6 @@ def test_zz_the_drawn_cases_were_not_trivial():
     assert SEEN['track_files'] >= 30 and SEEN['track_events'] > 2000, SEEN
     assert SEEN['otf_files'] >= 20 and SEEN['otf_events'] > 500, SEEN
     assert SEEN['collated'] >= 10 and SEEN['progenitor_lists'] >= 15, SEEN
+    assert SEEN.get('resumed', 0) >= 10, SEEN
     assert SEEN['progenitors_found'] > 10, SEEN
     print('live oracle-vs-reference cases:', SEEN)
