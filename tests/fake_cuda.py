@@ -162,8 +162,10 @@ class FakeLib:
 
 
 @contextlib.contextmanager
-def install(emul):
-    """Patch torch.cuda and the tracker's library handle; restore on exit."""
+def install(emul, lib_class=None):
+    """Patch torch.cuda and the tracker's library handle; restore on exit.
+    ``lib_class``: a ``FakeLib`` subclass (tests/hash_twin.py: the default
+    implementation tracked by a numpy twin instead of a no-op)."""
     from nbody_orbit_analysis_b200 import tracker, _lib
     saved = {}
     cuda = torch.cuda
@@ -194,7 +196,7 @@ def install(emul):
     def tensor(*a, **k):
         return real_tensor(*a, **host(k))
     torch.empty, torch.zeros, torch.tensor = empty, zeros, tensor
-    fake = FakeLib(_lib.lib, emul)
+    fake = (lib_class or FakeLib)(_lib.lib, emul)
     real_lib = tracker.lib
     tracker.lib = fake
     real_init = tracker.OrbitTracker.__init__

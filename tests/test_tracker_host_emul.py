@@ -409,7 +409,8 @@ def test_pjoin_empty_block_and_vanishing_halo(emul, pjoin_env, monkeypatch, tmp_
 # ---------------------------------------------------------------------------
 # the drop-in entry point, sharded over 2 ranks (gloo), against the oracle
 # ---------------------------------------------------------------------------
-def _entry_rank(rank, world, port, emul_path, out_dir, loader_side):
+def _entry_rank(rank, world, port, emul_path, out_dir, loader_side,
+                impl='pjoin'):
     import ctypes as C
     import sys
     import torch.distributed as dist
@@ -417,12 +418,17 @@ def _entry_rank(rank, world, port, emul_path, out_dir, loader_side):
     sys.path.insert(0, os.path.dirname(here))
     sys.path.insert(0, here)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
-                      OA_TRACK_IMPL='pjoin', OA_FAKE_CTAS='1')
+                      OA_TRACK_IMPL=impl, OA_FAKE_CTAS='1')
     import exchange_emul
     import fake_cuda as fc
     from nbody_orbit_analysis_b200 import pjoin as pj, sharded, track_orbits
-    emul_lib = C.CDLL(emul_path)
-    emul_lib.pj_emul_step.argtypes = [C.POINTER(pj.PJoinArgs), C.c_int]
+    emul_lib, lib_class = None, None
+    if impl == 'pjoin':
+        emul_lib = C.CDLL(emul_path)
+        emul_lib.pj_emul_step.argtypes = [C.POINTER(pj.PJoinArgs), C.c_int]
+    else:                      # default implementation: numpy twin of its kernel
+        import hash_twin
+        lib_class = hash_twin.TwinLib
     pj.TARGET, pj.LAG_PARTICLES = 400, 1 << 12
     exchange_emul.install(sharded)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -441,7 +447,7 @@ def _entry_rank(rank, world, port, emul_path, out_dir, loader_side):
             snap['_gpos'] = gpos
         return snap
     out = os.path.join(out_dir, 'sharded.h5')
-    with fc.install(emul_lib):
+    with fc.install(emul_lib, lib_class):
         track_orbits.track_orbits(sim.snapshot_numbers, sim.main_branches,
                                   regions, loader, out, verbose=False,
                                   device='cpu')
@@ -451,8 +457,9 @@ def _entry_rank(rank, world, port, emul_path, out_dir, loader_side):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('loader_side', [False, True])
-def test_track_orbits_sharded_entry_point(emul, tmp_path, loader_side):
+@pytest.mark.parametrize('loader_side,impl', [(False, 'pjoin'), (True, 'pjoin'),
+                                              (True, 'hash')])
+def test_track_orbits_sharded_entry_point(emul, tmp_path, loader_side, impl):
     """``track_orbits`` under a 2-rank process group: catalogue broadcast from
     rank 0, particles sharded by ID (by the driver, or by the loader with
     ``_gpos``), events merged in the reference order, rank 0 writes the file --
@@ -460,7 +467,7 @@ def test_track_orbits_sharded_entry_point(emul, tmp_path, loader_side):
     import torch.multiprocessing as mp
     from test_sharded_gloo import _free_port
     mp.spawn(_entry_rank, args=(2, _free_port(), emul._name, str(tmp_path),
-                                loader_side), nprocs=2, join=True)
+                                loader_side, impl), nprocs=2, join=True)
     sim = SynthSim(24000, 7, 5, dtype=np.float32, catalogue_dtype=np.float32,
                    late_halos=0.3)
     f_cpu = str(tmp_path / 'cpu.h5')
