@@ -171,6 +171,38 @@ def test_bench_end_to_end_on_fake_cuda(emul, pjoin_env, monkeypatch, capsys):
     assert set(line['host_phases_ms_per_step']) >= {'submit', 'collect'}
 
 
+def test_bench_default_implementation_on_the_numpy_twin(monkeypatch, capsys):
+    """``bench.py`` with the DEFAULT implementation, its kernel replaced by the
+    numpy twin (tests/hash_twin.py): the three passes (results left in HBM,
+    results copied to the host, end to end from host arrays) see the same events,
+    and the CPU-baseline sample agrees with the oracle."""
+    import argparse
+    import json
+    import bench
+    import hash_twin
+    from nbody_orbit_analysis_b200 import synth
+    monkeypatch.setattr(synth, 'DeviceSynth', HostSynth)
+    for k in ('WORLD_SIZE', 'OA_TRACK_IMPL', 'OA_BENCH_TO_HOST'):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv('OA_BENCH_CLOCK_PERIOD', '0.05')
+    args = argparse.Namespace(
+        gpus=1, steps=3, warmup=3, impl='b200', particles=8000, halos=6,
+        mode='pericentric', depth=2, profile=False, no_e2e=False, no_cpu=False,
+        cpu_particles=2000)
+    with fake_cuda.install(None, hash_twin.TwinLib):
+        bench.run_b200(args)
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines()
+                       if ln.startswith('{')][-1])
+    assert line['track_impl'] == 'hash' and line['parity'] == 'ok'
+    assert line['events_per_step'] > 100
+    assert line['value_results_to_host']['events_equal_device_run'] is True
+    assert line['e2e']['events_equal_device_run'] is True
+    assert line['e2e']['events_per_step'] == line['events_per_step']
+    cpu = line['cpu_baseline']
+    assert cpu['parity_vs_gpu_on_sample'] == 'ok' and cpu['sample_events'] > 0
+    assert 'error' not in line['e2e_entry_point']
+
+
 def test_bench_hash_branch_runs_on_fake_cuda(emul, monkeypatch, capsys):
     """The default implementation through ``bench.py`` with no-op kernels:
     every line of the GPU arm executes (numbers are meaningless)."""
@@ -227,7 +259,8 @@ class ShardedHostSynth(HostSynth):
         return dev, n, np.append(loc['region_offsets'], n).astype(np.int64)
 
 
-def _bench_rank(rank, world, port, emul_path, out_dir, batch=1, prepack=False):
+def _bench_rank(rank, world, port, emul_path, out_dir, batch=1, prepack=False,
+                impl='pjoin'):
     import argparse
     import contextlib
     import io
@@ -239,7 +272,7 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1, prepack=False):
     sys.path.insert(0, here)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
                       RANK=str(rank), LOCAL_RANK=str(rank),
-                      WORLD_SIZE=str(world), OA_TRACK_IMPL='pjoin',
+                      WORLD_SIZE=str(world), OA_TRACK_IMPL=impl,
                       OA_BENCH_CLOCK_PERIOD='0.05', OA_FAKE_CTAS='1',
                       OA_EXCHANGE_BATCH=str(batch),
                       OA_EXCHANGE_PREPACK='1' if prepack else '0')
@@ -266,16 +299,21 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1, prepack=False):
         mode='pericentric', depth=2, profile=False, no_e2e=world > 2,
         no_cpu=batch > 1, cpu_particles=2000)
     buf = io.StringIO()
-    with fc.install(emul_lib), contextlib.redirect_stdout(buf):
+    lib_class = None
+    if impl == 'hash':         # default implementation: numpy twin of its kernel
+        import hash_twin
+        lib_class = hash_twin.TwinLib
+    with fc.install(emul_lib, lib_class), contextlib.redirect_stdout(buf):
         bench.run_b200(args)
     with open(os.path.join(out_dir, 'out_%d' % rank), 'w') as fh:
         fh.write(buf.getvalue())
 
 
-@pytest.mark.parametrize('world,batch,prepack', [(2, 1, False), (2, 3, False),
-                                                 (2, 1, True)])
-def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, tmp_path,
-                                       monkeypatch, capsys):
+@pytest.mark.parametrize('world,batch,prepack,impl', [
+    (2, 1, False, 'pjoin'), (2, 3, False, 'pjoin'), (2, 1, True, 'pjoin'),
+    (2, 1, False, 'hash')])
+def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, impl,
+                                       tmp_path, monkeypatch, capsys):
     """The multi-GPU arm of ``bench.py`` with `world` ranks on the CPU: sharded
     snapshots, catalogue broadcast one snapshot ahead, asynchronous all-to-all
     exchange (numpy restatements of its kernels, gloo) and per-rank slices --
@@ -285,7 +323,7 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, tmp_path,
     import torch.multiprocessing as mp
     from test_sharded_gloo import _free_port
     mp.spawn(_bench_rank, args=(world, _free_port(), emul._name, str(tmp_path),
-                                batch, prepack), nprocs=world, join=True)
+                                batch, prepack, impl), nprocs=world, join=True)
     lines = [ln for ln in open(str(tmp_path / 'out_0')).read().splitlines()
              if ln.startswith('{')]
     multi = json.loads(lines[-1])
