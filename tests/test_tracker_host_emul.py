@@ -296,8 +296,9 @@ def _bench_rank(rank, world, port, emul_path, out_dir, batch=1, prepack=False,
         'gloo', rank=rank, world_size=world)
     args = argparse.Namespace(
         gpus=world, steps=3, warmup=3, impl='b200', particles=6000, halos=7,
-        mode='pericentric', depth=2, profile=False, no_e2e=world > 2,
-        no_cpu=batch > 1, cpu_particles=2000)
+        mode='pericentric', depth=2, profile=False,
+        no_e2e=world > 2 or batch > 1 or prepack,   # (variants: one pass each)
+        no_cpu=batch > 1 or prepack, cpu_particles=2000)
     buf = io.StringIO()
     lib_class = None
     if impl == 'hash':         # default implementation: numpy twin of its kernel
@@ -335,14 +336,15 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, impl,
         assert vh['value'] > 0 and vh['events_equal_device_run'] is True
     else:
         assert 'value_results_to_host' not in multi
-    if batch == 1:
+    base = batch == 1 and not prepack
+    if base:
         # a sample of whole halos, put back together from all ranks' shards,
         # through both exchange paths against the oracle on rank 0
         par = multi['parity_multi_gpu']
         assert par['parity_vs_oracle'] == 'ok' and par['sample_events'] > 0
         assert par['all_gather'] == par['all_to_all'] == 'ok'
         assert par['batched_all_to_all'] == 'ok'
-    if world == 2:
+    if world == 2 and base:
         assert multi['e2e']['value'] > 0
         assert multi['e2e']['events_per_step'] == multi['events_per_step']
     assert {'catalogue', 'submit', 'collect', 'start_merge'} | (
@@ -353,7 +355,7 @@ def test_bench_multi_rank_on_fake_cuda(emul, world, batch, prepack, impl,
 
     if prepack:
         # (OA_EXCHANGE_PREPACK=1: the pack kernels ran at submit time)
-        assert multi['exchange_prepacked'] >= 4
+        assert multi['exchange_prepacked'] >= 2
     if world != 2:
         return
     # one rank, whole universe
