@@ -323,6 +323,13 @@ class OrbitTracker:
         done.record(stream if stream is not None else self._main())
         cs.wait_event(done)
         via = C.c_void_p(cs.cuda_stream) if bulk else None
+        if bulk:
+            # the source was allocated on another stream (the exchange's): if its
+            # owner drops it before this copy has run, the caching allocator must
+            # not hand the block to that stream's next kernels
+            for t in tensors:
+                if t.is_cuda:
+                    t.record_stream(cs)
         names = names or [None] * len(tensors)
         out = [self._to_host_async(t, name=nm, reserve=reserve, step=step, via=via)
                for t, nm in zip(tensors, names)]
