@@ -693,16 +693,20 @@ def run_b200(args):
         e2e_run = timed_run(host, results='host')
         n_per_step = e2e_run['particles'] / K / world
         ev_per_step = e2e_run['events'] / K
+        # ids + pos + vel (+ global block positions when sharded) of one rank
+        h2d_rank = int(n_per_step * (40 if world > 1 else 32) + args.halos * 72)
         e2e = {'value': e2e_run['particles'] / (e2e_run['ms'] * 1e-3),
                'unit': 'particle-snapshots/s',
-               # ids + pos + vel (+ global block positions when sharded)
-               'h2d_bytes_per_step': int(n_per_step * (40 if world > 1 else 32)
-                                         + args.halos * 72),
-               'd2h_bytes_per_step': int(ev_per_step * 10 + args.halos * 8 + 8),
+               # whole job, like `value`: all ranks' uploads; every rank reads back
+               # its 1/N slice of the merged lists + the offsets
+               'h2d_bytes_per_step': h2d_rank * world,
+               'd2h_bytes_per_step': int(ev_per_step * 10
+                                         + world * (args.halos * 8 + 8)),
+               'h2d_bytes_per_step_per_gpu': h2d_rank,
                'ms_per_step': e2e_run['ms'] / K,
                'events_per_step': ev_per_step}
         # what the end-to-end number is bound by: the host->device link
-        e2e['h2d_gb_per_s_per_gpu'] = e2e['h2d_bytes_per_step'] / (
+        e2e['h2d_gb_per_s_per_gpu'] = h2d_rank / (
             e2e['ms_per_step'] * 1e-3) / 1e9
         # same data, two passes: the global event totals must be identical
         e2e['events_equal_device_run'] = bool(
