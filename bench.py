@@ -27,7 +27,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np

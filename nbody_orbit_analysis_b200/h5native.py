@@ -28,7 +28,6 @@ Validation status: written against the specification and read back by the
 independent parser below; NOT validated against libhdf5 in this image (there is
 none).  ``storage.py`` selects it with ``OA_STORAGE=hdf5``.
 """
-import io
 import os
 import struct
 

@@ -23,7 +23,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 from parity import assert_same_tree
 
-from nbody_orbit_analysis_b200 import h5shim, storage
+from nbody_orbit_analysis_b200 import storage
 from nbody_orbit_analysis_b200.synth import SynthSim
 from oracle import orbit_oracle as oracle
 from oracle import reference_harness
