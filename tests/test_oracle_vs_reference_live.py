@@ -1,7 +1,7 @@
 """Property tests: the CPU oracle against the UNMODIFIED reference, run live.
 
 The committed fixtures (tests/golden, test_oracle_golden.py) pin the oracle on
-23 fixed cases.  Here hypothesis draws the configuration -- particle and halo
+22 fixed cases.  Here hypothesis draws the configuration -- particle and halo
 counts, number of snapshots, dtypes, periodic / open box, scalar or (3,) box,
 Hubble flow, catalogue or derived bulk velocity, mass arrays, halos appearing
 mid-run, both modes -- and the oracle must write, bit for bit, the file the
