@@ -11,8 +11,12 @@ selection, result assembly, checkpoint / resume / device-state checkpoints) is
 compared with the oracle on the CPU as well.  It says nothing about the CUDA
 kernel itself: that is what the ``-m gpu`` tests are for.
 
-Not covered: the on-the-fly arithmetic (``onthefly = 1``), the hash table (the
-twin matches by ID directly; ``tab`` stays untouched).
+The on-the-fly variant (``onthefly = 1``: frame and v_r in the data dtype, no
+Hubble flow, raw angle change and 0 / 1 marks per matched previous particle,
+reference ``track_orbits_onthefly.py:71-205``) and the small kernels the
+on-the-fly driver calls around it (general ordered selection, gathers,
+per-segment sort keys, radix sort) are restated as well.  Not covered: the hash
+table (the twin matches by ID directly; ``tab`` stays untouched).
 """
 import ctypes as C
 
@@ -66,8 +70,6 @@ class TwinLib(fake_cuda.FakeLib):
     def oa_track_fused(self, args, stream):
         self.calls.append('oa_track_fused')
         a = args._obj
-        if a.onthefly:
-            raise NotImplementedError('the twin has no on-the-fly arithmetic')
         n, n_h = int(a.n_cur), int(a.n_regions)
         x64, f64 = bool(a.data_dtype), bool(a.frame_dtype)
         fl = C.c_double if x64 else C.c_float
@@ -92,8 +94,8 @@ class TwinLib(fake_cuda.FakeLib):
         if a.out_match:
             fdt = C.c_double if f64 else C.c_float
             diag = (_arr(a.out_rhat, 3 * n, fdt).reshape(-1, 3),
-                    _arr(a.out_vr, n, C.c_double), _arr(a.out_r, n, fdt),
-                    _arr(a.out_match, n, C.c_int64))
+                    _arr(a.out_vr, n, fdt if a.onthefly else C.c_double),
+                    _arr(a.out_r, n, fdt), _arr(a.out_match, n, C.c_int64))
             diag[3][:] = -1
         with np.errstate(all='ignore'):
             for j in range(n_h):
@@ -102,11 +104,23 @@ class TwinLib(fake_cuda.FakeLib):
                 assert lo == row['cur_begin'] and hi - lo == row['cur_count']
                 centre = row['centre_f'] if a.centre_f32 else row['centre']
                 bulk = row['bulk_f'] if a.bulk_f32 else row['bulk']
-                rh, vr, _ = oracle.region_frame(snap, (lo, hi), centre, bulk, H)
                 delta = snap['coordinates'][lo:hi] - centre
                 if a.periodic:
                     delta = oracle.minimum_image(delta, snap['box_size'])
-                rads = np.sqrt(np.einsum('...i,...i', delta, delta))
+                if a.onthefly:
+                    # track_orbits_onthefly.py:82-110: the work arrays have the
+                    # snapshot's dtypes (a float64 centre / bulk velocity is
+                    # rounded back on assignment), no Hubble term
+                    delta = delta.astype(snap['coordinates'].dtype)
+                    rv = (snap['velocities'][lo:hi] - bulk).astype(
+                        snap['velocities'].dtype)
+                    rads = np.sqrt(np.einsum('...i,...i', delta, delta))
+                    rh = delta / rads[:, np.newaxis]
+                    vr = np.einsum('...i,...i', rv, rh)
+                else:
+                    rh, vr, _ = oracle.region_frame(snap, (lo, hi), centre, bulk,
+                                                    H)
+                    rads = np.sqrt(np.einsum('...i,...i', delta, delta))
                 assert rh.dtype == (np.float64 if f64 else np.float32), \
                     'frame dtype of the launch arguments'
                 ang = np.zeros(hi - lo, dtype=np.float16)
@@ -115,10 +129,17 @@ class TwinLib(fake_cuda.FakeLib):
                     pr = rec_prev[plo:plo + cnt]
                     d = oracle.compare_radial_velocities(
                         ids[lo:hi], pr['id'], vr, pr['vr'], rh, pr['rhat'], mode)
-                    ang, eang = oracle.calc_angles(hi - lo, pr['angle'], d)
                     surviving = np.delete(np.arange(cnt), d['inds_departed'])
-                    mark_prev[plo + surviving[d['apsis_inds']]] = \
-                        eang.view(np.uint16)
+                    if a.onthefly:
+                        mark_prev[plo + surviving] = 0
+                        mark_prev[plo + surviving[d['apsis_inds']]] = 1
+                        if a.dangle_prev:
+                            _arr(a.dangle_prev, n_prev, fl)[plo + surviving] = \
+                                d['angle_changes']
+                    else:
+                        ang, eang = oracle.calc_angles(hi - lo, pr['angle'], d)
+                        mark_prev[plo + surviving[d['apsis_inds']]] = \
+                            eang.view(np.uint16)
                     if diag is not None:
                         diag[3][lo + d['inds_match']] = plo + surviving
                 rec['id'][lo:hi] = ids[lo:hi]
@@ -144,4 +165,83 @@ class TwinLib(fake_cuda.FakeLib):
 
     def oa_fill_u16(self, dst, n, value, stream):
         _arr(dst, n, C.c_uint16)[:] = value
+        return 0
+
+    # ---- the small kernels of the on-the-fly driver --------------------------------
+    @staticmethod
+    def _hits(marks, n, op, value):
+        m = _arr(marks, n, C.c_uint16)
+        return np.flatnonzero((m == value) if op == 1 else (m != value))
+
+    def oa_select_count(self, marks, n, op, value, ws, ws_bytes, total_dev, st):
+        _arr(total_dev, 1, C.c_int64)[0] = len(self._hits(marks, n, op, value))
+        return 0
+
+    def oa_select_gather(self, marks, n, op, value, ws, sel_out, st):
+        sel = self._hits(marks, n, op, value)
+        _arr(sel_out, len(sel), C.c_int64)[:] = sel
+        return 0
+
+    @staticmethod
+    def _count(n_sel, n_dev):
+        return int(_arr(n_dev, 1, C.c_int64)[0]) if n_dev else int(n_sel)
+
+    def oa_gather_record_ids(self, rec, frame_dtype, sel, n_sel, n_dev, out, st):
+        k = self._count(n_sel, n_dev)
+        s_ = _arr(sel, k, C.c_int64)
+        stride = 8 if frame_dtype else 4
+        n_rec = int(s_.max()) + 1 if k else 0
+        _arr(out, k, C.c_int64)[:] = _arr(rec, n_rec * stride, C.c_int64)[s_ * stride]
+        return 0
+
+    def oa_gather_i64(self, src, sel, n_sel, n_dev, out, st):
+        k = self._count(n_sel, n_dev)
+        s_ = _arr(sel, k, C.c_int64)
+        n_src = int(s_.max()) + 1 if k else 0
+        _arr(out, k, C.c_int64)[:] = _arr(src, n_src, C.c_int64)[s_]
+        return 0
+
+    def oa_gather_f(self, src, dtype, sel, n_sel, n_dev, out, st):
+        k = self._count(n_sel, n_dev)
+        s_ = _arr(sel, k, C.c_int64)
+        ct = C.c_double if dtype else C.c_float
+        n_src = int(s_.max()) + 1 if k else 0
+        _arr(out, k, ct)[:] = _arr(src, n_src, ct)[s_]
+        return 0
+
+    def oa_mark_unmatched(self, match, n, marks, st):
+        _arr(marks, n, C.c_uint16)[:] = _arr(match, n, C.c_int64) < 0
+        return 0
+
+    def oa_minmax_i64(self, x, n, out, st):
+        v = _arr(x, n, C.c_int64)
+        o = _arr(out, 2, C.c_int64)
+        o[0], o[1] = v.min(), v.max()
+        return 0
+
+    def oa_segment_sort_keys(self, ids, n, seg_off, n_seg, flag, minmax, key_lo,
+                             key_hi, index, st):
+        """csrc/oa_segment.cu: key_hi = segment, key_lo = id - min for segments
+        to be sorted, else the element's own position."""
+        off = _arr(seg_off, n_seg + 1, C.c_int64)
+        i = np.arange(n, dtype=np.int64)
+        seg = np.searchsorted(off[1:], i, side='right')
+        sort = np.ones(n, dtype=bool) if not flag else \
+            _arr(flag, n_seg, C.c_uint8)[seg] != 0
+        lo = _arr(minmax, 2, C.c_int64)[0]
+        _arr(key_lo, n, C.c_uint64)[:] = np.where(
+            sort, _arr(ids, n, C.c_int64) - lo, i).astype(np.uint64)
+        _arr(key_hi, n, C.c_uint64)[:] = seg.astype(np.uint64)
+        _arr(index, n, C.c_uint64)[:] = i.astype(np.uint64)
+        return 0
+
+    def oa_sort_pairs_u64(self, keys_in, vals_in, keys_out, vals_out, n, begin_bit,
+                          end_bit, ws, ws_bytes, st):
+        """Stable LSD radix sort on bits [begin_bit, end_bit)."""
+        k = _arr(keys_in, n, C.c_uint64)
+        mask = np.uint64(((1 << (end_bit - begin_bit)) - 1) if end_bit - begin_bit < 64
+                         else 0xFFFFFFFFFFFFFFFF)
+        order = np.argsort((k >> np.uint64(begin_bit)) & mask, kind='stable')
+        _arr(keys_out, n, C.c_uint64)[:] = k[order]
+        _arr(vals_out, n, C.c_uint64)[:] = _arr(vals_in, n, C.c_uint64)[order]
         return 0

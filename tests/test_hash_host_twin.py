@@ -148,3 +148,34 @@ def test_property_default_host_path_vs_oracle(tmp_path_factory, kw, mode,
         a = storage.tree(f_dev + '.checkpoint')['/angles']
         b = storage.tree(f_cpu + '.checkpoint')['/angles']
         assert a.shape == b.shape and f16_ulps(a, b).max(initial=0) == 0
+
+
+@pytest.fixture
+def twin_onthefly(twin, monkeypatch):
+    """The on-the-fly driver holds its own reference to the library."""
+    from nbody_orbit_analysis_b200 import track_orbits_onthefly
+    monkeypatch.setattr(track_orbits_onthefly, 'lib', twin)
+    return twin
+
+
+@pytest.mark.parametrize('name', list_fixtures('onthefly_'))
+def test_onthefly_reference_fixtures_through_the_host_path(twin_onthefly, name,
+                                                           tmp_path):
+    """a-12 on the CPU: the on-the-fly driver (two launches of the tracking
+    step, ordered selections, sorted entered / departed lists, dtype rules of
+    the reference's concatenations) against the reference's own files."""
+    import test_gpu_onthefly as otf
+    otf.test_onthefly_matches_reference_fixture(name, tmp_path)
+
+
+@pytest.mark.parametrize('mode', ['pericentric', 'apocentric'])
+@pytest.mark.parametrize('case', [
+    (12000, 9, np.float32, np.float32, {}, (), ()),
+    (12000, 9, np.float32, np.float64, {}, (2, 7), (5,)),
+    (8000, 9, np.float64, np.float64, {'mass_array': True}, (0,), (8,)),
+    (3000, 400, np.float32, np.float32, {}, (3, 4, 5), (10,)),
+], ids=['f32', 'f32c64_missing', 'f64_massarr_missing', 'tiny_blocks'])
+def test_onthefly_oracle_cases_through_the_host_path(twin_onthefly, case, mode,
+                                                     tmp_path):
+    import test_gpu_onthefly as otf
+    otf.test_onthefly_matches_oracle(case, mode, tmp_path)
