@@ -179,3 +179,49 @@ def test_onthefly_oracle_cases_through_the_host_path(twin_onthefly, case, mode,
                                                      tmp_path):
     import test_gpu_onthefly as otf
     otf.test_onthefly_matches_oracle(case, mode, tmp_path)
+
+
+@_deco
+@_given(kw=_cfg, mode=_st.sampled_from(['pericentric', 'apocentric']),
+        drop=_st.lists(_st.tuples(_st.integers(0, 1), _st.integers(0, 11)),
+                       max_size=3))
+def test_property_onthefly_host_path_vs_oracle(tmp_path_factory, kw, mode, drop):
+    """Drawn configurations through the on-the-fly entry point (halos missing
+    at s or at s-1, every dtype combination, mass arrays, open boxes)."""
+    import os
+    import test_gpu_onthefly as otf
+    from nbody_orbit_analysis_b200 import storage, track_orbits_onthefly
+    from nbody_orbit_analysis_b200.synth import SynthSim
+    from oracle import orbit_oracle as oracle
+    tmp = tmp_path_factory.mktemp('twin_otf')
+    kw = dict(kw, late_halos=0.0, hubble=False,
+              box_vector=kw['box_vector'] and kw['periodic'])
+    sim = SynthSim(**kw)
+    t = sim.n_snap - 1
+    links = np.stack([sim.main_branches[t], sim.main_branches[t - 1]])
+    for row, col in drop:
+        links[row, col % sim.n_halos] = -1
+    if not (links[0] != -1).any() or not (links[1] != -1).any():
+        return
+    snap_no = int(sim.snapshot_numbers[t])
+    f_dev, f_cpu = str(tmp / 'd_{}.h5'), str(tmp / 'c_{}.h5')
+    saved = os.environ.pop('OA_TRACK_IMPL', None)
+    real_lib = track_orbits_onthefly.lib
+    try:
+        with np.errstate(all='ignore'):
+            oracle.track_orbits_onthefly(
+                snap_no, links, sim.regions_onthefly, sim.load_snapshot_data,
+                f_cpu, mode=mode, storage=storage)
+            with fake_cuda.install(None, hash_twin.TwinLib) as fake:
+                track_orbits_onthefly.lib = fake
+                track_orbits_onthefly.track_orbits(
+                    snap_no, links, sim.regions_onthefly, sim.load_snapshot_data,
+                    f_dev, mode=mode, verbose=False)
+    finally:
+        track_orbits_onthefly.lib = real_lib
+        if saved is not None:
+            os.environ['OA_TRACK_IMPL'] = saved
+    name = '%0.3d' % snap_no
+    otf.compare_onthefly_trees(storage.tree(f_dev.format(name)),
+                               storage.tree(f_cpu.format(name)),
+                               kw['dtype'] == np.float64)
