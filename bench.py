@@ -642,9 +642,18 @@ def run_b200(args):
     dev_run = timed_run(results=results_in)
     value = dev_run['particles'] / (dev_run['ms'] * 1e-3)
     to_host_run = None
+    to_host_error = None
     if results_in == 'hbm' and os.environ.get('OA_BENCH_TO_HOST') != '0' and \
             os.environ.get('OA_BENCH_NO_EXCHANGE') != '1':
-        to_host_run = timed_run(results='host')
+        if world > 1:
+            to_host_run = timed_run(results='host')
+        else:
+            try:         # (one rank: a secondary pass must not cost the line)
+                to_host_run = timed_run(results='host')
+            except Exception as exc:
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                to_host_error = '%s: %s' % (type(exc).__name__, exc)
 
     # ---- end to end: host (pinned) snapshots ---------------------------------
     e2e = None
@@ -833,6 +842,8 @@ def run_b200(args):
                                     for i, n in enumerate(names)}}
         if host_results is not None:
             line['value_results_to_host'] = host_results
+        elif to_host_error is not None:
+            line['value_results_to_host'] = {'error': to_host_error}
         if e2e is not None:
             line['e2e'] = e2e
         elif not args.no_e2e:
