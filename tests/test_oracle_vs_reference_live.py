@@ -238,3 +238,23 @@ def test_zz_the_drawn_cases_were_not_trivial():
     assert SEEN.get('resumed', 0) >= 10, SEEN
     assert SEEN['progenitors_found'] > 10, SEEN
     print('live oracle-vs-reference cases:', SEEN)
+
+
+def test_vendored_reference_is_unmodified():
+    """``oracle/_ref`` (what travels to the GPU box for the CPU arm) holds the
+    reference's Python files byte for byte -- checked wherever the mounted tree
+    and the vendored copy both exist (the build container)."""
+    import filecmp
+    import os
+    here = os.path.dirname(os.path.abspath(reference_harness.__file__))
+    vendored = os.path.join(here, '_ref', 'orbitanalysis')
+    mounted = os.path.join(os.environ.get('OA_REFERENCE_ROOT', '/root/reference'),
+                           'orbitanalysis')
+    if not (os.path.isdir(vendored) and os.path.isdir(mounted)):
+        pytest.skip('needs both the mounted reference and oracle/_ref')
+    names = sorted(f for f in os.listdir(mounted) if f.endswith('.py'))
+    assert names and names == sorted(
+        f for f in os.listdir(vendored) if f.endswith('.py'))
+    for name in names:
+        assert filecmp.cmp(os.path.join(mounted, name),
+                           os.path.join(vendored, name), shallow=False), name
