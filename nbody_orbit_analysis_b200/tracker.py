@@ -291,6 +291,7 @@ class OrbitTracker:
             small = nbytes <= self.SMALL_COPY and nbytes % 4 == 0 and \
                 t.data_ptr() % 4 == 0 and via is None
             fn = lib.oa_copy_small if small else lib.oa_copy_async
+            self.launches += int(small)       # (a kernel of this library)
             check(fn(h.data_ptr(), t.data_ptr(), nbytes,
                      self._copy_st if via is None else via))
         return h
