@@ -94,8 +94,9 @@ int oa_copy_small(void* dst, const void* src, size_t bytes, void* stream);
  * (~10 GB/s) is slower than the host-to-device link (~52 GB/s).  Each thread
  * copies one contiguous, 4096-byte aligned part with the C library's memcpy
  * (non-temporal stores for large sizes: no read-for-ownership of the
- * destination).  n_threads <= 1, or fewer than 1 MiB per thread: plain memcpy
- * on the calling thread.  Blocks until the copy is complete. */
+ * destination).  At least 8 MiB per thread (fewer threads for smaller copies);
+ * n_threads <= 1 or less than 16 MiB: plain memcpy on the calling thread.
+ * Blocks until the copy is complete. */
 int oa_host_copy(void* dst, const void* src, size_t bytes, int n_threads);
 
 /* The region table on the HOST (host pointers, no CUDA call): what the Python

@@ -75,7 +75,8 @@ extern "C" size_t oa_synth_params_size(void) { return sizeof(oa_synth_params); }
 // ---- host-side assembly of the region table (see include/orbit_b200.h) -------------
 extern "C" int oa_host_copy(void* dst, const void* src, size_t bytes, int n_threads) {
     OA_REQUIRE(bytes == 0 || (dst && src), "oa_host_copy: null pointer");
-    const size_t min_part = (size_t)1 << 20;
+    // (a thread costs tens of microseconds to start: at least 8 MiB of copy each)
+    const size_t min_part = (size_t)8 << 20;
     size_t parts = n_threads > 1 ? (size_t)n_threads : 1;
     if (parts > 64) parts = 64;
     if (parts > bytes / min_part) parts = bytes / min_part;

@@ -78,8 +78,9 @@ _stage_threads = None
 
 def stage_threads():
     """Threads of a staging copy (``oa_host_copy``): the cores this process may
-    run on, shared between the ranks of the node, at most 16 (a copy is bound by
-    memory bandwidth before that); ``OA_STAGE_THREADS`` overrides."""
+    run on, shared between the ranks of the node, at most 8 (a copy is bound by
+    memory bandwidth before that, and every thread is started per call);
+    ``OA_STAGE_THREADS`` overrides."""
     global _stage_threads
     if _stage_threads is None:
         import os
@@ -91,7 +92,7 @@ def stage_threads():
             local = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
         except ValueError:
             local = 1
-        n = max(1, min(16, cores // local))
+        n = max(1, min(8, cores // local))
         try:
             n = max(1, int(os.environ.get('OA_STAGE_THREADS', n)))
         except ValueError:

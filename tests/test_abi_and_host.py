@@ -291,8 +291,8 @@ def test_pj2_plan_invariants():
         lens = (lens * rng.uniform(0.7, 1.6, n_h)).astype(np.int64)
 
 
-@pytest.mark.parametrize('nbytes', [0, 1, 4095, (1 << 20) - 1, (3 << 20) + 17,
-                                    (16 << 20) + 4097, (40 << 20) + 3])
+@pytest.mark.parametrize('nbytes', [0, 1, 4095, (8 << 20) - 1, (16 << 20) + 17,
+                                    (24 << 20) + 4097, (70 << 20) + 3])
 @pytest.mark.parametrize('threads', [0, 1, 3, 8, 100])
 def test_host_copy_is_a_memcpy(nbytes, threads):
     """``oa_host_copy`` (the staging copy of pageable loader arrays into the
