@@ -324,8 +324,12 @@ class _Writer:
             self._error = exc
 
     def submit(self, fn, *args):
+        import os
         import threading
         self.wait()
+        if os.environ.get('OA_WRITER_THREAD', '1') == '0':
+            fn(*args)                         # (escape hatch: write in line)
+            return
         self._thread = threading.Thread(target=self._run, args=(fn, args),
                                         name='orbit-b200-writer')
         self._thread.start()

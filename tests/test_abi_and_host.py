@@ -330,6 +330,20 @@ def test_stage_copy_paths(monkeypatch):
     monkeypatch.setattr(tracker, '_stage_threads', None)
 
 
+def test_writer_thread_can_be_switched_off(monkeypatch):
+    import threading
+    from nbody_orbit_analysis_b200.track_orbits import _Writer
+    monkeypatch.setenv('OA_WRITER_THREAD', '0')
+    seen = []
+    w = _Writer()
+    w.submit(lambda: seen.append(threading.current_thread() is
+                                 threading.main_thread()))
+    assert seen == [True]
+    with pytest.raises(OSError):
+        w.submit(lambda: (_ for _ in ()).throw(OSError('x')))
+    w.wait()
+
+
 def test_writer_thread_order_and_errors():
     """track_orbits._Writer: writes run one at a time in submission order; an
     exception raised by a write surfaces on the caller's thread at the next
